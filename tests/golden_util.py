@@ -1,0 +1,47 @@
+"""Loaders for the committed fixtures under tests/golden/ (made by oracle/gen_golden.py)."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_stats(name):
+    """-> (stat_names, [(grids[n,*shape], stats[n,K]), ...])"""
+    z = np.load(os.path.join(GOLDEN, f"stats_{name}.npz"))
+    groups = []
+    i = 0
+    while f"grids_{i}" in z:
+        groups.append((z[f"grids_{i}"], z[f"stats_{i}"]))
+        i += 1
+    return [str(s) for s in z["stat_names"]], groups
+
+
+class Trace:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, f"trace_{name}.npz"))
+        self.name = name
+        self.problem = str(z["meta_problem"])
+        self.rep = str(z["meta_rep"])
+        self.map_shape = tuple(int(v) for v in z["meta_map_shape"])
+        self.obs_window = tuple(int(v) for v in z["meta_obs_window"])
+        self.max_board_scans = int(z["meta_max_board_scans"])
+        cp = float(z["meta_change_percentage"])
+        self.change_percentage = None if cp < 0 else cp
+        self.controls = [str(s) for s in z["meta_controls"]] or None
+        self.weights = {str(k): float(v) for k, v in zip(z["meta_weight_keys"], z["meta_weight_vals"])}
+        self.raw_only = bool(z["meta_raw_only"])
+        self.target_names = [str(s) for s in z["meta_targets"]]
+        self.n_envs = int(z["n_envs"])
+        self.envs = []
+        for e in range(self.n_envs):
+            self.envs.append({k: z[f"{k}_{e}"] for k in
+                              ("grid0", "pos0", "stats0", "actions", "rewards", "dones", "stats", "pos", "grids",
+                               "obs", "obs_step", "changes", "trg")})
+
+    def targets(self, e):
+        return {k: float(v) for k, v in zip(self.target_names, self.envs[e]["trg"])}
+
+
+TRACES = ["binary_narrow", "binary_narrow_chg", "binary_turtle", "binary_wide_ctrl", "binary_cellular",
+          "zelda_turtle", "zelda_narrow", "zelda_wide_raw"]

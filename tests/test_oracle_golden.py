@@ -1,0 +1,76 @@
+"""CPU: pin oracle/pcgrl_oracle.py against fixtures produced by the real reference."""
+import numpy as np
+import pytest
+
+from oracle import pcgrl_oracle as O
+from tests.golden_util import TRACES, Trace, load_stats
+
+
+@pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda")])
+def test_stats_match_reference(name, problem):
+    names, groups = load_stats(name)
+    assert names == O.STAT_NAMES[problem]
+    n = 0
+    for grids, stats in groups:
+        for g, want in zip(grids, stats):
+            got = O.stats_vector(problem, O.get_stats(problem, g))
+            assert got == [int(v) for v in want], (g.shape, got, want)
+            n += 1
+    assert n > 100
+
+
+def test_known_answers():
+    # SURVEY.md section C, computed with the reference's helper.py
+    assert O.binary_stats(np.zeros((16, 16), int)) == {"regions": 1, "path-length": 30}
+    assert O.binary_stats(np.ones((16, 16), int)) == {"regions": 0, "path-length": 0}
+    rng = np.random.default_rng(12345)
+    want = [(30, 13), (34, 12), (22, 17)]
+    for r, p in want:
+        g = (rng.random((16, 16)) < 0.5).astype(np.uint8)
+        assert O.binary_stats(g) == {"regions": r, "path-length": p}
+    assert O.range_reward(3, 1, 1, 1) == -2
+    assert O.range_reward(0, 2, 1, 1) == -2
+    assert O.range_reward(130, 120, 125, 125) == -10
+
+
+def replay_oracle(tr: Trace, e: int):
+    d = tr.envs[e]
+    env = O.OracleEnv(tr.problem, tr.rep, tr.map_shape, weights=tr.weights, controls=tr.controls,
+                      max_board_scans=tr.max_board_scans, change_percentage=tr.change_percentage)
+    st0 = env.reset(d["grid0"], pos=d["pos0"], targets=tr.targets(e))
+    assert O.stats_vector(tr.problem, st0) == [int(v) for v in d["stats0"]]
+    n_tiles = len(O.TILES[tr.problem])
+    h, w = tr.obs_window[:2]
+    for t in range(len(d["rewards"])):
+        a = d["actions"][t]
+        if tr.rep == "wide" and not tr.raw_only:
+            a = O.actionmap_unravel(a, h, w, n_tiles)
+        elif tr.rep in ("narrow", "turtle"):
+            a = int(a)
+        r, done, _ = env.step(a)
+        assert done == bool(d["dones"][t]), (tr.name, e, t)
+        assert O.stats_vector(tr.problem, env.stats) == [int(v) for v in d["stats"][t]], (tr.name, e, t)
+        assert np.array_equal(env.grid, d["grids"][t]), (tr.name, e, t)
+        assert env.changes == int(d["changes"][t])
+        assert r == pytest.approx(float(d["rewards"][t]), rel=1e-6, abs=1e-9), (tr.name, e, t)
+        if tr.rep in ("narrow", "turtle"):
+            assert env.pos == [int(v) for v in d["pos"][t]], (tr.name, e, t)
+        if t in d["obs_step"]:
+            want = d["obs"][list(d["obs_step"]).index(t)]
+            if tr.rep in ("narrow", "turtle"):
+                got = O.cropped_onehot(env.grid, env.pos, tr.obs_window, n_tiles)
+            else:
+                got = O.full_onehot(env.grid, n_tiles)
+            if tr.controls:
+                ch = O.target_channels(got.shape[:-1], tr.controls, env.targets, env.stats, env.cond_bounds)
+                got = np.concatenate([ch, got], axis=-1)
+            assert got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+    assert bool(d["dones"][-1]) or tr.name in ("binary_cellular",)
+
+
+@pytest.mark.parametrize("name", TRACES)
+def test_trace_matches_reference(name):
+    tr = Trace(name)
+    for e in range(tr.n_envs):
+        replay_oracle(tr, e)
