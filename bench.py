@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched PCGRL step on B200 (the BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME] [--envs E]
+
+One "step" = one pass of the hot path (pcgrl_step: representation update -> get_stats -> reward) over the
+rank's whole env shard, with random actions, plus the auto-reset launches that episodes ending inside the
+timed region cause.  Prints ONE JSON line on rank 0 (see the task contract):
+  value     whole-job env-steps/s, actions already resident in HBM (device-timed, max over ranks)
+  e2e       same metric through the public host-buffer API (BatchedPcgrlEnv.step_host -> pcgrl_step_host):
+            actions H2D from pinned memory, reward/done/stats D2H, every step, inside the timed region
+  roofline  dominant kernel (k_step_bitboard) vs measured HBM peak: algorithmic bytes/launch / event time
+  cpu_baseline  the oracle (python port of the reference path) timed on this box's host cores (bounded sample)
+`--impl reference` times the reference's CPU implementation of the same path on all host cores: the real
+reference under oracle/refshim.py when /root/reference exists (build container), else the oracle port.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (problem, rep, map_shape, obs_window, controls, default envs/GPU)
+    "binary-narrow-16x16": ("binary", "narrow", (16, 16), (32, 32), None, 1 << 20),
+    "binary-wide-ctrl-16x16": ("binary", "wide", (16, 16), (16, 16), ["regions", "path-length"], 1 << 20),
+    "binary-turtle-16x16": ("binary", "turtle", (16, 16), (32, 32), None, 1 << 20),
+    "zelda-turtle-7x11": ("zelda", "turtle", (7, 11), (22, 22), None, 1 << 20),
+    "zelda-narrow-7x11": ("zelda", "narrow", (7, 11), (22, 22), None, 1 << 20),
+}
+METRIC = "env-steps/sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=800)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="binary-narrow-16x16", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: workload's)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:  # noqa: BLE001
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arms
+def _cpu_worker(args):
+    """profile_env.py-style loop (profile_env.py:121-171): reset; step(random action) until done; repeat."""
+    workload, seconds, seed, use_ref = args
+    problem, rep, shape, obs_window, controls, _ = WORKLOADS[workload]
+    rng = np.random.default_rng(seed)
+    from control_pcgrl_b200.config import TASK_DEFAULTS
+    weights = TASK_DEFAULTS[problem]["weights"]
+    n_tiles = {"binary": 2, "zelda": 8}[problem]
+    n_act = {"narrow": n_tiles, "turtle": 4 + n_tiles, "wide": obs_window[0] * obs_window[1] * n_tiles}[rep]
+    steps = 0
+    if use_ref:
+        from oracle import refshim as R
+        cfg = R.make_cfg(problem, rep, shape, obs_window=obs_window, weights=weights, controls=controls)
+        env = R.make_wrapped_env(cfg)
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < seconds:
+            env.reset()
+            done = False
+            while not done and time.perf_counter() - t0 < seconds:
+                _, _, done, _, _ = env.step(int(rng.integers(n_act)))
+                steps += 1
+        return steps, time.perf_counter() - t0
+    from oracle import pcgrl_oracle as O
+    env = O.OracleEnv(problem, rep, shape, weights=weights, controls=controls)
+    from oracle.pcgrl_oracle import INIT_PROBS
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        p = rng.random(n_tiles)
+        grid = rng.choice(n_tiles, size=shape, p=p / p.sum())
+        env.reset(grid, pos=[int(rng.random() * s) for s in shape])
+        done = False
+        while not done and time.perf_counter() - t0 < seconds:
+            a = int(rng.integers(n_act))
+            if rep == "wide":
+                a = O.actionmap_unravel(a, obs_window[0], obs_window[1], n_tiles)
+            _, done, _ = env.step(a)
+            steps += 1
+    return steps, time.perf_counter() - t0
+
+
+def cpu_arm(workload, seconds, cores, seed=0):
+    """-> (env-steps/s aggregate, kind, cores, sample description)"""
+    from oracle import refshim
+    use_ref = refshim.available()
+    kind = "reference" if use_ref else "port"
+    if cores <= 1:
+        s, dt = _cpu_worker((workload, seconds, seed, use_ref))
+        rate = s / dt
+    else:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(workload, seconds, seed + i, use_ref) for i in range(cores)])
+        rate = sum(s / dt for s, dt in res)
+    what = ("real reference stack under oracle/refshim.py" if use_ref else "oracle/pcgrl_oracle.py (python port)")
+    sample = (f"{what}; profile_env.py-style random-action episodes of {workload}, one env per process, "
+              f"{cores} process(es) x {seconds:.0f}s wall")
+    return rate, kind, cores, sample
+
+
+# ------------------------------------------------------------------------------------------- main
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    problem, rep, shape, obs_window, controls, default_envs = WORKLOADS[a.workload]
+    n_envs = a.envs or default_envs
+    cores_avail = len(os.sched_getaffinity(0))
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        seconds = max(2.0, min(20.0, 0.02 * (a.steps + a.warmup)))
+        rate, kind, cores, sample = cpu_arm(a.workload, seconds, cores_avail, a.seed)
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "int8/int32 stats, f64 reward", "data": "synthetic",
+                "config": {"workload": a.workload, "envs_per_gpu": n_envs},
+                "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import control_pcgrl_b200 as P
+    from control_pcgrl_b200 import _lib
+    from control_pcgrl_b200.dist import init_from_env, reduce_episode_stats
+
+    if world > 1:
+        init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load()
+
+    cfg = P.make_config(problem, rep, map_shape=shape, obs_window=obs_window, controls=controls)
+    env = P.BatchedPcgrlEnv(cfg, n_envs, device=dev, env_offset=rank * n_envs, seed=a.seed, auto_reset=True)
+    if controls:
+        env.sample_uniform_targets()
+    env.reset()
+    n_act = {"narrow": env.n_tiles, "turtle": 4 + env.n_tiles,
+             "wide": obs_window[0] * obs_window[1] * env.n_tiles}[rep]
+    gen = torch.Generator(device=dev).manual_seed(a.seed + rank)
+    POOL = 8   # distinct random action batches, cycled (resident in HBM before the timed region)
+    act_pool = [torch.randint(0, n_act, (n_envs,), generator=gen, device=dev, dtype=torch.int32) for _ in range(POOL)]
+    # ~300 MB scratch to push the working set out of L2 is unnecessary at the default size (grids alone are
+    # 268 MB > 126 MB L2); for small --envs we flush explicitly between steps.
+    grid_bytes = n_envs * env.row_stride
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if grid_bytes < (200 << 20) else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(k, timed):
+        """device-resident arm; returns (sum of per-launch step-kernel ms, total region ms)"""
+        evs = []
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        flush_ms = 0.0
+        t0.record()
+        for i in range(k):
+            if flush is not None:
+                f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+                f0.record(); flush.fill_(i & 0xFF); f1.record()
+                evs.append(("f", f0, f1))
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.pcgrl_step(env._cc, env._st, act_pool[i % POOL].data_ptr(), env._stream()), "pcgrl_step")
+            e1.record()
+            evs.append(("k", e0, e1))
+            env._after_step()     # auto-reset launches (inside the timed region)
+        t1.record()
+        torch.cuda.synchronize()
+        kern = sum(x.elapsed_time(y) for tag, x, y in evs if tag == "k")
+        flush_ms = sum(x.elapsed_time(y) for tag, x, y in evs if tag == "f")
+        return kern, t0.elapsed_time(t1) - flush_ms
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    run_steps(a.warmup, False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.pcgrl_launch_count()
+    kern_ms, region_ms = run_steps(a.steps, True)
+    launches = lib.pcgrl_launch_count() - launches0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([region_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    region_ms, kern_ms = float(t[0]), float(t[1])
+    value = world * n_envs * a.steps / (region_ms * 1e-3)
+
+    # ---- end-to-end arm (host buffers through the public API) -----------------------------------
+    e2e = None
+    if not a.no_e2e:
+        shape_a, dt_a = env.action_shape_dtype()
+        rng = np.random.default_rng(a.seed + 100 + rank)
+        host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(POOL)]
+        k_e2e = max(3, min(a.steps, 200))
+        for i in range(3):
+            env.step_host(host_acts[i % POOL])
+        barrier()
+        w0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sink = 0.0
+        for i in range(k_e2e):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            r, d, s = env.step_host(host_acts[i % POOL])
+            sink += float(r[0])
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        te = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = int(np.prod(shape_a)) * np.dtype(dt_a).itemsize
+        d2h = n_envs * (4 + 1 + 4 * env.K)
+        e2e = {"value": world * n_envs * k_e2e / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e,
+               "api": "BatchedPcgrlEnv.step_host -> pcgrl_step_host (pinned actions H2D; reward,done,stats D2H; sync)"}
+
+    # ---- optional NCCL episode-stat reduction (off the step path; exercised once) ----------------
+    red = reduce_episode_stats(env.stats, names=env.stat_names)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peak, peak_src = peaks()
+    step_bytes = env.step_bytes()
+    per_launch_ms = kern_ms / a.steps
+    achieved = step_bytes * n_envs / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "k_step_bitboard", "algorithmic_bytes_per_env_step": step_bytes,
+                "kernel_ms_per_launch": per_launch_ms, "peak_source": peak_src,
+                "note": "HBM bound is loose for this path; the binding resource is SM issue (see profiles/)"}
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get(a.workload)
+        except Exception:  # noqa: BLE001
+            pass
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        rate, kind, cores, sample = cpu_arm(a.workload, a.cpu_seconds, 1, a.seed)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+               "host_cores_available": cores_avail}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": region_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 grids / int32 stats / f64 reward math", "data": "synthetic",
+            "config": {"workload": a.workload, "envs_per_gpu": n_envs, "global_envs": world * n_envs,
+                       "actions": "uniform random, 8 pre-generated batches resident in HBM",
+                       "episode_steps": int(env.max_iterations) + 1, "auto_reset": True,
+                       "l2": ("inputs larger than L2 (%.0f MB grids)" % (grid_bytes / 1e6)) if flush is None
+                             else "256 MB L2 flush between steps (excluded from the timing)",
+                       "parallelism": f"env-sharded x{world}, no collective on the step path"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "mean_stats": {n: float(v) for n, v in zip(env.stat_names, red["mean"].tolist())}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

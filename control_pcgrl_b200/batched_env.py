@@ -1,0 +1,349 @@
+"""BatchedPcgrlEnv: N PCGRL level grids stepped at once on one B200.
+
+Host-side mirror of the reference's env step for a whole batch:
+  PcgrlEnv.reset/step           control_pcgrl/envs/pcgrl_env.py:158-188, 267-342
+  Representation.update         control_pcgrl/envs/reps/{narrow,turtle,wide,ca}_rep.py
+  Problem.get_stats             control_pcgrl/envs/probs/<game>/*_prob.py
+  ControlWrapper reward/targets control_pcgrl/control_wrappers.py:174-244, 318-345
+  obs wrappers                  control_pcgrl/wrappers.py:140-150, 232-257, 407-437
+
+All state lives in HBM as torch tensors; every method launches the hand-written sm_100a kernels of
+libpcgrl_sm100.so through the C ABI (include/pcgrl_b200.h).  PyTorch is only the allocator / stream
+provider.  No CPU path exists: constructing this class without CUDA raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import normalise
+from .problems import REPRESENTATION_ALIASES, get_spec
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class BatchedPcgrlEnv:
+    def __init__(self, cfg, n_envs: int, device="cuda:0", env_offset: int = 0, seed: int = 0,
+                 action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.PcgrlError("control_pcgrl_b200 needs a CUDA device (there is no CPU fallback)")
+        c = normalise(cfg)
+        self.cfg = cfg
+        self.problem = c.problem
+        self.representation = REPRESENTATION_ALIASES[c.representation]
+        self.map_shape = c.map_shape
+        self.obs_window = c.obs_window
+        self.spec = get_spec(self.problem, self.map_shape)
+        self.n_envs = int(n_envs)
+        self.device = torch.device(device)
+        self.env_offset = int(env_offset)
+        self.seed = int(seed)
+        self.auto_reset = auto_reset
+        self.ndim = len(self.map_shape)
+        self.cells = int(np.prod(self.map_shape))
+        self.row_stride = (self.cells + 15) // 16 * 16
+        self.n_tiles = self.spec.n_tiles
+        self.stat_names = list(self.spec.stat_names)
+        self.K = len(self.stat_names)
+
+        # pcgrl_env.py:235-241
+        self.max_iterations = self.cells * c.max_board_scans + 1
+        self.max_changes = None if c.change_percentage is None else max(int(c.change_percentage * self.cells), 1)
+
+        # ControlWrapper.__init__ (control_wrappers.py:27-121)
+        self.ctrl_metrics = list(c.controls or [])
+        self.static_trgs = OrderedDict(self.spec.static_trgs)
+        self.cond_bounds = dict(self.spec.cond_bounds)
+        self.metric_weights = {k: 0 for k in self.spec.reward_weights}
+        self.metric_weights.update(c.weights)
+        self.all_metrics = list(self.ctrl_metrics) + [k for k in self.static_trgs if k not in self.ctrl_metrics]
+        self.param_ranges = {k: abs(self.cond_bounds[k][1] - self.cond_bounds[k][0]) for k in self.ctrl_metrics}
+
+        rep = self.representation
+        if action_kind is None:
+            action_kind = {"narrow": "int32", "turtle": "int32", "wide": "wide_flat", "cellular": "ca_logits"}[rep]
+        self.action_kind = action_kind
+        ak = {"int32": _lib.ACT_INT32, "wide_coords": _lib.ACT_WIDE_COORDS, "wide_flat": _lib.ACT_WIDE_FLAT,
+              "ca_tiles": _lib.ACT_CA_TILES, "ca_logits": _lib.ACT_CA_LOGITS}[action_kind]
+
+        cc = _lib.Config()
+        cc.abi_version = _lib.PCGRL_ABI_VERSION
+        cc.problem = _lib.PROB_IDS[self.problem]
+        cc.representation = _lib.REP_IDS[rep]
+        cc.action_kind = ak
+        cc.ndim = self.ndim
+        for i in range(3):
+            cc.dims[i] = self.map_shape[i] if i < self.ndim else 1
+        cc.n_tiles = self.n_tiles
+        cc.n_stats = self.K
+        cc.row_stride = self.row_stride
+        cc.max_iterations = int(math.floor(self.max_iterations))
+        cc.max_changes = -1 if self.max_changes is None else int(self.max_changes)
+        # ActionMap takes (h, w) from the observation space == obs_window (wrappers.py:283-287, SURVEY A-7)
+        cc.act_h, cc.act_w = (self.obs_window[0], self.obs_window[1]) if ak == _lib.ACT_WIDE_FLAT else (0, 0)
+        cc.targets_per_env = 1 if self.ctrl_metrics else 0
+        cc.init_random_probs = 1 if random_init_probs else 0
+        for i, pr in enumerate(self.spec.init_probs):
+            cc.init_probs[i] = pr
+        for k, name in enumerate(self.stat_names):
+            cc.weights[k] = float(self.metric_weights.get(name, 0)) if name in self.all_metrics else 0.0
+        _lib.check(self.lib.pcgrl_config_check(cc), "pcgrl_config_check")
+        self._cc = cc
+
+        N, dev = self.n_envs, self.device
+        self.grids = torch.zeros((N, self.row_stride), dtype=torch.int8, device=dev)
+        self.pos = torch.zeros((N, 3), dtype=torch.int32, device=dev)
+        self.n_step = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.iteration = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.changes = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.stats = torch.zeros((N, self.K), dtype=torch.int32, device=dev)
+        self.targets = torch.zeros((N if self.ctrl_metrics else 1, self.K, 2), dtype=torch.float64, device=dev)
+        self.reward = torch.zeros(N, dtype=torch.float32, device=dev)
+        self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.changed = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
+        self.scratch = torch.empty(max(int(nscratch), 0), dtype=torch.uint8, device=dev) if nscratch > 0 else None
+        self._actions_dev = None
+        self._pinned = {}
+        self._epoch = 0
+        self._synced_steps = None     # steps since the last full reset while all envs are in lock-step
+        self.metric_trgs = OrderedDict(self.static_trgs)
+        self._write_targets(self.metric_trgs)
+
+        st = _lib.State()
+        st.n_envs, st.env_offset = N, self.env_offset
+        st.grids, st.pos, st.n_step = _ptr(self.grids), _ptr(self.pos), _ptr(self.n_step)
+        st.iteration, st.changes, st.stats = _ptr(self.iteration), _ptr(self.changes), _ptr(self.stats)
+        st.targets, st.reward, st.done = _ptr(self.targets), _ptr(self.reward), _ptr(self.done)
+        st.changed, st.status, st.scratch = _ptr(self.changed), _ptr(self.status), _ptr(self.scratch)
+        self._st = st
+
+    # ------------------------------------------------------------------ targets
+    def _target_rows(self, trgs):
+        rows = np.full((self.K, 2), np.nan, dtype=np.float64)
+        for k, name in enumerate(self.stat_names):
+            t = trgs.get(name, self.static_trgs.get(name, 0))
+            if isinstance(t, tuple):
+                rows[k] = (float(t[0]), float(t[1]))
+            else:
+                rows[k, 0] = float(t)
+        return rows
+
+    def _write_targets(self, trgs):
+        rows = torch.from_numpy(self._target_rows(trgs)).to(self.device)
+        self.targets[:] = rows.unsqueeze(0)
+
+    def set_trgs(self, trgs: dict, env_ids=None):
+        """ControlWrapper.set_trgs/do_set_trgs (control_wrappers.py:167-172) for all envs or a subset.
+        Values may be scalars / (lo, hi) tuples, or per-env arrays of scalars.  Like the reference, new
+        targets take effect for the reward from the next reset (last_loss is re-based there)."""
+        scalar = {k: v for k, v in trgs.items() if np.ndim(v) == 0 or isinstance(v, tuple)}
+        if env_ids is None:
+            self.metric_trgs.update(scalar)
+        rows = torch.from_numpy(self._target_rows({**self.metric_trgs, **scalar})).to(self.device)
+        if env_ids is None:
+            self.targets[:] = rows.unsqueeze(0)
+        else:
+            if not self.ctrl_metrics:
+                raise ValueError("per-env targets need controls (cfg.controls) so targets are stored per env")
+            self.targets[env_ids] = rows.unsqueeze(0)
+        for k, v in trgs.items():
+            if k in scalar:
+                continue
+            if not self.ctrl_metrics:
+                raise ValueError("per-env targets need controls (cfg.controls)")
+            col = self.stat_names.index(k)
+            vals = torch.as_tensor(np.asarray(v, dtype=np.float64), device=self.device)
+            idx = slice(None) if env_ids is None else env_ids
+            self.targets[idx, col, 0] = vals
+            self.targets[idx, col, 1] = float("nan")
+
+    def sample_uniform_targets(self, generator=None):
+        """The intended UniformNoiseyTargets behaviour (control_wrappers.py:452-458, SURVEY A-25):
+        trg_k ~ U(lo_k, hi_k) per env for every controlled metric."""
+        for k in self.ctrl_metrics:
+            lo, hi = self.cond_bounds[k]
+            u = torch.rand(self.n_envs, dtype=torch.float64, device=self.device, generator=generator)
+            col = self.stat_names.index(k)
+            self.targets[:, col, 0] = u * (hi - lo) + lo
+            self.targets[:, col, 1] = float("nan")
+
+    # ------------------------------------------------------------------ views
+    @property
+    def maps(self):
+        """[N, *map_shape] int8 view of the level grids (PcgrlEnv._rep._map for every env)."""
+        return self.grids[:, :self.cells].view(self.n_envs, *self.map_shape)
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _pack_grids(self, grids):
+        g = torch.as_tensor(np.asarray(grids) if not torch.is_tensor(grids) else grids)
+        g = g.to(device=self.device, dtype=torch.int8).reshape(self.n_envs, self.cells)
+        if self.row_stride == self.cells:
+            return g.contiguous()
+        out = torch.zeros((self.n_envs, self.row_stride), dtype=torch.int8, device=self.device)
+        out[:, :self.cells] = g
+        return out
+
+    # ------------------------------------------------------------------ reset / step
+    def reset(self, grids=None, pos=None, mask=None):
+        """Start episodes (all envs, or those where mask != 0).  grids: [N,*map_shape] initial maps
+        (PcgrlCtrlEnv.set_map semantics) or None for random maps; pos: [N,ndim] start positions."""
+        src = self._pack_grids(grids) if grids is not None else None
+        sp = None
+        if pos is not None:
+            p = torch.as_tensor(np.asarray(pos) if not torch.is_tensor(pos) else pos).to(self.device, torch.int32)
+            sp = torch.zeros((self.n_envs, 3), dtype=torch.int32, device=self.device)
+            sp[:, :self.ndim] = p.reshape(self.n_envs, self.ndim)
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._epoch += 1
+        _lib.check(self.lib.pcgrl_reset(self._cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
+                                        self._stream()), "pcgrl_reset")
+        self._synced_steps = 0 if mask is None else None
+        return self.stats
+
+    def step(self, actions: torch.Tensor):
+        """One env-step for all N envs.  `actions` is a device tensor laid out per `action_kind`.
+        Returns (reward[N] f32, done[N] u8) device tensors (overwritten by the next step)."""
+        a = self._check_actions(actions)
+        _lib.check(self.lib.pcgrl_step(self._cc, self._st, a.data_ptr(), self._stream()), "pcgrl_step")
+        self._after_step()
+        return self.reward, self.done
+
+    def _after_step(self):
+        if self._synced_steps is not None:
+            self._synced_steps += 1
+        if not self.auto_reset:
+            return
+        if self.max_changes is None and self._synced_steps is not None:
+            # every env hits `iteration > max_iterations` on the same step: no device->host sync needed
+            if self._synced_steps > self.max_iterations:
+                self.reset()
+        else:
+            self.reset(mask=self.done)
+
+    def _check_actions(self, actions):
+        if not torch.is_tensor(actions) or actions.device != self.device:
+            raise TypeError("actions must be a tensor on the env's device (use step_host for host arrays)")
+        want = {"int32": ((self.n_envs,), torch.int32), "wide_flat": ((self.n_envs,), torch.int32),
+                "wide_coords": ((self.n_envs, self.ndim + 1), torch.int32),
+                "ca_tiles": ((self.n_envs, self.row_stride), torch.int8),
+                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), torch.float32)}[self.action_kind]
+        if actions.dtype != want[1]:
+            raise TypeError(f"actions dtype {actions.dtype} != {want[1]} for action_kind {self.action_kind}")
+        a = actions.reshape(want[0]) if actions.numel() == int(np.prod(want[0])) else None
+        if a is None:
+            raise ValueError(f"actions shape {tuple(actions.shape)} does not match {want[0]}")
+        return a.contiguous()
+
+    def action_shape_dtype(self):
+        return {"int32": ((self.n_envs,), np.int32), "wide_flat": ((self.n_envs,), np.int32),
+                "wide_coords": ((self.n_envs, self.ndim + 1), np.int32),
+                "ca_tiles": ((self.n_envs, self.row_stride), np.int8),
+                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), np.float32)}[self.action_kind]
+
+    def _pinned_buf(self, name, shape, dtype):
+        b = self._pinned.get(name)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = b
+        return b
+
+    def step_host(self, actions: np.ndarray, want_stats=True):
+        """End-to-end step with HOST buffers (the call timed as `e2e`): actions are copied H2D from pinned
+        memory, the fused kernel runs, reward / done / stats are copied back, and the stream is synchronised.
+        Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats i32[N,K] or None)."""
+        shape, dt = self.action_shape_dtype()
+        tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float32: torch.float32}[dt]
+        a_pin = self._pinned_buf("actions", shape, tdt)
+        a_pin.numpy()[...] = np.asarray(actions, dtype=dt).reshape(shape)
+        if self._actions_dev is None:
+            self._actions_dev = torch.empty(shape, dtype=tdt, device=self.device)
+        r = self._pinned_buf("reward", (self.n_envs,), torch.float32)
+        d = self._pinned_buf("done", (self.n_envs,), torch.uint8)
+        s = self._pinned_buf("stats", (self.n_envs, self.K), torch.int32) if want_stats else None
+        _lib.check(self.lib.pcgrl_step_host(self._cc, self._st, a_pin.data_ptr(), self._actions_dev.data_ptr(),
+                                            a_pin.numel() * a_pin.element_size(), r.data_ptr(), d.data_ptr(),
+                                            _ptr(s), self._stream()), "pcgrl_step_host")
+        self._after_step()
+        return r.numpy(), d.numpy(), (s.numpy() if s is not None else None)
+
+    # ------------------------------------------------------------------ stats / observations
+    def compute_stats(self, grids) -> torch.Tensor:
+        """Problem.get_stats for arbitrary grids [n, *map_shape] (evolution's terminal call)."""
+        g = torch.as_tensor(np.asarray(grids) if not torch.is_tensor(grids) else grids)
+        n = g.shape[0]
+        g = g.to(device=self.device, dtype=torch.int8).reshape(n, self.cells)
+        if self.row_stride != self.cells:
+            buf = torch.zeros((n, self.row_stride), dtype=torch.int8, device=self.device)
+            buf[:, :self.cells] = g
+            g = buf
+        g = g.contiguous()
+        out = torch.empty((n, self.K), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.pcgrl_stats(self._cc, g.data_ptr(), out.data_ptr(), n, _ptr(self.scratch),
+                                        self._stream()), "pcgrl_stats")
+        return out
+
+    def obs_shape(self):
+        crop = self.representation in ("narrow", "turtle")
+        dims = self.obs_window if crop else self.map_shape
+        ch = (self.n_tiles + 1 if crop else self.n_tiles) + 2 * len(self.ctrl_metrics)
+        return (*dims, ch)
+
+    def observe(self, out: torch.Tensor | None = None, dtype=torch.float32):
+        """The wrapped observation of every env: [N, *obs_dims, channels] (channels last), exactly what
+        CroppedImagePCGRLWrapper / ActionMapImagePCGRLWrapper + ControlWrapper return per env."""
+        shape = (self.n_envs, *self.obs_shape())
+        if out is None:
+            out = torch.empty(shape, dtype=dtype, device=self.device)
+        if tuple(out.shape) != shape or not out.is_contiguous():
+            raise ValueError(f"out must be contiguous with shape {shape}")
+        crop = self.representation in ("narrow", "turtle")
+        oa = _lib.ObsArgs()
+        oa.crop = 1 if crop else 0
+        dims = self.obs_window if crop else self.map_shape
+        for i in range(3):
+            oa.obs_dims[i] = dims[i] if i < self.ndim else 1
+        oa.n_ctrl = len(self.ctrl_metrics)
+        for i, k in enumerate(self.ctrl_metrics):
+            oa.ctrl_idx[i] = self.stat_names.index(k)
+            oa.ctrl_range[i] = float(self.param_ranges[k])
+        oa.out_kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}[out.dtype]
+        oa.out = out.data_ptr()
+        _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")
+        return out
+
+    def check_status(self):
+        """Raise if any action so far was out of range (device-side flag; one D2H sync)."""
+        s = int(self.status.item())
+        if s:
+            self.status.zero_()
+            raise ValueError("an action outside the action space reached pcgrl_step (ignored on device)")
+
+    def step_bytes(self) -> int:
+        return int(self.lib.pcgrl_step_bytes(self._cc))
+
+    def stats_dict(self, i: int):
+        row = self.stats[i].tolist()
+        return OrderedDict(zip(self.stat_names, row))
+
+    def state_dict(self):
+        """Everything needed to reconstruct the env state (checkpoint row)."""
+        return {k: getattr(self, k).clone() for k in
+                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets")}
+
+    def load_state_dict(self, sd):
+        for k, v in sd.items():
+            getattr(self, k).copy_(v)
+        self._synced_steps = None

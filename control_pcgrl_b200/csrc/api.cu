@@ -1,0 +1,222 @@
+// extern "C" surface of libpcgrl_sm100.so (see include/pcgrl_b200.h for the contract).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "pcgrl_device.cuh"
+
+namespace pcgrl {
+cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
+cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(PCGRL_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+static int cells_of(const pcgrl_config* c) { return c->dims[0] * c->dims[1] * (c->ndim == 3 ? c->dims[2] : 1); }
+
+static int check(const pcgrl_config* c) {
+    if (!c) return fail(PCGRL_E_ARG, "config is NULL");
+    if (c->abi_version != PCGRL_ABI_VERSION) return fail(PCGRL_E_ARG, "abi_version mismatch");
+    if (c->ndim != 2 && c->ndim != 3) return fail(PCGRL_E_ARG, "ndim must be 2 or 3");
+    for (int i = 0; i < c->ndim; ++i)
+        if (c->dims[i] < 1) return fail(PCGRL_E_ARG, "dims must be >= 1");
+    if (c->n_tiles < 1 || c->n_tiles > PCGRL_MAX_TILES) return fail(PCGRL_E_ARG, "n_tiles out of range");
+    if (c->n_stats < 1 || c->n_stats > PCGRL_MAX_STATS) return fail(PCGRL_E_ARG, "n_stats out of range");
+    if (c->representation < PCGRL_REP_NARROW || c->representation > PCGRL_REP_CELLULAR)
+        return fail(PCGRL_E_ARG, "unknown representation");
+    const int cells = cells_of(c);
+    if (c->row_stride < cells || c->row_stride % 16) return fail(PCGRL_E_ARG, "row_stride must be >= cells and a multiple of 16");
+    static const int k_of[] = {2, 7, 7, 9, 3};
+    if (c->problem < 0 || c->problem > PCGRL_PROB_MINECRAFT_3D_MAZE) return fail(PCGRL_E_ARG, "unknown problem");
+    if (c->n_stats != k_of[c->problem]) return fail(PCGRL_E_ARG, "n_stats does not match the problem");
+    const int r = c->representation, a = c->action_kind;
+    const bool ok = ((r == PCGRL_REP_NARROW || r == PCGRL_REP_TURTLE) && a == PCGRL_ACT_INT32) ||
+                    (r == PCGRL_REP_WIDE && (a == PCGRL_ACT_WIDE_COORDS || a == PCGRL_ACT_WIDE_FLAT)) ||
+                    (r == PCGRL_REP_CELLULAR && (a == PCGRL_ACT_CA_TILES || a == PCGRL_ACT_CA_LOGITS));
+    if (!ok) return fail(PCGRL_E_ARG, "action_kind does not fit the representation");
+    if (a == PCGRL_ACT_WIDE_FLAT && (c->act_h < 1 || c->act_w < 1)) return fail(PCGRL_E_ARG, "act_h/act_w required");
+    return 0;
+}
+
+static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
+    std::memset(&p, 0, sizeof(p));
+    p.rep = c->representation;
+    p.action_kind = c->action_kind;
+    p.ndim = c->ndim;
+    p.d0 = c->dims[0];
+    p.d1 = c->dims[1];
+    p.d2 = c->ndim == 3 ? c->dims[2] : 1;
+    p.cells = cells_of(c);
+    p.row_stride = c->row_stride;
+    p.n_tiles = c->n_tiles;
+    p.n_stats = c->n_stats;
+    p.max_iterations = c->max_iterations;
+    p.max_changes = c->max_changes;
+    p.act_h = c->act_h;
+    p.act_w = c->act_w;
+    p.targets_per_env = c->targets_per_env;
+    p.init_random_probs = c->init_random_probs;
+    double tot = 0;
+    for (int t = 0; t < c->n_tiles; ++t) tot += c->init_probs[t] > 0 ? c->init_probs[t] : 0;
+    double run = 0;
+    for (int t = 0; t < c->n_tiles; ++t) {
+        run += (c->init_probs[t] > 0 ? c->init_probs[t] : 0) / (tot > 0 ? tot : 1);
+        p.init_cdf[t] = (float)run;
+    }
+    for (int k = 0; k < PCGRL_MAX_STATS; ++k) p.weights[k] = c->weights[k];
+    if (st) {
+        p.n_envs = st->n_envs;
+        p.env_offset = st->env_offset;
+        p.grids = st->grids;
+        p.pos = st->pos;
+        p.n_step = st->n_step;
+        p.iteration = st->iteration;
+        p.changes = st->changes;
+        p.stats = st->stats;
+        p.targets = st->targets;
+        p.reward = st->reward;
+        p.done = st->done;
+        p.changed = st->changed;
+        p.status = st->status;
+        p.scratch = st->scratch;
+    }
+}
+
+static int check_state(const pcgrl_state* st) {
+    if (!st) return fail(PCGRL_E_ARG, "state is NULL");
+    if (st->n_envs < 0) return fail(PCGRL_E_ARG, "n_envs < 0");
+    if (!st->grids || !st->pos || !st->n_step || !st->iteration || !st->changes || !st->stats || !st->targets ||
+        !st->reward || !st->done)
+        return fail(PCGRL_E_ARG, "a required state pointer is NULL");
+    return 0;
+}
+
+static int run(const KParams& p, int problem, void* stream) {
+    bool supported = false;
+    cudaError_t e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
+    if (!supported) return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet");
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+}  // namespace pcgrl
+
+using namespace pcgrl;
+
+extern "C" {
+
+int32_t pcgrl_abi_version(void) { return PCGRL_ABI_VERSION; }
+const char* pcgrl_last_error(void) { return g_err.c_str(); }
+int64_t pcgrl_launch_count(void) { return g_launches.load(); }
+
+int32_t pcgrl_config_check(pcgrl_config* cfg) {
+    if (!cfg) return fail(PCGRL_E_ARG, "config is NULL");
+    if (cfg->row_stride == 0 && (cfg->ndim == 2 || cfg->ndim == 3)) cfg->row_stride = (cells_of(cfg) + 15) / 16 * 16;
+    return check(cfg);
+}
+
+int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
+    if (check(cfg)) return -1;
+    (void)n_envs;
+    return 0;  // the bit-board problems keep all search state in registers / shared memory
+}
+
+int64_t pcgrl_step_bytes(const pcgrl_config* c) {
+    if (check(c)) return -1;
+    const int64_t G = cells_of(c), K = c->n_stats;
+    int64_t A = 4;
+    if (c->action_kind == PCGRL_ACT_WIDE_COORDS) A = 4 * (c->ndim + 1);
+    if (c->action_kind == PCGRL_ACT_CA_TILES) A = G;
+    if (c->action_kind == PCGRL_ACT_CA_LOGITS) A = 4 * (int64_t)c->n_tiles * G;
+    return 2 * G + A + 8 * K + 5 + (c->targets_per_env ? 16 * K : 0);
+}
+
+int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream) {
+    int r = check(cfg);
+    if (r) return r;
+    if ((r = check_state(st))) return r;
+    if (!actions) return fail(PCGRL_E_ARG, "actions is NULL");
+    KParams p;
+    fill(p, cfg, st);
+    p.mode = MODE_STEP;
+    p.actions = actions;
+    return run(p, cfg->problem, stream);
+}
+
+int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_t* mask, const int8_t* src_grids,
+                    const int32_t* src_pos, uint64_t seed, uint64_t epoch, void* stream) {
+    int r = check(cfg);
+    if (r) return r;
+    if ((r = check_state(st))) return r;
+    KParams p;
+    fill(p, cfg, st);
+    p.mode = MODE_RESET;
+    p.mask = mask;
+    p.src_grids = src_grids;
+    p.src_pos = src_pos;
+    p.seed = seed;
+    p.epoch = epoch;
+    return run(p, cfg->problem, stream);
+}
+
+int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats, int64_t n, void* scratch,
+                    void* stream) {
+    int r = check(cfg);
+    if (r) return r;
+    if (!grids || !stats || n < 0) return fail(PCGRL_E_ARG, "bad grids/stats/n");
+    KParams p;
+    fill(p, cfg, nullptr);
+    p.mode = MODE_STATS;
+    p.n_envs = n;
+    p.stats_grids = grids;
+    p.stats_out = stats;
+    p.scratch = scratch;
+    return run(p, cfg->problem, stream);
+}
+
+int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgrl_obs_args* obs, void* stream) {
+    int r = check(cfg);
+    if (r) return r;
+    if (!st || !st->grids || !st->pos || !obs || !obs->out) return fail(PCGRL_E_ARG, "bad observe arguments");
+    if (obs->n_ctrl < 0 || obs->n_ctrl > PCGRL_MAX_STATS) return fail(PCGRL_E_ARG, "n_ctrl out of range");
+    if (obs->n_ctrl > 0 && (!st->stats || !st->targets)) return fail(PCGRL_E_ARG, "control channels need stats/targets");
+    cudaError_t e = launch_observe(*cfg, *st, *obs, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "observe launch");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host, void* actions_dev,
+                        int64_t action_bytes, float* reward_host, uint8_t* done_host, int32_t* stats_host,
+                        void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (actions_host) {
+        if (!actions_dev || action_bytes < 0) return fail(PCGRL_E_ARG, "actions_dev / action_bytes");
+        if ((e = cudaMemcpyAsync(actions_dev, actions_host, (size_t)action_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return cuda_fail(e, "H2D actions");
+    }
+    int r = pcgrl_step(cfg, st, actions_dev, stream);
+    if (r) return r;
+    const size_t n = (size_t)st->n_envs;
+    if (reward_host && (e = cudaMemcpyAsync(reward_host, st->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(e, "D2H reward");
+    if (done_host && (e = cudaMemcpyAsync(done_host, st->done, n, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(e, "D2H done");
+    if (stats_host && (e = cudaMemcpyAsync(stats_host, st->stats, n * cfg->n_stats * sizeof(int32_t), cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+        return cuda_fail(e, "D2H stats");
+    if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(e, "stream sync");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,595 @@
+// Fused batched env-step kernel for the bit-board problems (maps up to 32x32):
+//   representation update -> get_stats -> ControlWrapper reward, one launch for the whole env shard.
+//
+// Reference path replaced (paths relative to /root/reference/control_pcgrl/):
+//   envs/pcgrl_env.py:267-342 (step), envs/reps/{narrow,turtle,wide,ca}_rep.py (update),
+//   envs/probs/binary/binary_prob.py:152-158, envs/probs/zelda/zelda_ctrl_prob.py:90-168 (get_stats),
+//   envs/helper.py:200-276 (calc_num_regions, run_dijkstra, calc_longest_path),
+//   control_wrappers.py:216-244,318-345 (reward = loss - last_loss).
+//
+// Work decomposition per CTA (TILE consecutive envs):
+//   A  thread-per-env: apply the action to the int8 grid in HBM (single-byte scatter, or whole-map rewrite
+//      for the cellular rep), advance counters, decide done, flag envs whose map changed;
+//   B  all threads: 128-bit coalesced loads of the changed grids, packed into per-plane bit-boards in
+//      shared memory (one bit per cell; a "plane" is a set of tile codes);
+//   C  sub-warp groups (G lanes, one 32-bit board word per lane) pull changed envs from a shared-memory
+//      queue and run the stat searches as level-synchronous bit-board BFS: shifts inside a lane for x+-1,
+//      lane shuffles for y+-1, warp ballots for the frontier-empty test;
+//   D  thread-per-env: fp64 loss(new stats) - loss(old stats), write stats / reward / done / counters.
+#include "pcgrl_device.cuh"
+
+namespace pcgrl {
+
+constexpr int THREADS = 128;
+// envs per CTA, bounded so the shared-memory bit-boards stay under the 48 KB static limit
+__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64); }
+
+// ------------------------------------------------------------------------------------------------
+// Problem policies: planes (tile-code sets packed to bit-boards) + the per-group stats state machine.
+// Each machine is a flat loop: one board expansion per iteration for every group of the warp, with
+// rare, group-uniform transitions -- so the 32/G grids that share a warp stay converged.
+// ------------------------------------------------------------------------------------------------
+struct BinaryProb {
+    static constexpr int P = 1;
+    static constexpr int K = 2;  // regions, path-length
+    __device__ static constexpr uint32_t plane_mask(int p) { return 0x1u; }  // {empty}
+};
+
+struct ZeldaProb {
+    static constexpr int P = 5;
+    static constexpr int K = 7;  // player key door enemies regions nearest-enemy path-length
+    // tiles: empty 0, solid 1, player 2, key 3, door 4, bat 5, scorpion 6, spider 7 (zelda_prob.py:20)
+    __device__ static constexpr uint32_t plane_mask(int p) {
+        return p == 0 ? 0xEDu   /* walkable {0,2,3,5,6,7}  zelda_ctrl_prob.py:101-104 */
+             : p == 1 ? 0x04u   /* player */
+             : p == 2 ? 0x08u   /* key */
+             : p == 3 ? 0x10u   /* door */
+             :          0xE0u;  /* enemies {5,6,7} */
+    }
+};
+
+// binary: regions + double-sweep longest path over the {empty} plane.
+//   helper.calc_longest_path runs, per component, BFS(first tile) -> far tile -> BFS(far) and keeps the max.
+//   Exact restatement used here: (1) isolated cells are components with eccentricity 0: count them with a
+//   popcount; (2) for the other components run the first sweep one component at a time (start = lowest
+//   remaining cell, far = lowest cell of the last non-empty level == np.argmax); (3) the second sweeps of
+//   all components run at once as a single multi-source BFS from the set of far tiles -- components are
+//   disconnected, so the number of levels until the joint frontier dies is max_c ecc(far_c).
+template <int G, bool TWO>
+struct BinaryMachine {
+    using Prob = BinaryProb;
+    uint32_t avail, front, base, fars;
+    int phase, level, ncomp;
+
+    __device__ __forceinline__ void init(const Group<G, TWO>& g, const uint32_t* bb /* [P][G] */) {
+        const uint32_t pass = bb[g.lig];
+        const uint32_t iso = pass & ~g.expand(pass);
+        ncomp = __popc(iso);          // per-lane partial; reduced over the group at the end
+        base = pass & ~iso;
+        avail = base;
+        front = 0;
+        fars = 0;
+        phase = 0;
+        level = 0;
+    }
+    // returns true when the item is finished (out[] then holds the K stats, valid in every lane)
+    __device__ __forceinline__ bool advance(const Group<G, TWO>& g, int* out) {
+        const uint32_t n = g.expand(front) & avail;
+        if (g.any(n)) {
+            avail ^= n;
+            front = n;
+            ++level;
+            return false;
+        }
+        if (phase == 0) {
+            bool found;
+            fars |= g.lowest(front, found);          // far tile of the component just swept (none on entry)
+            const uint32_t s = g.lowest(avail, found);
+            if (found) {                              // next component, first sweep
+                front = s;
+                avail ^= s;
+                if (s) ++ncomp;
+                return false;
+            }
+            phase = 1;                                // joint second sweep
+            front = fars;
+            avail = base & ~fars;
+            level = 0;
+            if (g.any(fars)) return false;
+        }
+        out[0] = g.sum(ncomp);
+        out[1] = level;
+        return true;
+    }
+};
+
+// zelda: tile counts, regions over the walkable plane, then (player == 1) BFS from the player:
+// nearest-enemy = first level >= 1 that touches an enemy, d(player->key) = level that touches the key;
+// then (key == 1 && door == 1) BFS from the key over walkable+door: d(key->door).  Unreached = -1 each
+// (run_dijkstra's fill value), added raw (zelda_ctrl_prob.py:134-150).
+template <int G, bool TWO>
+struct ZeldaMachine {
+    using Prob = ZeldaProb;
+    uint32_t avail, front, walk, player, key, door, enemy;
+    int phase, level, regions, near, dkey, ddoor;
+    int n_player, n_key, n_door, n_enemy;
+
+    __device__ __forceinline__ void init(const Group<G, TWO>& g, const uint32_t* bb) {
+        walk = bb[0 * G + g.lig];
+        player = bb[1 * G + g.lig];
+        key = bb[2 * G + g.lig];
+        door = bb[3 * G + g.lig];
+        enemy = bb[4 * G + g.lig];
+        n_player = g.sum(__popc(player));
+        n_key = g.sum(__popc(key));
+        n_door = g.sum(__popc(door));
+        n_enemy = g.sum(__popc(enemy));
+        const uint32_t iso = walk & ~g.expand(walk);
+        regions = __popc(iso);
+        avail = walk & ~iso;
+        front = 0;
+        phase = 0;
+        level = 0;
+        near = 0;
+        dkey = -1;
+        ddoor = -1;
+    }
+    __device__ __forceinline__ bool advance(const Group<G, TWO>& g, int* out) {
+        const uint32_t n = g.expand(front) & avail;
+        if (g.any(n)) {
+            avail ^= n;
+            front = n;
+            ++level;
+            if (phase == 1) {
+                if (near == 0 && g.any(n & enemy)) near = level;
+                if (g.any(n & key)) dkey = level;
+            } else if (phase == 2) {
+                if (g.any(n & door)) ddoor = level;
+            }
+            return false;
+        }
+        bool found;
+        if (phase == 0) {  // region flood fill, one component at a time
+            const uint32_t s = g.lowest(avail, found);
+            if (found) {
+                front = s;
+                avail ^= s;
+                if (s) ++regions;
+                return false;
+            }
+            regions = g.sum(regions);
+            if (n_player == 1 && (n_enemy > 0 || (n_key == 1 && n_door == 1))) {
+                phase = 1;
+                front = player;
+                avail = walk & ~player;
+                level = 0;
+                return false;
+            }
+            phase = 3;
+        } else if (phase == 1) {
+            if (n_key == 1 && n_door == 1) {
+                phase = 2;
+                front = key;
+                avail = (walk | door) & ~key;
+                level = 0;
+                return false;
+            }
+            phase = 3;
+        }
+        out[0] = n_player;
+        out[1] = n_key;
+        out[2] = n_door;
+        out[3] = n_enemy;
+        out[4] = regions;
+        out[5] = near;
+        out[6] = (n_player == 1 && n_key == 1 && n_door == 1) ? dkey + ddoor : 0;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// phase A helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cell_index(const KParams& p, int a0, int a1, int a2) {
+    return (a0 * p.d1 + a1) * p.d2 + a2;
+}
+
+// Apply one non-cellular action to env `gid`.  Returns change (0/1); updates pos / n_step in HBM.
+__device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
+    int8_t* grid = p.grids + gid * p.row_stride;
+    int32_t* pos = p.pos + gid * 3;
+    int change = 0;
+    if (p.rep == PCGRL_REP_NARROW) {
+        // reps/narrow_rep.py:89-102: write at _pos, then _pos = coords[n_step % N], then n_step += 1
+        const int a = ((const int32_t*)p.actions)[gid];
+        const int c = cell_index(p, pos[0], pos[1], pos[2]);
+        if ((unsigned)a >= (unsigned)p.n_tiles) {
+            if (p.status) atomicOr(p.status, 1);
+        } else {
+            const int old = grid[c];
+            change = old != a;
+            if (change) grid[c] = (int8_t)a;
+        }
+        const int ns = p.n_step[gid];
+        const int k = ns % p.cells;
+        pos[2] = k % p.d2;
+        pos[1] = (k / p.d2) % p.d1;
+        pos[0] = k / (p.d2 * p.d1);
+        p.n_step[gid] = ns + 1;
+    } else if (p.rep == PCGRL_REP_TURTLE) {
+        // reps/turtle_rep.py:87-107: 0..3 move along axis 0 / axis 1 (clamped), >= 4 writes tile a-4
+        const int a = ((const int32_t*)p.actions)[gid];
+        if (a >= 0 && a < 4) {
+            const int axis = a >> 1;
+            const int lim = (axis == 0 ? p.d0 : p.d1) - 1;
+            int v = pos[axis] + ((a & 1) ? 1 : -1);
+            pos[axis] = v < 0 ? 0 : (v > lim ? lim : v);
+        } else if (a >= 4 && a - 4 < p.n_tiles) {
+            const int c = cell_index(p, pos[0], pos[1], pos[2]);
+            const int t = a - 4;
+            const int old = grid[c];
+            change = old != t;
+            if (change) grid[c] = (int8_t)t;
+        } else if (p.status) {
+            atomicOr(p.status, 1);
+        }
+    } else {  // PCGRL_REP_WIDE
+        int q0, q1, q2 = 0, v;
+        if (p.action_kind == PCGRL_ACT_WIDE_FLAT) {
+            // wrappers.py:304-323: (y, x, v) = unravel(a, (h, w, C)); env.step([x, y, v]) -> _map[x, y] = v
+            const int a = ((const int32_t*)p.actions)[gid];
+            v = a % p.n_tiles;
+            const int x = (a / p.n_tiles) % p.act_w;
+            const int y = a / (p.n_tiles * p.act_w);
+            q0 = x;
+            q1 = y;
+            if (a < 0 || y >= p.act_h) q0 = -1;
+        } else {
+            const int32_t* a = (const int32_t*)p.actions + gid * (p.ndim + 1);
+            q0 = a[0];
+            q1 = a[1];
+            if (p.ndim == 3) q2 = a[2];
+            v = a[p.ndim];
+        }
+        if ((unsigned)q0 >= (unsigned)p.d0 || (unsigned)q1 >= (unsigned)p.d1 || (unsigned)q2 >= (unsigned)p.d2 ||
+            (unsigned)v >= (unsigned)p.n_tiles) {
+            if (p.status) atomicOr(p.status, 1);
+        } else {
+            const int c = cell_index(p, q0, q1, q2);
+            const int old = grid[c];
+            change = old != v;
+            if (change) grid[c] = (int8_t)v;
+            pos[0] = q0;
+            pos[1] = q1;
+            pos[2] = q2;
+        }
+    }
+    return change;
+}
+
+// Episode start for env `gid` (thread-per-env): grid from src or Philox, counters, start position.
+__device__ void reset_env(const KParams& p, int64_t gid) {
+    int8_t* grid = p.grids + gid * p.row_stride;
+    const uint64_t genv = (uint64_t)(p.env_offset + gid);
+    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
+    if (p.src_grids) {
+        const uint4* s = (const uint4*)(p.src_grids + gid * p.row_stride);
+        uint4* d = (uint4*)grid;
+        for (int i = 0; i < p.row_stride / 16; ++i) d[i] = s[i];
+    } else {
+        float cdf[PCGRL_MAX_TILES];
+        if (p.init_random_probs) {
+            // pcgrl_env.py:162-164 + helper.get_int_prob: per-episode tile probabilities U(0,1)^C, normalised
+            float tot = 0.f;
+            for (int t0 = 0; t0 < p.n_tiles; t0 += 4) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
+                                                         0x80000000u + t0), key);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                for (int j = 0; j < 4 && t0 + j < p.n_tiles; ++j) {
+                    tot += u01(rr[j]) + 1e-7f;
+                    cdf[t0 + j] = tot;
+                }
+            }
+            for (int t = 0; t < p.n_tiles; ++t) cdf[t] /= tot;
+        } else {
+            for (int t = 0; t < p.n_tiles; ++t) cdf[t] = p.init_cdf[t];
+        }
+        for (int c0 = 0; c0 < p.row_stride; c0 += 16) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            for (int q = 0; q < 4; ++q) {
+                const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
+                                                         (uint32_t)(c0 / 4 + q)), key);
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                for (int j = 0; j < 4; ++j) {
+                    const int c = c0 + q * 4 + j;
+                    int t = 0;
+                    if (c < p.cells) {
+                        const float u = u01(rr[j]);
+                        while (t < p.n_tiles - 1 && u >= cdf[t]) ++t;
+                    }
+                    w[q] |= (uint32_t)t << (8 * j);
+                }
+            }
+            *(uint4*)(grid + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    int32_t* pos = p.pos + gid * 3;
+    pos[0] = pos[1] = pos[2] = 0;
+    if (p.src_pos) {
+        pos[0] = p.src_pos[gid * 3 + 0];
+        pos[1] = p.src_pos[gid * 3 + 1];
+        pos[2] = p.src_pos[gid * 3 + 2];
+    } else if (p.rep == PCGRL_REP_TURTLE) {
+        // reps/turtle_rep.py:41-44: int(random() * dim) per axis
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch, 0xC0000000u), key);
+        pos[0] = min((int)(u01(r.x) * p.d0), p.d0 - 1);
+        pos[1] = min((int)(u01(r.y) * p.d1), p.d1 - 1);
+        if (p.ndim == 3) pos[2] = min((int)(u01(r.z) * p.d2), p.d2 - 1);
+    }
+    p.n_step[gid] = 0;
+    p.iteration[gid] = 0;
+    p.changes[gid] = 0;
+    // reward / done are step outputs: an auto-reset must not erase the finishing step's values
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <class Machine, int G, bool TWO>
+__global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
+    using Prob = typename Machine::Prob;
+    constexpr int P = Prob::P;
+    constexpr int K = Prob::K;
+    constexpr int BBW = P * G;  // board words per env
+    constexpr int TILE = tile_for(BBW);
+
+    __shared__ uint32_t s_bb[TILE * BBW];
+    __shared__ int32_t s_stats[TILE * K];
+    __shared__ int16_t s_list[TILE];   // compact list of tile-local env indices that need stats
+    __shared__ int16_t s_slot[TILE];   // env -> position in s_list, or -1
+    __shared__ uint8_t s_flag[TILE];   // cellular: map changed
+    __shared__ int s_count, s_next;
+
+    const int tid = threadIdx.x;
+    const int64_t base = (int64_t)blockIdx.x * TILE;
+    const int64_t n_total = p.n_envs;
+    const int tile_n = (int)min((int64_t)TILE, n_total - base);
+    const int8_t* grids_in = (p.mode == MODE_STATS) ? p.stats_grids : p.grids;
+
+    if (tid == 0) {
+        s_count = 0;
+        s_next = 0;
+    }
+    for (int e = tid; e < TILE; e += THREADS) {
+        s_slot[e] = -1;
+        s_flag[e] = 0;
+    }
+    __syncthreads();
+
+    // ---------------- cellular: whole-map rewrite, cooperative over the CTA -----------------------
+    if (p.mode == MODE_STEP && p.rep == PCGRL_REP_CELLULAR) {
+        if (p.action_kind == PCGRL_ACT_CA_TILES) {
+            const int chunks = p.row_stride / 16;
+            for (int i = tid; i < tile_n * chunks; i += THREADS) {
+                const int e = i / chunks, c = i - e * chunks;
+                const int64_t off = (base + e) * p.row_stride + c * 16;
+                const uint4 nw = *(const uint4*)((const int8_t*)p.actions + off);
+                uint4* dst = (uint4*)(p.grids + off);
+                const uint4 od = *dst;
+                if (nw.x != od.x || nw.y != od.y || nw.z != od.z || nw.w != od.w) {
+                    *dst = nw;
+                    s_flag[e] = 1;
+                }
+            }
+        } else {  // PCGRL_ACT_CA_LOGITS: float32 [N, C, cells]; argmax over C, ties -> lowest index
+            for (int i = tid; i < tile_n * p.cells; i += THREADS) {
+                const int e = i / p.cells, c = i - e * p.cells;
+                const float* lg = (const float*)p.actions + (base + e) * (int64_t)p.n_tiles * p.cells + c;
+                float best = lg[0];
+                int bi = 0;
+                for (int t = 1; t < p.n_tiles; ++t) {
+                    const float v = lg[(int64_t)t * p.cells];
+                    if (v > best) {
+                        best = v;
+                        bi = t;
+                    }
+                }
+                int8_t* g = p.grids + (base + e) * p.row_stride + c;
+                if (*g != bi) {
+                    *g = (int8_t)bi;
+                    s_flag[e] = 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase A: per-env action / reset, counters, change flag -----------------------
+    for (int e = tid; e < TILE; e += THREADS) {
+        bool need = false;
+        if (e < tile_n) {
+            const int64_t gid = base + e;
+            if (p.mode == MODE_STEP) {
+                int change = (p.rep == PCGRL_REP_CELLULAR) ? (int)s_flag[e] : apply_action(p, gid);
+                const int it = p.iteration[gid] + 1;   // pcgrl_env.py:279
+                const int ch = p.changes[gid] + change;
+                p.iteration[gid] = it;
+                if (change) p.changes[gid] = ch;
+                bool done = it > p.max_iterations;     // :307
+                if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
+                p.done[gid] = done;
+                if (p.changed) p.changed[gid] = change != 0;
+                need = change != 0;                    // :314 stats only when the map changed
+                if (!need) p.reward[gid] = 0.f;
+            } else if (p.mode == MODE_RESET) {
+                need = p.mask == nullptr || p.mask[gid] != 0;
+                if (need) reset_env(p, gid);
+            } else {
+                need = true;
+            }
+        }
+        // warp-aggregated append to the compact work list
+        const unsigned bal = __ballot_sync(0xffffffffu, need);
+        if (bal) {
+            const int lane = tid & 31;
+            int off = 0;
+            if (lane == 0) off = atomicAdd(&s_count, __popc(bal));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (need) {
+                const int slot = off + __popc(bal & ((1u << lane) - 1u));
+                s_list[slot] = (int16_t)e;
+                s_slot[e] = (int16_t)slot;
+            }
+        }
+    }
+    __syncthreads();
+    const int M = s_count;
+
+    // ---------------- phase B: coalesced 128-bit grid loads -> per-plane bit-boards in smem --------
+    for (int i = tid; i < M * BBW; i += THREADS) s_bb[i] = 0;
+    __syncthreads();
+    {
+        const int chunks = p.row_stride / 16;
+        const int W = (p.ndim == 2) ? p.d1 : p.d2;
+        for (int i = tid; i < M * chunks; i += THREADS) {
+            const int slot = i / chunks, c = i - slot * chunks;
+            const int e = s_list[slot];
+            const uint4 v = *(const uint4*)(grids_in + (base + e) * p.row_stride + c * 16);
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            int cell = c * 16;
+            int y = cell / W, x = cell - y * W;
+            uint32_t acc[P];
+#pragma unroll
+            for (int q = 0; q < P; ++q) acc[q] = 0;
+            int cur = TWO ? (y >> 1) : y;
+            uint32_t* bb = s_bb + slot * BBW;
+#pragma unroll
+            for (int b = 0; b < 16; ++b, ++cell) {
+                if (cell < p.cells) {
+                    const int l = TWO ? (y >> 1) : y;
+                    if (l != cur) {
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            if (acc[q]) atomicOr(&bb[q * G + cur], acc[q]);
+                            acc[q] = 0;
+                        }
+                        cur = l;
+                    }
+                    const uint32_t t = (w4[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
+                    const int bit = TWO ? ((y & 1) * 16 + x) : x;
+#pragma unroll
+                    for (int q = 0; q < P; ++q) acc[q] |= ((Prob::plane_mask(q) >> t) & 1u) << bit;
+                    if (++x == W) {
+                        x = 0;
+                        ++y;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+                if (acc[q]) atomicOr(&bb[q * G + cur], acc[q]);
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase C: group-per-grid stat searches, dynamic queue --------------------------
+    {
+        const int W = (p.ndim == 2) ? p.d1 : p.d2;
+        Group<G, TWO> g(W);
+        Machine m;
+        int item = -1;
+        bool active = true;
+        auto fetch = [&]() {
+            int it = 0;
+            if (g.lig == 0) it = atomicAdd(&s_next, 1);
+            it = __shfl_sync(g.gmask, it, g.gbase);
+            item = it;
+            active = it < M;
+            if (active) m.init(g, s_bb + it * BBW);
+        };
+        fetch();
+        while (__any_sync(0xffffffffu, active)) {
+            if (active) {
+                int out[K];
+                if (m.advance(g, out)) {
+                    if (g.lig == 0) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                    }
+                    fetch();
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase D: reward (fp64), stats / outputs --------------------------------------
+    for (int e = tid; e < tile_n; e += THREADS) {
+        const int slot = s_slot[e];
+        if (slot < 0) continue;
+        const int64_t gid = base + e;
+        int32_t nw[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) nw[k] = s_stats[slot * K + k];
+        if (p.mode == MODE_STATS) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) p.stats_out[gid * K + k] = nw[k];
+            continue;
+        }
+        int32_t* st = p.stats + gid * K;
+        if (p.mode == MODE_STEP) {
+            int32_t od[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) od[k] = st[k];
+            const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
+            const double r = control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
+            p.reward[gid] = (float)r;
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) st[k] = nw[k];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side dispatch
+// ------------------------------------------------------------------------------------------------
+template <class Machine, int G, bool TWO>
+static cudaError_t launch(const KParams& p, cudaStream_t s) {
+    constexpr int TILE = tile_for(Machine::Prob::P * G);
+    const int64_t ctas = (p.n_envs + TILE - 1) / TILE;
+    if (ctas == 0) return cudaSuccess;
+    k_step_bitboard<Machine, G, TWO><<<(unsigned)ctas, THREADS, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <template <int, bool> class Machine>
+static cudaError_t dispatch_shape(const KParams& p, cudaStream_t s, bool& supported) {
+    const int H = (p.ndim == 2) ? p.d0 : -1, W = p.d1;
+    supported = true;
+    if (p.ndim != 2) {
+        supported = false;
+        return cudaSuccess;
+    }
+    if (W <= 16 && H <= 16) {
+        const int nw = (H + 1) / 2;
+        if (nw <= 1) return launch<Machine<1, true>, 1, true>(p, s);
+        if (nw <= 2) return launch<Machine<2, true>, 2, true>(p, s);
+        if (nw <= 4) return launch<Machine<4, true>, 4, true>(p, s);
+        return launch<Machine<8, true>, 8, true>(p, s);
+    }
+    if (W <= 32 && H <= 32) {
+        if (H <= 16) return launch<Machine<16, false>, 16, false>(p, s);
+        return launch<Machine<32, false>, 32, false>(p, s);
+    }
+    supported = false;
+    return cudaSuccess;
+}
+
+cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported) {
+    if (problem == PCGRL_PROB_BINARY) return dispatch_shape<BinaryMachine>(p, s, supported);
+    if (problem == PCGRL_PROB_ZELDA) return dispatch_shape<ZeldaMachine>(p, s, supported);
+    supported = false;
+    return cudaSuccess;
+}
+
+}  // namespace pcgrl

@@ -1,0 +1,157 @@
+/*
+ * pcgrl_b200.h -- C ABI of libpcgrl_sm100.so: the batched, B200-native PCGRL environment step.
+ *
+ * This is the drop-in boundary for ONE hot path of smearle/control-pcgrl: env.step() for thousands of
+ * level grids at once (representation update -> problem get_stats -> ControlWrapper reward).
+ * The reference has no native layer (it is 100 % Python), so there is no existing FFI to mirror;
+ * each entry point below names the reference Python interface it replaces (paths relative to
+ * /root/reference/control_pcgrl/).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every pointer in the *_args structs is a DEVICE pointer owned by the caller
+ *     (PyTorch tensors in the Python host), except where a field says "host".
+ *   - launches are asynchronous on the `stream` argument (a cudaStream_t passed as void*).
+ *   - the library keeps no global state except a thread-local last-error string; it allocates no
+ *     device memory: callers size scratch with pcgrl_scratch_bytes() and pass it in.
+ *   - return value: 0 = ok, negative = error (PCGRL_E_*); pcgrl_last_error() gives the message.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device every launch
+ *     entry point returns PCGRL_E_CUDA.
+ */
+#ifndef PCGRL_B200_H
+#define PCGRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGRL_ABI_VERSION 1
+
+/* problems: envs/probs/__init__.py:31-58 (the five BASELINE.json names) */
+enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_SMB = 3,
+       PCGRL_PROB_MINECRAFT_3D_MAZE = 4 };
+/* representations: envs/reps/__init__.py:11-23 */
+enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP_CELLULAR = 3 };
+/* action encodings */
+enum {
+    PCGRL_ACT_INT32 = 0,       /* narrow/turtle: int32[N]  (Discrete, reps/narrow_rep.py:65, turtle_rep.py:70) */
+    PCGRL_ACT_WIDE_COORDS = 1, /* wide: int32[N, ndim+1] = [*coords, tile]  (reps/wide_rep.py:23-24,35-40)   */
+    PCGRL_ACT_WIDE_FLAT = 2,   /* wide: int32[N] flat ActionMap index over (act_h, act_w, C); writes _map[x, y]
+                                  (wrappers.py:304-323)                                                      */
+    PCGRL_ACT_CA_TILES = 3,    /* cellular: int8[N, row_stride] already-argmaxed next map                    */
+    PCGRL_ACT_CA_LOGITS = 4    /* cellular: float32[N, C, cells] logits; argmax over C, lowest index wins
+                                  (reps/ca_rep.py:31-44, wrappers.py:157-165)                                */
+};
+enum { PCGRL_E_ARG = -1, PCGRL_E_CUDA = -2, PCGRL_E_UNSUPPORTED = -3 };
+
+#define PCGRL_MAX_STATS 16
+#define PCGRL_MAX_TILES 16
+
+/* Static description of one env shard.  Mirrors what PcgrlEnv.__init__/adjust_param derive
+ * (envs/pcgrl_env.py:39-94, 221-247). */
+typedef struct pcgrl_config {
+    int32_t abi_version;      /* PCGRL_ABI_VERSION */
+    int32_t problem;          /* PCGRL_PROB_* */
+    int32_t representation;   /* PCGRL_REP_* */
+    int32_t action_kind;      /* PCGRL_ACT_* */
+    int32_t ndim;             /* 2 or 3 */
+    int32_t dims[3];          /* 2D: {H, W, 1};  3D: {Z, Y, X} -- numpy axis order of _map */
+    int32_t n_tiles;          /* C */
+    int32_t n_stats;          /* K, order = the problem's get_stats dict order */
+    int32_t row_stride;       /* bytes per env in `grids` (cells rounded up to a multiple of 16) */
+    int32_t max_iterations;   /* pcgrl_env.py:241 */
+    int32_t max_changes;      /* pcgrl_env.py:235-239; < 0 = unlimited */
+    int32_t act_h, act_w;     /* PCGRL_ACT_WIDE_FLAT only: ActionMap's (h, w) (wrappers.py:283-287) */
+    int32_t targets_per_env;  /* 1: targets is [N,K,2]; 0: targets is [1,K,2] shared by all envs */
+    int32_t init_random_probs;/* reset: 1 = draw per-episode tile probabilities U(0,1)^C normalised
+                                 (pcgrl_env.py:162-164), 0 = use init_probs as given */
+    float   init_probs[PCGRL_MAX_TILES]; /* tile init distribution, normalised by the library */
+    double  weights[PCGRL_MAX_STATS];    /* ControlWrapper.metric_weights per stat (0 = not in all_metrics),
+                                            control_wrappers.py:41-45,78-84 */
+} pcgrl_config;
+
+/* Device-resident state of N envs + the per-step inputs/outputs.
+ * Replaces: PcgrlEnv.step (envs/pcgrl_env.py:267-342), Representation.update (envs/reps/*.py),
+ * Problem.get_stats (envs/probs/<game>/*_prob.py) and ControlWrapper.step/get_loss
+ * (control_wrappers.py:216-244, 318-345). */
+typedef struct pcgrl_state {
+    int64_t  n_envs;
+    int64_t  env_offset;   /* global index of env 0 of this shard (only seeds the reset RNG) */
+    int8_t*  grids;        /* [N, row_stride] tile codes, row-major cells (C order of _map); in place */
+    int32_t* pos;          /* [N, 3] agent position in numpy axis order (unused axes 0) */
+    int32_t* n_step;       /* [N] narrow scan counter (reps/narrow_rep.py:98-100) */
+    int32_t* iteration;    /* [N] PcgrlEnv._iteration */
+    int32_t* changes;      /* [N] PcgrlEnv._changes */
+    int32_t* stats;        /* [N, K] current _rep_stats; read (old) and written (new) by step */
+    const double* targets; /* [N or 1, K, 2] (lo, hi): hi = NaN -> scalar target lo, else the integer range
+                              np.arange(lo, hi) (control_wrappers.py:336-343) */
+    float*   reward;       /* [N] out: loss(new stats) - loss(old stats), evaluated in fp64 */
+    uint8_t* done;         /* [N] out: done == truncated (pcgrl_env.py:307-310) */
+    uint8_t* changed;      /* [N] out, may be NULL: 1 if the map changed (stats were recomputed) */
+    int32_t* status;       /* [1] device error word, may be NULL: bit0 = an action was out of range */
+    void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0 */
+} pcgrl_state;
+
+/* -- queries (host only, no CUDA calls) ------------------------------------------------------- */
+int32_t     pcgrl_abi_version(void);
+const char* pcgrl_last_error(void);
+/* Validate a config and fill derived fields left at 0 (row_stride). */
+int32_t     pcgrl_config_check(pcgrl_config* cfg);
+int64_t     pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs);
+/* Algorithmic HBM bytes one env-step moves (2G + A + 8K + 5 [+ 16K per-env targets]). */
+int64_t     pcgrl_step_bytes(const pcgrl_config* cfg);
+
+/* -- launches ---------------------------------------------------------------------------------- */
+/* One env-step for every env of the shard.  `actions` layout depends on cfg->action_kind. */
+int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream);
+
+/* (Re)start episodes: PcgrlEnv.reset (envs/pcgrl_env.py:158-188) + Representation.reset
+ * (envs/reps/representation.py:65-76) + ControlWrapper.reset (control_wrappers.py:174-187).
+ *   mask      [N] uint8 or NULL (= all envs): which envs to reset
+ *   src_grids [N, row_stride] int8 or NULL: initial maps (set_map, pcgrl_ctrl_env.py:12-14); NULL = draw
+ *             each cell from the tile distribution with Philox4x32-10 keyed by (seed, env, epoch)
+ *   src_pos   [N, 3] int32 or NULL: start positions (turtle); NULL = narrow: cell 0, turtle: random
+ * Zeroes the counters and recomputes stats; reward/done keep what the last step wrote (so an auto-reset
+ * does not erase the finishing step's outputs). */
+int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_t* mask,
+                    const int8_t* src_grids, const int32_t* src_pos, uint64_t seed, uint64_t epoch,
+                    void* stream);
+
+/* Stats only: Problem.get_stats on n grids (evolution's terminal call, evo/evolve.py:1107-1116).
+ * grids [n, row_stride] int8 -> stats [n, K] int32. */
+int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats, int64_t n, void* scratch,
+                    void* stream);
+
+/* Observation tensors (control_pcgrl/wrappers.py Cropped :407-437 + OneHotEncoding :232-257 + ToImage
+ * :140-150, and ControlWrapper.observe_metric_trgs control_wrappers.py:189-214).
+ *   crop != 0 : window obs_dims centred on pos, channel 0 = out-of-bounds, C+1 one-hot channels
+ *   crop == 0 : the whole map, C one-hot channels (wide / cellular stacks)
+ *   n_ctrl controlled metrics prepend 2*n_ctrl constant planes (trg/range, value/range); ctrl_idx[i] is the
+ *   stat index, ctrl_range[i] = |hi - lo| of cond_bounds.
+ *   out_kind: 0 = uint8, 1 = float32, 2 = float64 (the reference's np.eye dtype).  Output layout [N, *obs_dims, channels] (channels last). */
+typedef struct pcgrl_obs_args {
+    int32_t crop;
+    int32_t obs_dims[3];
+    int32_t n_ctrl;
+    int32_t ctrl_idx[PCGRL_MAX_STATS];
+    double  ctrl_range[PCGRL_MAX_STATS];
+    int32_t out_kind;
+    void*   out;
+} pcgrl_obs_args;
+int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgrl_obs_args* obs, void* stream);
+
+/* -- host-buffer convenience (the end-to-end path timed as `e2e` in bench.py) ------------------ */
+/* Copies `actions` (host, pinned or pageable) to `actions_dev`, runs pcgrl_step, copies reward/done/stats
+ * back to the host buffers, and synchronises the stream.  Any host pointer may be NULL to skip that copy. */
+int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host,
+                        void* actions_dev, int64_t action_bytes, float* reward_host, uint8_t* done_host,
+                        int32_t* stats_host, void* stream);
+
+/* Counter of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t pcgrl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGRL_B200_H */
