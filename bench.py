@@ -214,8 +214,13 @@ def main():
     n_act = {"narrow": env.n_tiles, "turtle": 4 + env.n_tiles,
              "wide": obs_window[0] * obs_window[1] * env.n_tiles}[rep]
     gen = torch.Generator(device=dev).manual_seed(a.seed + rank)
-    POOL = 8   # distinct random action batches, cycled (resident in HBM before the timed region)
-    act_pool = [torch.randint(0, n_act, (n_envs,), generator=gen, device=dev, dtype=torch.int32) for _ in range(POOL)]
+    # one distinct uniform-random action batch per step, all resident in HBM before the timed region.
+    # (Cycling a small pool would be wrong: the narrow scan revisits a cell every 256 steps and would replay
+    # the same action on it, so nothing would change after the first board scan.)
+    POOL = min(a.steps + a.warmup, max(16, int(6e9 // (4 * n_envs))))
+    act_all = torch.randint(0, n_act, (POOL, n_envs), generator=gen, device=dev, dtype=torch.int32)
+    act_pool = [act_all[i] for i in range(POOL)]
+    step_no = [0]
     # ~300 MB scratch to push the working set out of L2 is unnecessary at the default size (grids alone are
     # 268 MB > 126 MB L2); for small --envs we flush explicitly between steps.
     grid_bytes = n_envs * env.row_stride
@@ -240,7 +245,9 @@ def main():
                 evs.append(("f", f0, f1))
             e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
-            _lib.check(lib.pcgrl_step(env._cc, env._st, act_pool[i % POOL].data_ptr(), env._stream()), "pcgrl_step")
+            _lib.check(lib.pcgrl_step(env._cc, env._st, act_pool[step_no[0] % POOL].data_ptr(), env._stream()),
+                       "pcgrl_step")
+            step_no[0] += 1
             e1.record()
             evs.append(("k", e0, e1))
             env._after_step()     # auto-reset launches (inside the timed region)
@@ -272,10 +279,11 @@ def main():
     if not a.no_e2e:
         shape_a, dt_a = env.action_shape_dtype()
         rng = np.random.default_rng(a.seed + 100 + rank)
-        host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(POOL)]
         k_e2e = max(3, min(a.steps, 200))
+        HP = min(k_e2e + 3, max(8, int(2e9 // (4 * n_envs))))
+        host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(HP)]
         for i in range(3):
-            env.step_host(host_acts[i % POOL])
+            env.step_host(host_acts[i % HP])
         barrier()
         w0 = time.perf_counter()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -284,7 +292,7 @@ def main():
         for i in range(k_e2e):
             if flush is not None:
                 flush.fill_(i & 0xFF)
-            r, d, s = env.step_host(host_acts[i % POOL])
+            r, d, s = env.step_host(host_acts[(i + 3) % HP])
             sink += float(r[0])
         e1.record()
         torch.cuda.synchronize()
@@ -332,7 +340,7 @@ def main():
             "ms_per_step": region_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 grids / int32 stats / f64 reward math", "data": "synthetic",
             "config": {"workload": a.workload, "envs_per_gpu": n_envs, "global_envs": world * n_envs,
-                       "actions": "uniform random, 8 pre-generated batches resident in HBM",
+                       "actions": f"uniform random, {POOL} distinct pre-generated batches resident in HBM",
                        "episode_steps": int(env.max_iterations) + 1, "auto_reset": True,
                        "l2": ("inputs larger than L2 (%.0f MB grids)" % (grid_bytes / 1e6)) if flush is None
                              else "256 MB L2 flush between steps (excluded from the timing)",

@@ -83,68 +83,91 @@ __device__ __forceinline__ double control_loss(const int32_t* st, const double* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sub-warp groups: G consecutive lanes own one level grid as a bit-board, one 32-bit word per lane.
-//   TWO = true : a word holds two rows of up to 16 cells (row 2l in bits 0..15, row 2l+1 in 16..31)
+// Bit-boards: one thread owns one level grid as NW 32-bit words held in registers.
+//   TWO = true : a word holds two rows of up to 16 cells (row 2i in bits 0..15, row 2i+1 in 16..31)
 //   TWO = false: a word holds one row of up to 32 cells
-// Bit order (lane, bit) is monotonic in the row-major cell index, so "lowest set bit of the group"
+// Bit order (word, bit) is monotonic in the row-major cell index, so "lowest set bit of the board"
 // == "first cell in the reference's y-outer/x-inner scan" (envs/helper.py:23-25).
+// No cross-lane traffic at all: x+-1 are shifts inside a word, y+-1 are funnel shifts between
+// neighbouring words (TWO) or plain neighbouring words.
 // ------------------------------------------------------------------------------------------------
-template <int G, bool TWO>
-struct Group {
-    static_assert(G == 1 || G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "group size");
-    int lane;      // lane in warp
-    int lig;       // lane in group
-    int gbase;     // first lane of the group
-    uint32_t gmask;  // warp mask of the group's lanes
-    uint32_t mask_l, mask_r;
-
-    __device__ __forceinline__ Group(int width) {
-        lane = threadIdx.x & 31;
-        lig = lane & (G - 1);
-        gbase = lane & ~(G - 1);
-        gmask = (G == 32) ? 0xffffffffu : (((1u << (G & 31)) - 1u) << gbase);
-        // horizontal shifts must not leak between the two 16-bit rows of a word (only possible when the
-        // rows are exactly 16 wide; narrower rows have never-passable padding bits in between)
-        mask_l = (TWO && width == 16) ? 0xFFFEFFFEu : 0xFFFFFFFFu;
-        mask_r = (TWO && width == 16) ? 0x7FFF7FFFu : 0xFFFFFFFFu;
-    }
-
-    // 4-neighbourhood dilation of the board (one bit per cell); caller ANDs with the passable set.
-    // Must be executed by all lanes of the group (uses group-masked shuffles).
-    __device__ __forceinline__ uint32_t expand(uint32_t f) const {
-        uint32_t up = __shfl_up_sync(gmask, f, 1, G);      // word of the rows above
-        uint32_t dn = __shfl_down_sync(gmask, f, 1, G);    // word of the rows below
-        if (G == 1 || lig == 0) up = 0;
-        if (G == 1 || lig == G - 1) dn = 0;
-        uint32_t u, d;
-        if (TWO) {
-            u = __funnelshift_l(up, f, 16);   // cell (y,x) <- (y-1,x): low row from prev word's high row
-            d = __funnelshift_r(f, dn, 16);   // cell (y,x) <- (y+1,x)
-        } else {
-            u = up;
-            d = dn;
-        }
-        return ((f << 1) & mask_l) | ((f >> 1) & mask_r) | u | d;
-    }
-
-    __device__ __forceinline__ bool any(uint32_t x) const { return (__ballot_sync(gmask, x != 0) & gmask) != 0; }
-
-    // One-hot board holding only the lowest set cell of x (all-zero if x is empty).
-    __device__ __forceinline__ uint32_t lowest(uint32_t x, bool& found) const {
-        const uint32_t b = __ballot_sync(gmask, x != 0) & gmask;
-        found = b != 0;
-        const int first = found ? (__ffs(b) - 1) : gbase;
-        const uint32_t w = __shfl_sync(gmask, x, first);
-        return (found && lane == first) ? (w & (0u - w)) : 0u;
-    }
-
-    // sum over the group's lanes
-    __device__ __forceinline__ int sum(int v) const {
+template <int NW, bool TWO>
+struct Board {
+    // n = dilate4(f) & av;  returns OR of all words of n (zero <=> frontier died)
+    __device__ static __forceinline__ uint32_t expand_and(const uint32_t (&f)[NW], const uint32_t (&av)[NW],
+                                                          uint32_t (&n)[NW]) {
+        uint32_t any = 0;
 #pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
-        return v;
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t up = i > 0 ? f[i - 1] : 0u;
+            const uint32_t dn = i < NW - 1 ? f[i + 1] : 0u;
+            uint32_t h, u, d;
+            if (TWO) {
+                // the two 16-bit rows of a word must not leak into each other.  Rows narrower than 16 have
+                // never-passable padding bits, for which the masks are no-ops, so they are always applied.
+                h = ((f[i] << 1) & 0xFFFEFFFEu) | ((f[i] >> 1) & 0x7FFF7FFFu);
+                u = __funnelshift_l(up, f[i], 16);  // cell (y,x) <- (y-1,x)
+                d = __funnelshift_r(f[i], dn, 16);  // cell (y,x) <- (y+1,x)
+            } else {
+                h = (f[i] << 1) | (f[i] >> 1);
+                u = up;
+                d = dn;
+            }
+            n[i] = (h | u | d) & av[i];
+            any |= n[i];
+        }
+        return any;
     }
-    __device__ __forceinline__ int bcast(int v, int src_lig) const { return __shfl_sync(gmask, v, gbase + src_lig); }
+    // One-hot board holding only the lowest set cell of x (all zero if x is empty): the multi-word
+    // two's-complement identity  X & -X, with the borrow rippling through the words as a carry chain
+    // (sub.cc / subc.cc), i.e. 2 ALU ops per word and no compares, selects or indices.
+    __device__ static __forceinline__ void lowest(const uint32_t (&x)[NW], uint32_t (&out)[NW]) {
+        uint32_t neg[NW];
+        if constexpr (NW == 1) {
+            neg[0] = 0u - x[0];
+        } else if constexpr (NW == 2) {
+            asm("sub.cc.u32 %0, 0, %2;\n\tsubc.u32 %1, 0, %3;" : "=r"(neg[0]), "=r"(neg[1]) : "r"(x[0]), "r"(x[1]));
+        } else if constexpr (NW == 4) {
+            asm("sub.cc.u32 %0, 0, %4;\n\tsubc.cc.u32 %1, 0, %5;\n\tsubc.cc.u32 %2, 0, %6;\n\tsubc.u32 %3, 0, %7;"
+                : "=r"(neg[0]), "=r"(neg[1]), "=r"(neg[2]), "=r"(neg[3])
+                : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]));
+        } else if constexpr (NW == 8) {
+            asm("sub.cc.u32 %0, 0, %8;\n\tsubc.cc.u32 %1, 0, %9;\n\tsubc.cc.u32 %2, 0, %10;\n\t"
+                "subc.cc.u32 %3, 0, %11;\n\tsubc.cc.u32 %4, 0, %12;\n\tsubc.cc.u32 %5, 0, %13;\n\t"
+                "subc.cc.u32 %6, 0, %14;\n\tsubc.u32 %7, 0, %15;"
+                : "=r"(neg[0]), "=r"(neg[1]), "=r"(neg[2]), "=r"(neg[3]), "=r"(neg[4]), "=r"(neg[5]), "=r"(neg[6]),
+                  "=r"(neg[7])
+                : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+        } else {
+            // wide boards (maps up to 32x32): ripple the borrow by hand
+            uint32_t borrow = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                neg[i] = 0u - x[i] - borrow;
+                borrow = (x[i] | borrow) ? 1u : 0u;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NW; ++i) out[i] = x[i] & neg[i];
+    }
+    __device__ static __forceinline__ uint32_t any(const uint32_t (&x)[NW]) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) r |= x[i];
+        return r;
+    }
+    __device__ static __forceinline__ int popcount(const uint32_t (&x)[NW]) {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) c += __popc(x[i]);
+        return c;
+    }
+    __device__ static __forceinline__ uint32_t any_and(const uint32_t (&a)[NW], const uint32_t (&b)[NW]) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) r |= a[i] & b[i];
+        return r;
+    }
 };
 
 }  // namespace pcgrl

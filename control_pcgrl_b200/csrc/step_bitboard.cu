@@ -12,9 +12,9 @@
 //      for the cellular rep), advance counters, decide done, flag envs whose map changed;
 //   B  all threads: 128-bit coalesced loads of the changed grids, packed into per-plane bit-boards in
 //      shared memory (one bit per cell; a "plane" is a set of tile codes);
-//   C  sub-warp groups (G lanes, one 32-bit board word per lane) pull changed envs from a shared-memory
-//      queue and run the stat searches as level-synchronous bit-board BFS: shifts inside a lane for x+-1,
-//      lane shuffles for y+-1, warp ballots for the frontier-empty test;
+//   C  thread-per-grid: every thread pulls changed envs from a shared-memory queue and runs the stat
+//      searches as level-synchronous bit-board BFS held entirely in registers (NW 32-bit words): shifts
+//      inside a word for x+-1, funnel shifts between neighbouring words for y+-1, no cross-lane traffic;
 //   D  thread-per-env: fp64 loss(new stats) - loss(old stats), write stats / reward / done / counters.
 #include "pcgrl_device.cuh"
 
@@ -22,24 +22,24 @@ namespace pcgrl {
 
 constexpr int THREADS = 128;
 // envs per CTA, bounded so the shared-memory bit-boards stay under the 48 KB static limit
-__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64); }
+__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 8 ? 512 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
 
 // ------------------------------------------------------------------------------------------------
-// Problem policies: planes (tile-code sets packed to bit-boards) + the per-group stats state machine.
-// Each machine is a flat loop: one board expansion per iteration for every group of the warp, with
-// rare, group-uniform transitions -- so the 32/G grids that share a warp stay converged.
+// Problem policies: planes (tile-code sets packed to bit-boards) + the per-thread stats state machine.
+// Each machine is a flat loop: one board expansion per trip, with rare transitions -- so the 32 grids
+// that share a warp execute the same instruction stream whatever phase each of them is in.
 // ------------------------------------------------------------------------------------------------
 struct BinaryProb {
     static constexpr int P = 1;
     static constexpr int K = 2;  // regions, path-length
-    __device__ static constexpr uint32_t plane_mask(int p) { return 0x1u; }  // {empty}
+    __host__ __device__ static constexpr uint32_t plane_mask(int p) { return 0x1u; }  // {empty}
 };
 
 struct ZeldaProb {
     static constexpr int P = 5;
     static constexpr int K = 7;  // player key door enemies regions nearest-enemy path-length
     // tiles: empty 0, solid 1, player 2, key 3, door 4, bat 5, scorpion 6, spider 7 (zelda_prob.py:20)
-    __device__ static constexpr uint32_t plane_mask(int p) {
+    __host__ __device__ static constexpr uint32_t plane_mask(int p) {
         return p == 0 ? 0xEDu   /* walkable {0,2,3,5,6,7}  zelda_ctrl_prob.py:101-104 */
              : p == 1 ? 0x04u   /* player */
              : p == 2 ? 0x08u   /* key */
@@ -55,49 +55,75 @@ struct ZeldaProb {
 //   remaining cell, far = lowest cell of the last non-empty level == np.argmax); (3) the second sweeps of
 //   all components run at once as a single multi-source BFS from the set of far tiles -- components are
 //   disconnected, so the number of levels until the joint frontier dies is max_c ecc(far_c).
-template <int G, bool TWO>
+template <int NW, bool TWO>
 struct BinaryMachine {
     using Prob = BinaryProb;
-    uint32_t avail, front, base, fars;
+    using B = Board<NW, TWO>;
+    uint32_t avail[NW], front[NW], fars[NW];
+    uint32_t* base;  // shared-memory copy of the non-isolated passable cells (re-read for the joint sweep)
     int phase, level, ncomp;
 
-    __device__ __forceinline__ void init(const Group<G, TWO>& g, const uint32_t* bb /* [P][G] */) {
-        const uint32_t pass = bb[g.lig];
-        const uint32_t iso = pass & ~g.expand(pass);
-        ncomp = __popc(iso);          // per-lane partial; reduced over the group at the end
-        base = pass & ~iso;
-        avail = base;
-        front = 0;
-        fars = 0;
+    __device__ __forceinline__ void init(uint32_t* bb /* [P][NW] in shared memory */) {
+        uint32_t pass[NW], ones[NW], nb[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            pass[i] = bb[i];
+            ones[i] = 0xFFFFFFFFu;
+        }
+        B::expand_and(pass, ones, nb);
+        ncomp = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t iso = pass[i] & ~nb[i];
+            ncomp += __popc(iso);
+            avail[i] = pass[i] & ~iso;
+            bb[i] = avail[i];
+            front[i] = 0;
+            fars[i] = 0;
+        }
+        base = bb;
         phase = 0;
         level = 0;
     }
-    // returns true when the item is finished (out[] then holds the K stats, valid in every lane)
-    __device__ __forceinline__ bool advance(const Group<G, TWO>& g, int* out) {
-        const uint32_t n = g.expand(front) & avail;
-        if (g.any(n)) {
-            avail ^= n;
-            front = n;
+    // one board expansion (or one transition); returns true when out[] holds the K stats
+    __device__ __forceinline__ bool advance(int* out) {
+        uint32_t n[NW];
+        if (B::expand_and(front, avail, n)) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                avail[i] ^= n[i];
+                front[i] = n[i];
+            }
             ++level;
             return false;
         }
         if (phase == 0) {
-            bool found;
-            fars |= g.lowest(front, found);          // far tile of the component just swept (none on entry)
-            const uint32_t s = g.lowest(avail, found);
-            if (found) {                              // next component, first sweep
-                front = s;
-                avail ^= s;
-                if (s) ++ncomp;
+            uint32_t lo[NW];
+            B::lowest(front, lo);             // far tile of the component just swept (nothing on entry)
+#pragma unroll
+            for (int i = 0; i < NW; ++i) fars[i] |= lo[i];
+            B::lowest(avail, lo);             // first tile of the next component
+            if (B::any(lo)) {
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    front[i] = lo[i];
+                    avail[i] ^= lo[i];
+                }
+                ++ncomp;
                 return false;
             }
-            phase = 1;                                // joint second sweep
-            front = fars;
-            avail = base & ~fars;
+            phase = 1;  // joint second sweep from every far tile
+            uint32_t any = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                front[i] = fars[i];
+                avail[i] = base[i] & ~fars[i];
+                any |= fars[i];
+            }
             level = 0;
-            if (g.any(fars)) return false;
+            if (any) return false;
         }
-        out[0] = g.sum(ncomp);
+        out[0] = ncomp;
         out[1] = level;
         return true;
     }
@@ -107,70 +133,102 @@ struct BinaryMachine {
 // nearest-enemy = first level >= 1 that touches an enemy, d(player->key) = level that touches the key;
 // then (key == 1 && door == 1) BFS from the key over walkable+door: d(key->door).  Unreached = -1 each
 // (run_dijkstra's fill value), added raw (zelda_ctrl_prob.py:134-150).
-template <int G, bool TWO>
+template <int NW, bool TWO>
 struct ZeldaMachine {
     using Prob = ZeldaProb;
-    uint32_t avail, front, walk, player, key, door, enemy;
+    using B = Board<NW, TWO>;
+    uint32_t avail[NW], front[NW];
+    const uint32_t* bb;  // planes in shared memory: walk, player, key, door, enemy
     int phase, level, regions, near, dkey, ddoor;
     int n_player, n_key, n_door, n_enemy;
 
-    __device__ __forceinline__ void init(const Group<G, TWO>& g, const uint32_t* bb) {
-        walk = bb[0 * G + g.lig];
-        player = bb[1 * G + g.lig];
-        key = bb[2 * G + g.lig];
-        door = bb[3 * G + g.lig];
-        enemy = bb[4 * G + g.lig];
-        n_player = g.sum(__popc(player));
-        n_key = g.sum(__popc(key));
-        n_door = g.sum(__popc(door));
-        n_enemy = g.sum(__popc(enemy));
-        const uint32_t iso = walk & ~g.expand(walk);
-        regions = __popc(iso);
-        avail = walk & ~iso;
-        front = 0;
+    __device__ __forceinline__ void load(int plane, uint32_t (&x)[NW]) const {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) x[i] = bb[plane * NW + i];
+    }
+    __device__ __forceinline__ void init(uint32_t* planes) {
+        bb = planes;
+        uint32_t walk[NW], t[NW], ones[NW], nb[NW];
+        load(0, walk);
+        load(1, t);
+        n_player = B::popcount(t);
+        load(2, t);
+        n_key = B::popcount(t);
+        load(3, t);
+        n_door = B::popcount(t);
+        load(4, t);
+        n_enemy = B::popcount(t);
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ones[i] = 0xFFFFFFFFu;
+        B::expand_and(walk, ones, nb);
+        regions = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t iso = walk[i] & ~nb[i];
+            regions += __popc(iso);
+            avail[i] = walk[i] & ~iso;
+            front[i] = 0;
+        }
         phase = 0;
         level = 0;
         near = 0;
         dkey = -1;
         ddoor = -1;
     }
-    __device__ __forceinline__ bool advance(const Group<G, TWO>& g, int* out) {
-        const uint32_t n = g.expand(front) & avail;
-        if (g.any(n)) {
-            avail ^= n;
-            front = n;
+    __device__ __forceinline__ bool advance(int* out) {
+        uint32_t n[NW];
+        if (B::expand_and(front, avail, n)) {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                avail[i] ^= n[i];
+                front[i] = n[i];
+            }
             ++level;
             if (phase == 1) {
-                if (near == 0 && g.any(n & enemy)) near = level;
-                if (g.any(n & key)) dkey = level;
+                uint32_t t[NW];
+                load(4, t);
+                if (near == 0 && B::any_and(n, t)) near = level;
+                load(2, t);
+                if (B::any_and(n, t)) dkey = level;
             } else if (phase == 2) {
-                if (g.any(n & door)) ddoor = level;
+                uint32_t t[NW];
+                load(3, t);
+                if (B::any_and(n, t)) ddoor = level;
             }
             return false;
         }
-        bool found;
         if (phase == 0) {  // region flood fill, one component at a time
-            const uint32_t s = g.lowest(avail, found);
-            if (found) {
-                front = s;
-                avail ^= s;
-                if (s) ++regions;
+            uint32_t lo[NW];
+            B::lowest(avail, lo);
+            if (B::any(lo)) {
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    front[i] = lo[i];
+                    avail[i] ^= lo[i];
+                }
+                ++regions;
                 return false;
             }
-            regions = g.sum(regions);
             if (n_player == 1 && (n_enemy > 0 || (n_key == 1 && n_door == 1))) {
-                phase = 1;
-                front = player;
-                avail = walk & ~player;
+                phase = 1;  // BFS from the player over the walkable plane
+                uint32_t walk[NW];
+                load(0, walk);
+                load(1, front);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) avail[i] = walk[i] & ~front[i];
                 level = 0;
                 return false;
             }
             phase = 3;
         } else if (phase == 1) {
             if (n_key == 1 && n_door == 1) {
-                phase = 2;
-                front = key;
-                avail = (walk | door) & ~key;
+                phase = 2;  // BFS from the key over walkable + door
+                uint32_t walk[NW], door[NW];
+                load(0, walk);
+                load(3, door);
+                load(2, front);
+#pragma unroll
+                for (int i = 0; i < NW; ++i) avail[i] = (walk[i] | door[i]) & ~front[i];
                 level = 0;
                 return false;
             }
@@ -333,14 +391,40 @@ __device__ void reset_env(const KParams& p, int64_t gid) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 16 tile codes (one 128-bit load) -> one 16-bit membership mask per plane (bit i = cell i in the plane).
+// Tile codes are < 8 for every bit-board problem, so a plane is an 8-entry 0/1 table that PRMT looks up
+// for 4 cells at once; the multiply then gathers the four 0/1 bytes into bits 24..27.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ constexpr uint32_t lut_bytes(uint32_t mask, int first) {
+    return ((mask >> first) & 1u) | (((mask >> (first + 1)) & 1u) << 8) | (((mask >> (first + 2)) & 1u) << 16) |
+           (((mask >> (first + 3)) & 1u) << 24);
+}
+template <class Prob>
+__device__ __forceinline__ void pack16(const uint4 v, uint32_t (&out)[Prob::P]) {
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < Prob::P; ++q) out[q] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t t = w4[k] | (w4[k] >> 4);
+        const uint32_t sel = ((t & 0xFFu) | ((t >> 8) & 0xFF00u)) & 0x7777u;  // 4 nibbles = 4 tile codes
+#pragma unroll
+        for (int q = 0; q < Prob::P; ++q) {
+            const uint32_t b = __byte_perm(lut_bytes(Prob::plane_mask(q), 0), lut_bytes(Prob::plane_mask(q), 4), sel);
+            out[q] |= ((b * 0x01020408u) >> 24) << (4 * k);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <class Machine, int G, bool TWO>
+template <class Machine, int NW, bool TWO>
 __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     using Prob = typename Machine::Prob;
     constexpr int P = Prob::P;
     constexpr int K = Prob::K;
-    constexpr int BBW = P * G;  // board words per env
+    constexpr int BBW = P * NW;  // board words per env
     constexpr int TILE = tile_for(BBW);
 
     __shared__ uint32_t s_bb[TILE * BBW];
@@ -446,78 +530,72 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     const int M = s_count;
 
     // ---------------- phase B: coalesced 128-bit grid loads -> per-plane bit-boards in smem --------
-    for (int i = tid; i < M * BBW; i += THREADS) s_bb[i] = 0;
-    __syncthreads();
+    // 16 cells (one uint4) are turned into a 16-bit membership mask per plane with SIMD-in-register ops:
+    // a PRMT table lookup maps 4 tile codes to 4 0/1 bytes, a multiply gathers them into a nibble.
     {
         const int chunks = p.row_stride / 16;
         const int W = (p.ndim == 2) ? p.d1 : p.d2;
-        for (int i = tid; i < M * chunks; i += THREADS) {
-            const int slot = i / chunks, c = i - slot * chunks;
-            const int e = s_list[slot];
-            const uint4 v = *(const uint4*)(grids_in + (base + e) * p.row_stride + c * 16);
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-            int cell = c * 16;
-            int y = cell / W, x = cell - y * W;
-            uint32_t acc[P];
+        const bool word_is_32_bytes = TWO ? (W == 16) : (W == 32);
+        if (word_is_32_bytes) {
+            // a board word is exactly 32 consecutive cells: one thread builds one word, no atomics
+            for (int i = tid; i < M * NW; i += THREADS) {
+                const int slot = i / NW, j = i - slot * NW;
+                const int8_t* g = grids_in + (base + s_list[slot]) * p.row_stride + j * 32;
+                uint32_t lo[P], hi[P];
 #pragma unroll
-            for (int q = 0; q < P; ++q) acc[q] = 0;
-            int cur = TWO ? (y >> 1) : y;
-            uint32_t* bb = s_bb + slot * BBW;
+                for (int q = 0; q < P; ++q) lo[q] = hi[q] = 0;
+                if (2 * j < chunks) pack16<Prob>(*(const uint4*)g, lo);
+                if (2 * j + 1 < chunks) pack16<Prob>(*(const uint4*)(g + 16), hi);
 #pragma unroll
-            for (int b = 0; b < 16; ++b, ++cell) {
-                if (cell < p.cells) {
-                    const int l = TWO ? (y >> 1) : y;
-                    if (l != cur) {
+                for (int q = 0; q < P; ++q) s_bb[slot * BBW + q * NW + j] = lo[q] | (hi[q] << 16);
+            }
+        } else {
+            for (int i = tid; i < M * BBW; i += THREADS) s_bb[i] = 0;
+            __syncthreads();
+            for (int i = tid; i < M * chunks; i += THREADS) {
+                const int slot = i / chunks, c = i - slot * chunks;
+                uint32_t lin[P];
+                pack16<Prob>(*(const uint4*)(grids_in + (base + s_list[slot]) * p.row_stride + c * 16), lin);
+                uint32_t* bb = s_bb + slot * BBW;
+                int cell = c * 16;
+                const int end = min(cell + 16, p.cells);
+                int y = cell / W, x = cell - y * W;
+                while (cell < end) {   // one row segment at a time (at most ceil(16/W)+1 of them)
+                    const int len = min(W - x, end - cell);
+                    const int word = TWO ? (y >> 1) : y;
+                    const int sh = TWO ? ((y & 1) * 16 + x) : x;
+                    const uint32_t m = (1u << len) - 1u;
 #pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            if (acc[q]) atomicOr(&bb[q * G + cur], acc[q]);
-                            acc[q] = 0;
-                        }
-                        cur = l;
+                    for (int q = 0; q < P; ++q) {
+                        const uint32_t seg = (lin[q] >> (cell - c * 16)) & m;
+                        if (seg) atomicOr(&bb[q * NW + word], seg << sh);
                     }
-                    const uint32_t t = (w4[b >> 2] >> ((b & 3) * 8)) & 0xFFu;
-                    const int bit = TWO ? ((y & 1) * 16 + x) : x;
-#pragma unroll
-                    for (int q = 0; q < P; ++q) acc[q] |= ((Prob::plane_mask(q) >> t) & 1u) << bit;
-                    if (++x == W) {
-                        x = 0;
-                        ++y;
-                    }
+                    cell += len;
+                    x = 0;
+                    ++y;
                 }
             }
-#pragma unroll
-            for (int q = 0; q < P; ++q)
-                if (acc[q]) atomicOr(&bb[q * G + cur], acc[q]);
         }
     }
     __syncthreads();
 
-    // ---------------- phase C: group-per-grid stat searches, dynamic queue --------------------------
+    // ---------------- phase C: thread-per-grid stat searches, dynamic queue --------------------------
+    // Each thread pulls the next changed env from the shared-memory queue as soon as it finishes one, so
+    // lanes with short searches do not idle behind long ones; the search itself is a flat loop (one board
+    // expansion per trip) so lanes in different phases of different grids execute the same instructions.
     {
-        const int W = (p.ndim == 2) ? p.d1 : p.d2;
-        Group<G, TWO> g(W);
         Machine m;
-        int item = -1;
-        bool active = true;
-        auto fetch = [&]() {
-            int it = 0;
-            if (g.lig == 0) it = atomicAdd(&s_next, 1);
-            it = __shfl_sync(g.gmask, it, g.gbase);
-            item = it;
-            active = it < M;
-            if (active) m.init(g, s_bb + it * BBW);
-        };
-        fetch();
-        while (__any_sync(0xffffffffu, active)) {
-            if (active) {
-                int out[K];
-                if (m.advance(g, out)) {
-                    if (g.lig == 0) {
+        int item = atomicAdd(&s_next, 1);
+        bool active = item < M;
+        if (active) m.init(s_bb + item * BBW);
+        while (active) {
+            int out[K];
+            if (m.advance(out)) {
 #pragma unroll
-                        for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
-                    }
-                    fetch();
-                }
+                for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                item = atomicAdd(&s_next, 1);
+                active = item < M;
+                if (active) m.init(s_bb + item * BBW);
             }
         }
     }
@@ -553,12 +631,12 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
-template <class Machine, int G, bool TWO>
+template <class Machine, int NW, bool TWO>
 static cudaError_t launch(const KParams& p, cudaStream_t s) {
-    constexpr int TILE = tile_for(Machine::Prob::P * G);
+    constexpr int TILE = tile_for(Machine::Prob::P * NW);
     const int64_t ctas = (p.n_envs + TILE - 1) / TILE;
     if (ctas == 0) return cudaSuccess;
-    k_step_bitboard<Machine, G, TWO><<<(unsigned)ctas, THREADS, 0, s>>>(p);
+    k_step_bitboard<Machine, NW, TWO><<<(unsigned)ctas, THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
 
