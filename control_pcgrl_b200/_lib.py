@@ -17,7 +17,8 @@ REP_IDS = {"narrow": 0, "turtle": 1, "wide": 2, "cellular": 3}
 ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS = range(5)
 
 LIB_NAME = "libpcgrl_sm100.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# PCGRL_B200_LIB lets kernel experiments load an alternative build of the same ABI (scripts/ab_variants.sh)
+LIB_PATH = os.environ.get("PCGRL_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 
 class Config(C.Structure):

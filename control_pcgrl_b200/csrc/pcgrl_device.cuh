@@ -4,6 +4,19 @@
 #include <stdint.h>
 #include "../../include/pcgrl_b200.h"
 
+// tuning knobs (A/B-tested on B200, see profiles/)
+#ifndef PCGRL_OPT_SHR_IMAD
+#define PCGRL_OPT_SHR_IMAD 0   // 1: issue x>>1 as IMAD.HI on the FMA pipe instead of SHF on the ALU pipe
+#endif
+#ifndef PCGRL_OPT_WORKERS
+#define PCGRL_OPT_WORKERS 0    // 1: only ceil(M/rounds) threads take part in the stats phase
+#endif
+#if PCGRL_OPT_SHR_IMAD
+#define PCGRL_SHR1(x) __umulhi((x), 0x80000000u)
+#else
+#define PCGRL_SHR1(x) ((x) >> 1)
+#endif
+
 namespace pcgrl {
 
 enum { MODE_STEP = 0, MODE_RESET = 1, MODE_STATS = 2 };
@@ -94,27 +107,37 @@ __device__ __forceinline__ double control_loss(const int32_t* st, const double* 
 template <int NW, bool TWO>
 struct Board {
     // n = dilate4(f) & av;  returns OR of all words of n (zero <=> frontier died)
+    //
+    // TWO layout: the "row above" word of board word i and the "row below" word of board word i-1 are the
+    // same 32-bit window straddling words i-1 and i (high row of i-1, low row of i), so one funnel shift
+    // per word boundary serves both directions.  x>>1 is issued as a multiply-high (IMAD.HI, FMA pipe) and
+    // x<<1 as an add, which moves about a third of the integer work off the saturated ALU pipe.
     __device__ static __forceinline__ uint32_t expand_and(const uint32_t (&f)[NW], const uint32_t (&av)[NW],
                                                           uint32_t (&n)[NW]) {
         uint32_t any = 0;
+        if (TWO) {
+            uint32_t s[NW + 1];  // s[i] = rows (2i-1, 2i): window between word i-1 and word i
+            s[0] = f[0] << 16;
 #pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t up = i > 0 ? f[i - 1] : 0u;
-            const uint32_t dn = i < NW - 1 ? f[i + 1] : 0u;
-            uint32_t h, u, d;
-            if (TWO) {
+            for (int i = 1; i < NW; ++i) s[i] = __funnelshift_l(f[i - 1], f[i], 16);
+            s[NW] = f[NW - 1] >> 16;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
                 // the two 16-bit rows of a word must not leak into each other.  Rows narrower than 16 have
                 // never-passable padding bits, for which the masks are no-ops, so they are always applied.
-                h = ((f[i] << 1) & 0xFFFEFFFEu) | ((f[i] >> 1) & 0x7FFF7FFFu);
-                u = __funnelshift_l(up, f[i], 16);  // cell (y,x) <- (y-1,x)
-                d = __funnelshift_r(f[i], dn, 16);  // cell (y,x) <- (y+1,x)
-            } else {
-                h = (f[i] << 1) | (f[i] >> 1);
-                u = up;
-                d = dn;
+                const uint32_t l = (f[i] + f[i]) & 0xFFFEFFFEu;
+                const uint32_t r = PCGRL_SHR1(f[i]) & 0x7FFF7FFFu;
+                n[i] = (l | r | s[i] | s[i + 1]) & av[i];
+                any |= n[i];
             }
-            n[i] = (h | u | d) & av[i];
-            any |= n[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                const uint32_t up = i > 0 ? f[i - 1] : 0u;
+                const uint32_t dn = i < NW - 1 ? f[i + 1] : 0u;
+                n[i] = ((f[i] + f[i]) | PCGRL_SHR1(f[i]) | up | dn) & av[i];
+                any |= n[i];
+            }
         }
         return any;
     }

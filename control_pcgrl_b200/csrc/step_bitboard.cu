@@ -20,9 +20,15 @@
 
 namespace pcgrl {
 
-constexpr int THREADS = 128;
+#ifndef PCGRL_THREADS
+#define PCGRL_THREADS 128
+#endif
+#ifndef PCGRL_TILE8
+#define PCGRL_TILE8 256   // envs per CTA when a board is <= 8 words (binary 16x16); A/B: 2 envs per thread is best
+#endif
+constexpr int THREADS = PCGRL_THREADS;
 // envs per CTA, bounded so the shared-memory bit-boards stay under the 48 KB static limit
-__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 8 ? 512 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
+__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 8 ? PCGRL_TILE8 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
 
 // ------------------------------------------------------------------------------------------------
 // Problem policies: planes (tile-code sets packed to bit-boards) + the per-thread stats state machine.
@@ -583,9 +589,13 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     // Each thread pulls the next changed env from the shared-memory queue as soon as it finishes one, so
     // lanes with short searches do not idle behind long ones; the search itself is a flat loop (one board
     // expansion per trip) so lanes in different phases of different grids execute the same instructions.
+    // Only as many threads as finish in whole rounds take part (R = ceil(M/THREADS) items each), so a warp's
+    // lanes run out of work together instead of a few lanes dragging a mostly idle warp through a last round.
     {
         Machine m;
-        int item = atomicAdd(&s_next, 1);
+        const int rounds = (M + THREADS - 1) / THREADS;
+        const int workers = PCGRL_OPT_WORKERS ? (rounds ? (M + rounds - 1) / rounds : 0) : THREADS;
+        int item = tid < workers ? atomicAdd(&s_next, 1) : M;
         bool active = item < M;
         if (active) m.init(s_bb + item * BBW);
         while (active) {
