@@ -107,6 +107,86 @@ def zelda_grids():
     return out
 
 
+def sokoban_grids():
+    rng = np.random.default_rng(31)
+    out = []
+    for shape in [(5, 5), (5, 5), (6, 7), (4, 8)]:
+        for _ in range(60):
+            out.append(rng.choice(5, size=shape, p=[0.45, 0.4, 0.05, 0.05, 0.05]).astype(np.uint8))
+        # solver-friendly: one player, k crates, k targets, sparse walls (so _run_game actually runs)
+        for _ in range(110):
+            k = int(rng.integers(1, 4))
+            g = (rng.random(shape) < rng.choice([0.0, 0.1, 0.2, 0.3])).astype(np.uint8)
+            cells = rng.permutation(g.size)[:1 + 2 * k]
+            g.flat[cells[0]] = 2
+            g.flat[cells[1:1 + k]] = 3
+            g.flat[cells[1 + k:]] = 4
+            out.append(g)
+    return out
+
+
+def smb_grids():
+    rng = np.random.default_rng(32)
+    base = np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02])
+    base /= base.sum()
+    out = []
+    for shape, n in [((116, 16), 50), ((16, 116), 24), ((16, 40), 30), ((12, 12), 40)]:
+        for i in range(n):
+            p = base
+            if i % 4 == 3:
+                p = rng.random(7)
+                p /= p.sum()
+            g = rng.choice(7, size=shape, p=p).astype(np.uint8)
+            if i % 4 == 2:      # a solid ground row with gaps, like a real level
+                g[-2:, :] = np.where(rng.random((2, shape[1])) < 0.85, 1, 0)
+            out.append(g)
+    return out
+
+
+def floors_map(rng, size, wall_p=0.2, hole_p=0.15):
+    """3D maps with storeys every 3 layers: long walks, stairs and jumps (random maps rarely have them)."""
+    g = (rng.random((size,) * 3) < wall_p).astype(np.uint8)
+    for z in range(3, size, 3):
+        g[z] = (rng.random((size, size)) >= hole_p).astype(np.uint8)
+    return g
+
+
+def _test3d_maps():
+    """The hand-built maps of the reference's test3D.py (test_map_1..23), read in place."""
+    src = open(os.path.join(R.REF_ROOT, "test3D.py")).read().split("\n")
+    start = next(i for i, ln in enumerate(src) if ln.startswith("test_map_1 "))
+    end = next(i for i, ln in enumerate(src) if ln.startswith("def get_test_state"))
+    ns = {}
+    exec("\n".join(src[start:end]), ns)
+    return [np.array(ns[f"test_map_{i}"]["map"], dtype=np.uint8) for i in range(1, 24)]
+
+
+def maze3d_grids():
+    rng = np.random.default_rng(33)
+    out = []
+    for size, n in [(14, 10), (10, 8), (8, 8), (6, 8)]:
+        for p in (0.15, 0.3, 0.5, 0.7):
+            for _ in range(n):
+                out.append((rng.random((size,) * 3) < p).astype(np.uint8))
+        for _ in range(n):
+            out.append(floors_map(rng, size, wall_p=float(rng.choice([0.1, 0.2, 0.35])),
+                                  hole_p=float(rng.choice([0.05, 0.15, 0.3]))))
+    out.append(np.zeros((14, 14, 14), np.uint8))
+    out.append(np.ones((14, 14, 14), np.uint8))
+    H = R.load_helpers()
+    kept = 0
+    for m in _test3d_maps():
+        try:        # non-cubic maps hit the IndexError of helper_3D.py:531 (SURVEY A-21)
+            smap = H.h3.get_string_map(m, TILES["minecraft_3D_maze"])
+            H.h3.calc_longest_path(smap, H.h3.get_tile_locations(smap, TILES["minecraft_3D_maze"]), ["AIR"])
+        except IndexError:
+            continue
+        out.append(m)
+        kept += 1
+    print("test3D.py maps usable:", kept, "of 23")
+    return out
+
+
 def save_stats_fixture(problem, grids, name=None):
     by_shape = {}
     for g in grids:
@@ -127,13 +207,13 @@ def save_stats_fixture(problem, grids, name=None):
 # ------------------------------------------------------------------------------------------ traces
 def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None, n_envs=4, seed=0,
               max_board_scans=3, change_percentage=None, raw_only=False, n_steps=None, init_p=None,
-              targets=None, obs_every=97):
+              targets=None, obs_every=97, action_p=None, grid_every=1):
     rng = np.random.default_rng(seed)
     cfg = R.make_cfg(problem, rep, map_shape, obs_window=obs_window, weights=weights, controls=controls,
                      max_board_scans=max_board_scans, change_percentage=change_percentage)
     n_tiles = len(TILES[problem])
     rec = dict(grid0=[], pos0=[], actions=[], rewards=[], dones=[], stats=[], pos=[], grids=[], stats0=[],
-               obs=[], obs_step=[], obs0=[], changes=[], trg=[])
+               obs=[], obs_step=[], obs0=[], changes=[], trg=[], grids_step=[])
     for e in range(n_envs):
         env = R.make_wrapped_env(cfg, raw_only=raw_only)
         if init_p is None:
@@ -151,22 +231,23 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
         rep_obj = u._rep.unwrapped
         pos0 = [int(v) for v in rep_obj._pos] if rep in ("narrow", "turtle") else [0] * len(map_shape)
         stats0 = [int(u._rep_stats[k]) for k in STAT_NAMES[problem]]
-        acts, rews, dones, stats, poss, grids, obs_l, obs_s, chg = [], [], [], [], [], [], [], [], []
+        acts, rews, dones, stats, poss, grids, obs_l, obs_s, chg, grid_s = [], [], [], [], [], [], [], [], [], []
         done = False
         t = 0
         while not done and (n_steps is None or t < n_steps):
             if rep == "cellular":
                 a = rng.random((n_tiles, *map_shape)).astype(np.float32)
                 if t % 3 == 2:      # sometimes keep most of the map: near-no-op logits
-                    a = np.eye(n_tiles, dtype=np.float32)[u._rep.unwrapped._map.astype(int)].transpose(2, 0, 1).copy()
+                    a = np.moveaxis(np.eye(n_tiles, dtype=np.float32)[u._rep.unwrapped._map.astype(int)], -1, 0).copy()
                     if t % 6 == 2:
-                        a[:, rng.integers(map_shape[0]), rng.integers(map_shape[1])] = rng.random(n_tiles)
+                        a[(slice(None), *[rng.integers(s) for s in map_shape])] = rng.random(n_tiles)
                 act_store = a
             elif rep == "wide" and raw_only:
                 a = [int(rng.integers(s)) for s in map_shape] + [int(rng.integers(n_tiles))]
                 act_store = np.array(a)
             else:
-                a = int(rng.integers(env.action_space.n))
+                a = int(rng.integers(env.action_space.n)) if action_p is None else \
+                    int(rng.choice(env.action_space.n, p=action_p))
                 act_store = a
             ob, r, done, trunc, info = env.step(a)
             acts.append(act_store)
@@ -175,8 +256,10 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
             stats.append([int(u._rep_stats[k]) for k in STAT_NAMES[problem]])
             p = getattr(rep_obj, "_pos", None)
             poss.append([int(v) for v in p] if p is not None and rep in ("narrow", "turtle") else [0] * len(map_shape))
-            grids.append(np.array(rep_obj._map, dtype=np.uint8))
             chg.append(int(info["changes"]))
+            if t % grid_every == 0 or done or (n_steps is not None and t + 1 == n_steps):
+                grids.append(np.array(rep_obj._map, dtype=np.uint8))
+                grid_s.append(t)
             if (t % obs_every == 0 or done) and not raw_only:
                 obs_l.append(np.asarray(ob, dtype=np.float64))
                 obs_s.append(t)
@@ -185,7 +268,7 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
         rec["actions"].append(np.array(acts)); rec["rewards"].append(rews); rec["dones"].append(dones)
         rec["stats"].append(stats); rec["pos"].append(poss); rec["grids"].append(np.stack(grids))
         rec["obs"].append(np.stack(obs_l) if obs_l else np.zeros((0,))); rec["obs_step"].append(obs_s)
-        rec["changes"].append(chg); rec["trg"].append(trg_e)
+        rec["changes"].append(chg); rec["trg"].append(trg_e); rec["grids_step"].append(grid_s)
     arrays = {"n_envs": np.array(n_envs)}
     for k, v in rec.items():
         if k == "obs0":
@@ -229,6 +312,40 @@ def main(which=None):
                                                   raw_only=True, n_envs=2,
                                                   init_p=[0.58, 0.3, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02]),
     }
+    SOK_W = {"player": 3, "crate": 2, "regions": 5, "ratio": 2, "dist-win": 0.5, "sol-length": 1}
+    SMB_W = {"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
+             "jumps-dist": 2, "dist-win": 5, "sol-length": 1}
+    MC_W = {"regions": 1, "path-length": 2, "n_jump": 3}
+    SOK_P = [0.45, 0.4, 0.05, 0.05, 0.05]
+    SOK_AP = [0.62, 0.12, 0.04, 0.11, 0.11]        # biased so the solver preconditions hold now and then
+    SMB_P = list(np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02]) / 0.95)
+    jobs.update({
+        "stats_sokoban": lambda: save_stats_fixture("sokoban", sokoban_grids()),
+        "stats_smb": lambda: save_stats_fixture("smb", smb_grids()),
+        "stats_maze3d": lambda: save_stats_fixture("minecraft_3D_maze", maze3d_grids(), "maze3d"),
+        "trace_sokoban_narrow": lambda: run_trace("sokoban_narrow", "sokoban", "narrow", (5, 5), (10, 10), SOK_W, seed=11,
+                                                  init_p=SOK_AP, action_p=SOK_AP, n_envs=6, obs_every=17),
+        "trace_sokoban_turtle": lambda: run_trace("sokoban_turtle", "sokoban", "turtle", (5, 5), (10, 10), SOK_W, seed=12,
+                                                  init_p=SOK_AP, n_envs=4, obs_every=17),
+        "trace_sokoban_cellular": lambda: run_trace("sokoban_cellular", "sokoban", "cellular", (5, 5), (5, 5), SOK_W,
+                                                    seed=13, raw_only=True, n_envs=3, init_p=SOK_P),
+        "trace_smb_narrow": lambda: run_trace("smb_narrow", "smb", "narrow", (116, 16), (32, 32), SMB_W, seed=14,
+                                              init_p=SMB_P, n_envs=2, n_steps=300, grid_every=100, obs_every=233),
+        "trace_smb_narrow_small": lambda: run_trace("smb_narrow_small", "smb", "narrow", (20, 16), (32, 32), SMB_W,
+                                                    seed=20, init_p=SMB_P, n_envs=2, grid_every=60, obs_every=233),
+        "trace_smb_turtle_small": lambda: run_trace("smb_turtle_small", "smb", "turtle", (14, 20), (28, 28), SMB_W,
+                                                    seed=15, init_p=SMB_P, n_envs=2, grid_every=50, obs_every=211),
+        "trace_maze3d_narrow": lambda: run_trace("maze3d_narrow", "minecraft_3D_maze", "narrow", (14, 14, 14),
+                                                 (14, 14, 14), MC_W, seed=16, raw_only=True, n_envs=2, n_steps=400,
+                                                 grid_every=100),
+        "trace_maze3d_turtle": lambda: run_trace("maze3d_turtle", "minecraft_3D_maze", "turtle", (7, 7, 7), (7, 7, 7),
+                                                 MC_W, seed=17, raw_only=True, n_envs=2, grid_every=50),
+        "trace_maze3d_wide_raw": lambda: run_trace("maze3d_wide_raw", "minecraft_3D_maze", "wide", (6, 6, 6), (6, 6, 6),
+                                                   MC_W, seed=18, raw_only=True, n_envs=2, grid_every=40),
+        "trace_maze3d_cellular": lambda: run_trace("maze3d_cellular", "minecraft_3D_maze", "cellular", (6, 6, 6),
+                                                   (6, 6, 6), MC_W, seed=19, raw_only=True, n_envs=2, n_steps=30,
+                                                   init_p=[0.5, 0.5]),
+    })
     for k, fn in jobs.items():
         if which and k not in which:
             continue

@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of minecraft_3D_maze get_stats (control-pcgrl @ 8bde536).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this; the product never does.
+
+Parity status: PINNED -- tests/test_oracle_golden.py checks it against tests/golden/stats_maze3d.npz
+(written by oracle/gen_golden.py from the real helper_3D.py / Minecraft3DmazeProblem) and, in the build
+container, tests/test_oracle_vs_reference.py compares it with the live reference on fresh random maps.
+
+Citations are relative to /root/reference/control_pcgrl/envs/.  Grids are int arrays [z, y, x]
+(0 = AIR, passable; 1 = DIRT).  The reference carries whole path *lists* through its FIFO queue
+(helper_3D.py:430,484); only three scalars per cell are observable in the outputs, so this restatement
+keeps, per cell: dist (= len(path), the start counts 1), njump, and the order of first recording
+(dict insertion order of `paths`).  SURVEY.md section F.
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import numpy as np
+
+DIRS = ((1, 0), (0, 1), (-1, 0), (0, -1))          # helper_3D.py:220
+
+
+def count_regions_3d(air):
+    """helper_3D.py:396-406 calc_num_regions + :354-383 _flood_fill: 6-connected AIR components."""
+    Z, Y, X = air.shape
+    seen = np.zeros_like(air, dtype=bool)
+    a = air.tolist()
+    s = seen.tolist()
+    n = 0
+    for z in range(Z):
+        for y in range(Y):
+            for x in range(X):
+                if a[z][y][x] and not s[z][y][x]:
+                    n += 1
+                    s[z][y][x] = True
+                    st = [(x, y, z)]
+                    while st:
+                        cx, cy, cz = st.pop()
+                        for dx, dy, dz in ((-1, 0, 0), (1, 0, 0), (0, -1, 0), (0, 1, 0), (0, 0, -1), (0, 0, 1)):
+                            nx, ny, nz = cx + dx, cy + dy, cz + dz
+                            if 0 <= nx < X and 0 <= ny < Y and 0 <= nz < Z and a[nz][ny][nx] and not s[nz][ny][nx]:
+                                s[nz][ny][nx] = True
+                                st.append((nx, ny, nz))
+    return n
+
+
+def moves(a, x, y, z, Z, Y, X):
+    """helper_3D.py:214-319 _passable: for each direction at most one foothold, by branch priority
+    walk (+1) -> step down (+2) -> step up (+2) -> jump level (+2) / up (+3) / down (+3).
+    Yields (nx, ny, nz, cost, is_jump).  `a[z][y][x]` is True for passable (AIR) cells.
+    The caller guarantees head-room at (x, y, z), i.e. z + 1 < Z (:443)."""
+    out = []
+    for dx, dy in DIRS:
+        nx, ny, nz = x + dx, y + dy, z
+        if nx < 0 or ny < 0 or nx >= X or ny >= Y:                     # :225
+            continue
+        if (nz == 0 or not a[nz - 1][ny][nx]) and a[nz][ny][nx] and a[nz + 1][ny][nx]:       # :229-237
+            out.append((nx, ny, nz, 1, 0))
+        elif ((nz - 1 == 0 or (nz - 1 > 0 and not a[nz - 2][ny][nx])) and a[nz - 1][ny][nx]
+              and a[nz][ny][nx] and a[nz + 1][ny][nx]):                                      # :243-252
+            out.append((nx, ny, nz - 1, 2, 0))
+        elif (nz + 2 < Z and not a[nz][ny][nx] and a[nz + 1][ny][nx] and a[nz + 2][ny][nx]
+              and a[nz + 2][y][x]):                                                           # :259-266
+            out.append((nx, ny, nz + 1, 2, 0))
+        else:
+            jx, jy, jz = x + 2 * dx, y + 2 * dy, z
+            if (nz - 2 >= 0 and nz + 2 < Z and a[nz + 2][ny][nx] and a[nz + 1][ny][nx] and a[nz][ny][nx]
+                    and a[nz - 1][ny][nx] and a[nz - 2][ny][nx] and a[nz + 2][y][x]
+                    and 0 <= jx < X and 0 <= jy < Y):                                        # :279-288
+                if a[jz + 1][jy][jx] and a[jz + 2][jy][jx] and a[jz][jy][jx] and not a[jz - 1][jy][jx]:
+                    out.append((jx, jy, jz, 2, 1))                                           # :289-296
+                elif (jz + 3 < Z and a[jz + 3][jy][jx] and a[jz + 2][jy][jx] and a[jz + 1][jy][jx]
+                      and not a[jz][jy][jx]):
+                    out.append((jx, jy, jz + 1, 3, 1))                                       # :297-304
+                elif a[jz][jy][jx] and a[jz + 1][jy][jx] and a[jz - 1][jy][jx] and not a[jz - 2][jy][jx]:
+                    out.append((jx, jy, jz - 1, 3, 1))                                       # :305-312
+    return out
+
+
+def search(a, sx, sy, sz, Z, Y, X, counters=None):
+    """helper_3D.py:422-490 run_dijkstra: FIFO label-correcting search.
+    Returns (order, dist, njump): `order` = cells in first-recording order (dict insertion order of
+    `paths`), dist[cell] = len(paths[cell]), njump[cell] = jumps[cell]."""
+    dist, njump, order = {}, {}, []
+    q = deque([(sx, sy, sz, 1, 0)])
+    pops = 0
+    maxq = 1
+    while q:
+        cx, cy, cz, ln, nj = q.popleft()
+        pops += 1
+        c = (cx, cy, cz)
+        old = dist.get(c, 0)
+        if 0 < old <= ln:                                              # :437-440
+            continue
+        if cz + 1 == Z or not a[cz + 1][cy][cx]:                       # :443-445 (never records)
+            continue
+        if old == 0:
+            order.append(c)
+        dist[c] = ln                                                   # :449
+        njump[c] = nj                                                  # :450
+        for nx, ny, nz, cost, j in moves(a, cx, cy, cz, Z, Y, X):      # :455-484
+            q.append((nx, ny, nz, ln + cost, nj + j))
+        if len(q) > maxq:
+            maxq = len(q)
+    if counters is not None:
+        counters["pops"] = max(counters.get("pops", 0), pops)
+        counters["maxq"] = max(counters.get("maxq", 0), maxq)
+        counters["searches"] = counters.get("searches", 0) + 1
+        counters["total_pops"] = counters.get("total_pops", 0) + pops
+    return order, dist, njump
+
+
+def _far(order, dist):
+    """np.argmax over the insertion-ordered lengths (helper_3D.py:538-541): first maximum."""
+    best, bd = None, -1
+    for c in order:
+        if dist[c] > bd:
+            best, bd = c, dist[c]
+    return best, bd
+
+
+def longest_path_3d(air, counters=None):
+    """helper_3D.py:503-563 calc_longest_path -> (path-length, n_jump).
+
+    Reproduces: candidate scan in (z, y, x) order (:22-29, :513); the three skip rules (:515-526);
+    `visited_map[np.array(list(paths.keys()))] = 1` (:531), which indexes axis 0 with every x, y and z
+    value of every recorded cell, i.e. marks whole z-planes (and raises IndexError when a value is
+    >= the depth, so only maps with X, Y <= Z work); n_jump overwritten by every processed component
+    while the length keeps the maximum (:553-560)."""
+    Z, Y, X = air.shape
+    a = air.tolist()
+    plane_visited = [False] * Z          # final_visited_map is only ever set by whole planes ...
+    cell_visited = set()                 # ... or by the single no-head-room cells of :520-522
+    final_value, n_jump = 0, 0
+    for z in range(Z):
+        for y in range(Y):
+            for x in range(X):
+                if not a[z][y][x]:
+                    continue
+                if plane_visited[z] or (x, y, z) in cell_visited:      # :515
+                    continue
+                if z + 1 == Z or not a[z + 1][y][x]:                   # :520-522
+                    cell_visited.add((x, y, z))
+                    continue
+                if z - 1 < 0 or a[z - 1][y][x]:                        # :525-526
+                    continue
+                order, dist, _ = search(a, x, y, z, Z, Y, X, counters)
+                for (cx, cy, cz) in order:                             # :531
+                    for v in (cx, cy, cz):
+                        if v >= Z:
+                            raise IndexError(f"index {v} is out of bounds for axis 0 with size {Z}")
+                        plane_visited[v] = True
+                far, _ = _far(order, dist)
+                order2, dist2, jumps2 = search(a, far[0], far[1], far[2], Z, Y, X, counters)
+                far2, max_dist = _far(order2, dist2)
+                n_jump = jumps2[far2]                                  # :553 (last component wins)
+                if max_dist > final_value:                             # :558
+                    final_value = max_dist
+    return final_value, n_jump
+
+
+def maze3d_stats(grid, counters=None):
+    """probs/minecraft/minecraft_3D_maze_prob.py:143-181."""
+    air = np.asarray(grid) == 0
+    length, nj = longest_path_3d(air, counters)
+    return {"regions": count_regions_3d(air), "path-length": int(length), "n_jump": int(nj)}

@@ -242,6 +242,36 @@ def problem_constants(problem, map_shape):
                          "path-length": (0, mp)},
             default_weights={"player": 3, "key": 3, "door": 3, "regions": 5, "enemies": 1,
                              "nearest-enemy": 1, "path-length": 1})
+    if problem == "sokoban":
+        # sokoban_prob.py:30-31 hard-codes 5x5 before sokoban_ctrl_prob.py:11-56 derives these (A-15)
+        w = h = 5
+        mp = np.ceil(w / 2 + 1) * h
+        return dict(
+            static_trgs={"player": 1, "crate": (2, 3), "regions": 1, "ratio": 0, "dist-win": 0, "sol-length": mp},
+            cond_bounds={"player": (1, w * h), "crate": (1, w * h / 2 - max(w, h)), "target": (1, w * h),
+                         "ratio": (0, w * h), "dist-win": (0, w * h * (w + h)), "sol-length": (0, 2 * mp),
+                         "regions": (0, w * h / 2)},
+            default_weights={"player": 3, "crate": 1, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1})
+    if problem == "smb":
+        # smb_prob.py:16-17 hard-codes 116x16 before smb_ctrl_prob.py:8-35 derives these (A-15)
+        w, h = 116, 16
+        msl = np.ceil(w) * 3
+        return dict(
+            static_trgs={"dist-floor": 0, "disjoint-tubes": 0, "enemies": (10, 30), "empty": (900, w * h),
+                         "noise": 0, "jumps": (20, w * h), "jumps-dist": 0, "dist-win": 0, "sol-length": msl},
+            cond_bounds={"dist-floor": (0, w * h), "disjoint-tubes": (0, w * h), "enemies": (0, w * h),
+                         "empty": (0, w), "noise": (0, w * h), "jumps": (0, w), "jumps-dist": (0, w * h),
+                         "dist-win": (0, w), "sol-length": (0, msl)},
+            default_weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
+                             "jumps-dist": 2, "dist-win": 5, "sol-length": 1})
+    if problem == "minecraft_3D_maze":
+        # minecraft_3D_maze_prob.py:33-35 hard-codes 15^3 before :43-69 derives these (A-15)
+        w = h = l = 15
+        mp = 2 * (h // 3) * (np.ceil(w / 2) * l + np.floor(l / 2))
+        return dict(
+            static_trgs={"regions": 1, "path-length": 10 * mp, "n_jump": 5},
+            cond_bounds={"regions": (0, np.ceil(w * l / 2 * h)), "path-length": (0, mp), "n_jump": (0, mp // 2)},
+            default_weights={"regions": 0, "path-length": 100, "n_jump": 100})
     raise KeyError(problem)
 
 

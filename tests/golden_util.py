@@ -35,9 +35,13 @@ class Trace:
         self.n_envs = int(z["n_envs"])
         self.envs = []
         for e in range(self.n_envs):
-            self.envs.append({k: z[f"{k}_{e}"] for k in
-                              ("grid0", "pos0", "stats0", "actions", "rewards", "dones", "stats", "pos", "grids",
-                               "obs", "obs_step", "changes", "trg")})
+            d = {k: z[f"{k}_{e}"] for k in
+                 ("grid0", "pos0", "stats0", "actions", "rewards", "dones", "stats", "pos", "grids",
+                  "obs", "obs_step", "changes", "trg")}
+            # newer traces keep the grid only every few steps: grid_at[t] -> index into d["grids"]
+            steps = z[f"grids_step_{e}"] if f"grids_step_{e}" in z else np.arange(len(d["rewards"]))
+            d["grid_at"] = {int(t): i for i, t in enumerate(steps)}
+            self.envs.append(d)
 
     def targets(self, e):
         return {k: float(v) for k, v in zip(self.target_names, self.envs[e]["trg"])}
@@ -45,3 +49,7 @@ class Trace:
 
 TRACES = ["binary_narrow", "binary_narrow_chg", "binary_turtle", "binary_wide_ctrl", "binary_cellular",
           "zelda_turtle", "zelda_narrow", "zelda_wide_raw"]
+TRACES_SEARCH = ["sokoban_narrow", "sokoban_turtle", "sokoban_cellular", "smb_narrow", "smb_narrow_small",
+                 "smb_turtle_small", "maze3d_narrow", "maze3d_turtle", "maze3d_wide_raw", "maze3d_cellular"]
+# traces that stop before the episode ends (n_steps cap in oracle/gen_golden.py)
+TRACES_OPEN_ENDED = ("binary_cellular", "smb_narrow", "maze3d_narrow", "maze3d_cellular")

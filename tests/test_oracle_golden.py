@@ -3,10 +3,11 @@ import numpy as np
 import pytest
 
 from oracle import pcgrl_oracle as O
-from tests.golden_util import TRACES, Trace, load_stats
+from tests.golden_util import TRACES, TRACES_OPEN_ENDED, TRACES_SEARCH, Trace, load_stats
 
 
-@pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda")])
+@pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
+                                          ("sokoban", "sokoban"), ("smb", "smb"), ("maze3d", "minecraft_3D_maze")])
 def test_stats_match_reference(name, problem):
     names, groups = load_stats(name)
     assert names == O.STAT_NAMES[problem]
@@ -50,7 +51,8 @@ def replay_oracle(tr: Trace, e: int):
         r, done, _ = env.step(a)
         assert done == bool(d["dones"][t]), (tr.name, e, t)
         assert O.stats_vector(tr.problem, env.stats) == [int(v) for v in d["stats"][t]], (tr.name, e, t)
-        assert np.array_equal(env.grid, d["grids"][t]), (tr.name, e, t)
+        if t in d["grid_at"]:
+            assert np.array_equal(env.grid, d["grids"][d["grid_at"][t]]), (tr.name, e, t)
         assert env.changes == int(d["changes"][t])
         assert r == pytest.approx(float(d["rewards"][t]), rel=1e-6, abs=1e-9), (tr.name, e, t)
         if tr.rep in ("narrow", "turtle"):
@@ -66,10 +68,10 @@ def replay_oracle(tr: Trace, e: int):
                 got = np.concatenate([ch, got], axis=-1)
             assert got.shape == want.shape
             np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
-    assert bool(d["dones"][-1]) or tr.name in ("binary_cellular",)
+    assert bool(d["dones"][-1]) or tr.name in TRACES_OPEN_ENDED
 
 
-@pytest.mark.parametrize("name", TRACES)
+@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH)
 def test_trace_matches_reference(name):
     tr = Trace(name)
     for e in range(tr.n_envs):
