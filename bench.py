@@ -37,6 +37,11 @@ WORKLOADS = {
     "binary-turtle-16x16": ("binary", "turtle", (16, 16), (32, 32), None, 1 << 20),
     "zelda-turtle-7x11": ("zelda", "turtle", (7, 11), (22, 22), None, 1 << 20),
     "zelda-narrow-7x11": ("zelda", "narrow", (7, 11), (22, 22), None, 1 << 20),
+    # BASELINE.json configs 4 and 5 (search-based stats: warp-per-grid kernels)
+    "minecraft_3D_maze-narrow-14x14x14": ("minecraft_3D_maze", "narrow", (14, 14, 14), (14, 14, 14), None, 1 << 16),
+    "sokoban-cellular-5x5": ("sokoban", "cellular", (5, 5), (5, 5), None, 1 << 20),
+    "sokoban-narrow-5x5": ("sokoban", "narrow", (5, 5), (10, 10), None, 1 << 20),
+    "smb-narrow-116x16": ("smb", "narrow", (116, 16), (32, 32), None, 1 << 16),
 }
 METRIC = "env-steps/sec"
 UNIT = "env-steps/s"
@@ -118,24 +123,28 @@ def _cpu_worker(args):
     rng = np.random.default_rng(seed)
     from control_pcgrl_b200.config import TASK_DEFAULTS
     weights = TASK_DEFAULTS[problem]["weights"]
-    n_tiles = {"binary": 2, "zelda": 8}[problem]
-    n_act = {"narrow": n_tiles, "turtle": 4 + n_tiles, "wide": obs_window[0] * obs_window[1] * n_tiles}[rep]
+    from oracle.pcgrl_oracle import INIT_PROBS, TILES
+    n_tiles = len(TILES[problem])
+    n_act = {"narrow": n_tiles, "turtle": 4 + n_tiles, "wide": obs_window[0] * obs_window[1] * n_tiles,
+             "cellular": 0}[rep]
     steps = 0
     if use_ref:
         from oracle import refshim as R
         cfg = R.make_cfg(problem, rep, shape, obs_window=obs_window, weights=weights, controls=controls)
-        env = R.make_wrapped_env(cfg)
+        # the reference's wrapped stacks are broken upstream for 3D problems and for cellular (SURVEY A-9, A-22):
+        # those run the raw env under ControlWrapper
+        env = R.make_wrapped_env(cfg, raw_only=(len(shape) == 3 or rep == "cellular"))
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < seconds:
             env.reset()
             done = False
             while not done and time.perf_counter() - t0 < seconds:
-                _, _, done, _, _ = env.step(int(rng.integers(n_act)))
+                a = rng.random((n_tiles, *shape), dtype=np.float32) if rep == "cellular" else int(rng.integers(n_act))
+                _, _, done, _, _ = env.step(a)
                 steps += 1
         return steps, time.perf_counter() - t0
     from oracle import pcgrl_oracle as O
     env = O.OracleEnv(problem, rep, shape, weights=weights, controls=controls)
-    from oracle.pcgrl_oracle import INIT_PROBS
     t0 = time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         p = rng.random(n_tiles)
@@ -143,7 +152,10 @@ def _cpu_worker(args):
         env.reset(grid, pos=[int(rng.random() * s) for s in shape])
         done = False
         while not done and time.perf_counter() - t0 < seconds:
-            a = int(rng.integers(n_act))
+            if rep == "cellular":
+                a = rng.random((n_tiles, *shape), dtype=np.float32)
+            else:
+                a = int(rng.integers(n_act))
             if rep == "wide":
                 a = O.actionmap_unravel(a, obs_window[0], obs_window[1], n_tiles)
             _, done, _ = env.step(a)
@@ -207,18 +219,32 @@ def main():
     lib = _lib.load()
 
     cfg = P.make_config(problem, rep, map_shape=shape, obs_window=obs_window, controls=controls)
-    env = P.BatchedPcgrlEnv(cfg, n_envs, device=dev, env_offset=rank * n_envs, seed=a.seed, auto_reset=True)
+    env = P.BatchedPcgrlEnv(cfg, n_envs, device=dev, env_offset=rank * n_envs, seed=a.seed, auto_reset=True,
+                            action_kind="ca_tiles" if rep == "cellular" else None)
     if controls:
         env.sample_uniform_targets()
     env.reset()
     n_act = {"narrow": env.n_tiles, "turtle": 4 + env.n_tiles,
-             "wide": obs_window[0] * obs_window[1] * env.n_tiles}[rep]
+             "wide": obs_window[0] * obs_window[1] * env.n_tiles, "cellular": 0}[rep]
     gen = torch.Generator(device=dev).manual_seed(a.seed + rank)
     # one distinct uniform-random action batch per step, all resident in HBM before the timed region.
     # (Cycling a small pool would be wrong: the narrow scan revisits a cell every 256 steps and would replay
     # the same action on it, so nothing would change after the first board scan.)
-    POOL = min(a.steps + a.warmup, max(16, int(6e9 // (4 * n_envs))))
-    act_all = torch.randint(0, n_act, (POOL, n_envs), generator=gen, device=dev, dtype=torch.int32)
+    shape_a, dt_a = env.action_shape_dtype()
+    bytes_a = int(np.prod(shape_a)) * np.dtype(dt_a).itemsize
+    POOL = min(a.steps + a.warmup, max(16, int(6e9 // bytes_a)))
+    if rep == "cellular":
+        # cellular: each action is a whole next map (pre-argmaxed int8 tiles), drawn from the problem's tile
+        # distribution so that the solver preconditions of sokoban hold as often as in generated levels
+        cdf = torch.tensor(np.cumsum(env.spec.init_probs) / np.sum(env.spec.init_probs), device=dev,
+                           dtype=torch.float32)
+        act_all = torch.empty((POOL, *shape_a), device=dev, dtype=torch.int8)
+        for i in range(POOL):
+            u = torch.rand(shape_a, generator=gen, device=dev)
+            act_all[i] = torch.searchsorted(cdf, u).clamp_(max=env.n_tiles - 1).to(torch.int8)
+            act_all[i, :, env.cells:] = 0
+    else:
+        act_all = torch.randint(0, n_act, (POOL, n_envs), generator=gen, device=dev, dtype=torch.int32)
     act_pool = [act_all[i] for i in range(POOL)]
     step_no = [0]
     # ~300 MB scratch to push the working set out of L2 is unnecessary at the default size (grids alone are
@@ -277,11 +303,13 @@ def main():
     # ---- end-to-end arm (host buffers through the public API) -----------------------------------
     e2e = None
     if not a.no_e2e:
-        shape_a, dt_a = env.action_shape_dtype()
         rng = np.random.default_rng(a.seed + 100 + rank)
         k_e2e = max(3, min(a.steps, 200))
-        HP = min(k_e2e + 3, max(8, int(2e9 // (4 * n_envs))))
-        host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(HP)]
+        HP = min(k_e2e + 3, max(8, int(2e9 // bytes_a)))
+        if rep == "cellular":
+            host_acts = [act_pool[i % POOL].cpu().numpy() for i in range(HP)]
+        else:
+            host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(HP)]
         for i in range(3):
             env.step_host(host_acts[i % HP])
         barrier()
@@ -300,7 +328,7 @@ def main():
         te = torch.tensor([max(e0.elapsed_time(e1) * 1e-3, wall)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = int(np.prod(shape_a)) * np.dtype(dt_a).itemsize
+        h2d = bytes_a
         d2h = n_envs * (4 + 1 + 4 * env.K)
         e2e = {"value": world * n_envs * k_e2e / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e,
@@ -319,7 +347,7 @@ def main():
     per_launch_ms = kern_ms / a.steps
     achieved = step_bytes * n_envs / (per_launch_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_step_bitboard", "algorithmic_bytes_per_env_step": step_bytes,
+                "traffic": None, "kernel": "k_step_bitboard" if problem in ("binary", "zelda") else "k_step_search", "algorithmic_bytes_per_env_step": step_bytes,
                 "kernel_ms_per_launch": per_launch_ms, "peak_source": peak_src,
                 "note": "HBM bound is loose for this path; the binding resource is SM issue (see profiles/)"}
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")

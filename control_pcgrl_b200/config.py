@@ -58,6 +58,16 @@ TASK_DEFAULTS = {
     "zelda": dict(map_shape=(7, 11), obs_window=(22, 22),
                   weights={"player": 3, "key": 3, "door": 3, "regions": 5, "enemies": 1, "nearest-enemy": 2,
                            "path-length": 1}),
+    # no configs/task/*.yaml upstream for these: the structured configs of configs/config.py:89-165
+    # (SokobanConfig, SMBConfig, MinecraftMazeConfig); sokoban's 5x5 is the Problem constructor's size
+    "sokoban": dict(map_shape=(5, 5), obs_window=(10, 10),
+                    weights={"player": 3, "crate": 2, "target": 2, "regions": 5, "ratio": 2, "dist-win": 0,
+                             "sol-length": 1}),
+    "smb": dict(map_shape=(116, 16), obs_window=(32, 32),
+                weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
+                         "jumps-dist": 2, "dist-win": 5, "sol-length": 1}),
+    "minecraft_3D_maze": dict(map_shape=(15, 15, 15), obs_window=(30, 30, 30),
+                              weights={"path-length": 100, "n_jump": 100, "regions": 0}),
 }
 
 

@@ -9,6 +9,7 @@
 
 namespace pcgrl {
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
+cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
 
 static thread_local std::string g_err;
@@ -103,7 +104,11 @@ static int check_state(const pcgrl_state* st) {
 
 static int run(const KParams& p, int problem, void* stream) {
     bool supported = false;
-    cudaError_t e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
+    cudaError_t e;
+    if (problem == PCGRL_PROB_MINECRAFT_3D_MAZE)
+        e = launch_maze3d(p, (cudaStream_t)stream, supported);
+    else
+        e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
     if (!supported) return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet");
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -17,6 +17,7 @@
 //      inside a word for x+-1, funnel shifts between neighbouring words for y+-1, no cross-lane traffic;
 //   D  thread-per-env: fp64 loss(new stats) - loss(old stats), write stats / reward / done / counters.
 #include "pcgrl_device.cuh"
+#include "step_common.cuh"
 
 namespace pcgrl {
 
@@ -252,151 +253,6 @@ struct ZeldaMachine {
 };
 
 // ------------------------------------------------------------------------------------------------
-// phase A helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int cell_index(const KParams& p, int a0, int a1, int a2) {
-    return (a0 * p.d1 + a1) * p.d2 + a2;
-}
-
-// Apply one non-cellular action to env `gid`.  Returns change (0/1); updates pos / n_step in HBM.
-__device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
-    int8_t* grid = p.grids + gid * p.row_stride;
-    int32_t* pos = p.pos + gid * 3;
-    int change = 0;
-    if (p.rep == PCGRL_REP_NARROW) {
-        // reps/narrow_rep.py:89-102: write at _pos, then _pos = coords[n_step % N], then n_step += 1
-        const int a = ((const int32_t*)p.actions)[gid];
-        const int c = cell_index(p, pos[0], pos[1], pos[2]);
-        if ((unsigned)a >= (unsigned)p.n_tiles) {
-            if (p.status) atomicOr(p.status, 1);
-        } else {
-            const int old = grid[c];
-            change = old != a;
-            if (change) grid[c] = (int8_t)a;
-        }
-        const int ns = p.n_step[gid];
-        const int k = ns % p.cells;
-        pos[2] = k % p.d2;
-        pos[1] = (k / p.d2) % p.d1;
-        pos[0] = k / (p.d2 * p.d1);
-        p.n_step[gid] = ns + 1;
-    } else if (p.rep == PCGRL_REP_TURTLE) {
-        // reps/turtle_rep.py:87-107: 0..3 move along axis 0 / axis 1 (clamped), >= 4 writes tile a-4
-        const int a = ((const int32_t*)p.actions)[gid];
-        if (a >= 0 && a < 4) {
-            const int axis = a >> 1;
-            const int lim = (axis == 0 ? p.d0 : p.d1) - 1;
-            int v = pos[axis] + ((a & 1) ? 1 : -1);
-            pos[axis] = v < 0 ? 0 : (v > lim ? lim : v);
-        } else if (a >= 4 && a - 4 < p.n_tiles) {
-            const int c = cell_index(p, pos[0], pos[1], pos[2]);
-            const int t = a - 4;
-            const int old = grid[c];
-            change = old != t;
-            if (change) grid[c] = (int8_t)t;
-        } else if (p.status) {
-            atomicOr(p.status, 1);
-        }
-    } else {  // PCGRL_REP_WIDE
-        int q0, q1, q2 = 0, v;
-        if (p.action_kind == PCGRL_ACT_WIDE_FLAT) {
-            // wrappers.py:304-323: (y, x, v) = unravel(a, (h, w, C)); env.step([x, y, v]) -> _map[x, y] = v
-            const int a = ((const int32_t*)p.actions)[gid];
-            v = a % p.n_tiles;
-            const int x = (a / p.n_tiles) % p.act_w;
-            const int y = a / (p.n_tiles * p.act_w);
-            q0 = x;
-            q1 = y;
-            if (a < 0 || y >= p.act_h) q0 = -1;
-        } else {
-            const int32_t* a = (const int32_t*)p.actions + gid * (p.ndim + 1);
-            q0 = a[0];
-            q1 = a[1];
-            if (p.ndim == 3) q2 = a[2];
-            v = a[p.ndim];
-        }
-        if ((unsigned)q0 >= (unsigned)p.d0 || (unsigned)q1 >= (unsigned)p.d1 || (unsigned)q2 >= (unsigned)p.d2 ||
-            (unsigned)v >= (unsigned)p.n_tiles) {
-            if (p.status) atomicOr(p.status, 1);
-        } else {
-            const int c = cell_index(p, q0, q1, q2);
-            const int old = grid[c];
-            change = old != v;
-            if (change) grid[c] = (int8_t)v;
-            pos[0] = q0;
-            pos[1] = q1;
-            pos[2] = q2;
-        }
-    }
-    return change;
-}
-
-// Episode start for env `gid` (thread-per-env): grid from src or Philox, counters, start position.
-__device__ void reset_env(const KParams& p, int64_t gid) {
-    int8_t* grid = p.grids + gid * p.row_stride;
-    const uint64_t genv = (uint64_t)(p.env_offset + gid);
-    const uint2 key = make_uint2((uint32_t)p.seed, (uint32_t)(p.seed >> 32));
-    if (p.src_grids) {
-        const uint4* s = (const uint4*)(p.src_grids + gid * p.row_stride);
-        uint4* d = (uint4*)grid;
-        for (int i = 0; i < p.row_stride / 16; ++i) d[i] = s[i];
-    } else {
-        float cdf[PCGRL_MAX_TILES];
-        if (p.init_random_probs) {
-            // pcgrl_env.py:162-164 + helper.get_int_prob: per-episode tile probabilities U(0,1)^C, normalised
-            float tot = 0.f;
-            for (int t0 = 0; t0 < p.n_tiles; t0 += 4) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
-                                                         0x80000000u + t0), key);
-                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-                for (int j = 0; j < 4 && t0 + j < p.n_tiles; ++j) {
-                    tot += u01(rr[j]) + 1e-7f;
-                    cdf[t0 + j] = tot;
-                }
-            }
-            for (int t = 0; t < p.n_tiles; ++t) cdf[t] /= tot;
-        } else {
-            for (int t = 0; t < p.n_tiles; ++t) cdf[t] = p.init_cdf[t];
-        }
-        for (int c0 = 0; c0 < p.row_stride; c0 += 16) {
-            uint32_t w[4] = {0, 0, 0, 0};
-            for (int q = 0; q < 4; ++q) {
-                const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
-                                                         (uint32_t)(c0 / 4 + q)), key);
-                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-                for (int j = 0; j < 4; ++j) {
-                    const int c = c0 + q * 4 + j;
-                    int t = 0;
-                    if (c < p.cells) {
-                        const float u = u01(rr[j]);
-                        while (t < p.n_tiles - 1 && u >= cdf[t]) ++t;
-                    }
-                    w[q] |= (uint32_t)t << (8 * j);
-                }
-            }
-            *(uint4*)(grid + c0) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-    int32_t* pos = p.pos + gid * 3;
-    pos[0] = pos[1] = pos[2] = 0;
-    if (p.src_pos) {
-        pos[0] = p.src_pos[gid * 3 + 0];
-        pos[1] = p.src_pos[gid * 3 + 1];
-        pos[2] = p.src_pos[gid * 3 + 2];
-    } else if (p.rep == PCGRL_REP_TURTLE) {
-        // reps/turtle_rep.py:41-44: int(random() * dim) per axis
-        const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch, 0xC0000000u), key);
-        pos[0] = min((int)(u01(r.x) * p.d0), p.d0 - 1);
-        pos[1] = min((int)(u01(r.y) * p.d1), p.d1 - 1);
-        if (p.ndim == 3) pos[2] = min((int)(u01(r.z) * p.d2), p.d2 - 1);
-    }
-    p.n_step[gid] = 0;
-    p.iteration[gid] = 0;
-    p.changes[gid] = 0;
-    // reward / done are step outputs: an auto-reset must not erase the finishing step's values
-}
-
-// ------------------------------------------------------------------------------------------------
 // 16 tile codes (one 128-bit load) -> one 16-bit membership mask per plane (bit i = cell i in the plane).
 // Tile codes are < 8 for every bit-board problem, so a plane is an 8-entry 0/1 table that PRMT looks up
 // for 4 cells at once; the multiply then gathers the four 0/1 bytes into bits 24..27.
@@ -456,83 +312,8 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     }
     __syncthreads();
 
-    // ---------------- cellular: whole-map rewrite, cooperative over the CTA -----------------------
-    if (p.mode == MODE_STEP && p.rep == PCGRL_REP_CELLULAR) {
-        if (p.action_kind == PCGRL_ACT_CA_TILES) {
-            const int chunks = p.row_stride / 16;
-            for (int i = tid; i < tile_n * chunks; i += THREADS) {
-                const int e = i / chunks, c = i - e * chunks;
-                const int64_t off = (base + e) * p.row_stride + c * 16;
-                const uint4 nw = *(const uint4*)((const int8_t*)p.actions + off);
-                uint4* dst = (uint4*)(p.grids + off);
-                const uint4 od = *dst;
-                if (nw.x != od.x || nw.y != od.y || nw.z != od.z || nw.w != od.w) {
-                    *dst = nw;
-                    s_flag[e] = 1;
-                }
-            }
-        } else {  // PCGRL_ACT_CA_LOGITS: float32 [N, C, cells]; argmax over C, ties -> lowest index
-            for (int i = tid; i < tile_n * p.cells; i += THREADS) {
-                const int e = i / p.cells, c = i - e * p.cells;
-                const float* lg = (const float*)p.actions + (base + e) * (int64_t)p.n_tiles * p.cells + c;
-                float best = lg[0];
-                int bi = 0;
-                for (int t = 1; t < p.n_tiles; ++t) {
-                    const float v = lg[(int64_t)t * p.cells];
-                    if (v > best) {
-                        best = v;
-                        bi = t;
-                    }
-                }
-                int8_t* g = p.grids + (base + e) * p.row_stride + c;
-                if (*g != bi) {
-                    *g = (int8_t)bi;
-                    s_flag[e] = 1;
-                }
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---------------- phase A: per-env action / reset, counters, change flag -----------------------
-    for (int e = tid; e < TILE; e += THREADS) {
-        bool need = false;
-        if (e < tile_n) {
-            const int64_t gid = base + e;
-            if (p.mode == MODE_STEP) {
-                int change = (p.rep == PCGRL_REP_CELLULAR) ? (int)s_flag[e] : apply_action(p, gid);
-                const int it = p.iteration[gid] + 1;   // pcgrl_env.py:279
-                const int ch = p.changes[gid] + change;
-                p.iteration[gid] = it;
-                if (change) p.changes[gid] = ch;
-                bool done = it > p.max_iterations;     // :307
-                if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
-                p.done[gid] = done;
-                if (p.changed) p.changed[gid] = change != 0;
-                need = change != 0;                    // :314 stats only when the map changed
-                if (!need) p.reward[gid] = 0.f;
-            } else if (p.mode == MODE_RESET) {
-                need = p.mask == nullptr || p.mask[gid] != 0;
-                if (need) reset_env(p, gid);
-            } else {
-                need = true;
-            }
-        }
-        // warp-aggregated append to the compact work list
-        const unsigned bal = __ballot_sync(0xffffffffu, need);
-        if (bal) {
-            const int lane = tid & 31;
-            int off = 0;
-            if (lane == 0) off = atomicAdd(&s_count, __popc(bal));
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (need) {
-                const int slot = off + __popc(bal & ((1u << lane) - 1u));
-                s_list[slot] = (int16_t)e;
-                s_slot[e] = (int16_t)slot;
-            }
-        }
-    }
-    __syncthreads();
+    // ---------------- phase A: representation update / reset, counters, change flag ----------------
+    phase_a<THREADS, TILE>(p, base, tile_n, s_list, s_slot, s_flag, &s_count);
     const int M = s_count;
 
     // ---------------- phase B: coalesced 128-bit grid loads -> per-plane bit-boards in smem --------
@@ -612,30 +393,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     __syncthreads();
 
     // ---------------- phase D: reward (fp64), stats / outputs --------------------------------------
-    for (int e = tid; e < tile_n; e += THREADS) {
-        const int slot = s_slot[e];
-        if (slot < 0) continue;
-        const int64_t gid = base + e;
-        int32_t nw[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) nw[k] = s_stats[slot * K + k];
-        if (p.mode == MODE_STATS) {
-#pragma unroll
-            for (int k = 0; k < K; ++k) p.stats_out[gid * K + k] = nw[k];
-            continue;
-        }
-        int32_t* st = p.stats + gid * K;
-        if (p.mode == MODE_STEP) {
-            int32_t od[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) od[k] = st[k];
-            const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
-            const double r = control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
-            p.reward[gid] = (float)r;
-        }
-#pragma unroll
-        for (int k = 0; k < K; ++k) st[k] = nw[k];
-    }
+    phase_d<THREADS, K>(p, base, tile_n, s_slot, s_stats);
 }
 
 // ------------------------------------------------------------------------------------------------

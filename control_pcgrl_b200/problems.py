@@ -61,7 +61,57 @@ def zelda_spec(map_shape):
                         "path-length": 1})
 
 
-_SPECS = {"binary": binary_spec, "zelda": zelda_spec}
+def sokoban_spec(map_shape):
+    """sokoban/sokoban_prob.py:26-52 + sokoban/sokoban_ctrl_prob.py:11-56.  The constructor hard-codes 5x5
+    before the targets / bounds are derived; adjust_param later overwrites _height/_width only (SURVEY A-15)."""
+    w = h = 5
+    max_path = float(math.ceil(w / 2 + 1) * h)
+    return ProblemSpec(
+        name="sokoban", tiles=["empty", "solid", "player", "crate", "target"],
+        stat_names=["player", "crate", "target", "regions", "dist-win", "sol-length", "ratio"],
+        init_probs=[0.45, 0.4, 0.05, 0.05, 0.05], border_tile="solid", ndim=2,
+        static_trgs=OrderedDict([("player", 1), ("crate", (2, 3)), ("regions", 1), ("ratio", 0), ("dist-win", 0),
+                                 ("sol-length", max_path)]),
+        cond_bounds={"player": (1, w * h), "crate": (1, w * h / 2 - max(w, h)), "target": (1, w * h),
+                     "ratio": (0, w * h), "dist-win": (0, w * h * (w + h)), "sol-length": (0, 2 * max_path),
+                     "regions": (0, w * h / 2)},
+        reward_weights={"player": 3, "crate": 1, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1})
+
+
+def smb_spec(map_shape):
+    """smb/smb_prob.py:12-37 + smb/smb_ctrl_prob.py:8-35 (targets / bounds from the hard-coded 116x16)."""
+    w, h = 116, 16
+    max_sol = float(math.ceil(w) * 3)
+    return ProblemSpec(
+        name="smb", tiles=["empty", "solid", "enemy", "brick", "question", "coin", "tube"],
+        stat_names=["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist", "dist-win",
+                    "sol-length"],
+        init_probs=[0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02], border_tile="empty", ndim=2,
+        static_trgs=OrderedDict([("dist-floor", 0), ("disjoint-tubes", 0), ("enemies", (10, 30)),
+                                 ("empty", (900, w * h)), ("noise", 0), ("jumps", (20, w * h)), ("jumps-dist", 0),
+                                 ("dist-win", 0), ("sol-length", max_sol)]),
+        cond_bounds={"dist-floor": (0, w * h), "disjoint-tubes": (0, w * h), "enemies": (0, w * h), "empty": (0, w),
+                     "noise": (0, w * h), "jumps": (0, w), "jumps-dist": (0, w * h), "dist-win": (0, w),
+                     "sol-length": (0, max_sol)},
+        reward_weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
+                        "jumps-dist": 2, "dist-win": 5, "sol-length": 1})
+
+
+def minecraft_3d_maze_spec(map_shape):
+    """minecraft/minecraft_3D_maze_prob.py:26-81 (targets / bounds from the hard-coded 15^3)."""
+    w = h = l = 15
+    max_path = float(2 * (h // 3) * (math.ceil(w / 2) * l + math.floor(l / 2)))
+    return ProblemSpec(
+        name="minecraft_3D_maze", tiles=["AIR", "DIRT"], stat_names=["regions", "path-length", "n_jump"],
+        init_probs=[1.0, 0.0], border_tile="DIRT", ndim=3,
+        static_trgs=OrderedDict([("regions", 1), ("path-length", 10 * max_path), ("n_jump", 5)]),
+        cond_bounds={"regions": (0, float(math.ceil(w * l / 2 * h))), "path-length": (0, max_path),
+                     "n_jump": (0, max_path // 2)},
+        reward_weights={"regions": 0, "path-length": 100, "n_jump": 100})
+
+
+_SPECS = {"binary": binary_spec, "zelda": zelda_spec, "sokoban": sokoban_spec, "smb": smb_spec,
+          "minecraft_3D_maze": minecraft_3d_maze_spec}
 
 
 def get_spec(problem: str, map_shape) -> ProblemSpec:

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.golden_util import TRACES, Trace, load_stats
+from tests.golden_util import TRACES, TRACES_SEARCH, Trace, load_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -20,23 +20,25 @@ def _mk(problem, rep, map_shape, n, **kw):
     return P.BatchedPcgrlEnv(cfg, n, **extra)
 
 
-@pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda")])
+@pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
+                                          ("maze3d", "minecraft_3D_maze"), ("sokoban", "sokoban"), ("smb", "smb")])
 def test_stats_kernel_matches_reference_fixtures(name, problem):
     _, groups = load_stats(name)
     total = 0
     for grids, stats in groups:
         shape = grids.shape[1:]
-        if max(shape) > 32:
+        if max(shape) > 32 and problem in ("binary", "zelda"):
             continue
         env = _mk(problem, "narrow", shape, 1)
         got = env.compute_stats(grids).cpu().numpy()
         bad = np.flatnonzero((got != stats).any(axis=1))
         assert bad.size == 0, (name, shape, bad[:5], got[bad[:5]], stats[bad[:5]])
+        env.check_status()
         total += len(grids)
     assert total > 100
 
 
-@pytest.mark.parametrize("name", TRACES)
+@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH)
 def test_trace_replay_matches_reference(name):
     tr = Trace(name)
     n = tr.n_envs
@@ -75,7 +77,8 @@ def test_trace_replay_matches_reference(name):
             d = tr.envs[e]
             assert bool(done[e]) == bool(d["dones"][t]), (name, e, t)
             assert stats[e].tolist() == [int(v) for v in d["stats"][t]], (name, e, t)
-            assert np.array_equal(maps[e].astype(np.uint8), d["grids"][t]), (name, e, t)
+            if t in d["grid_at"]:
+                assert np.array_equal(maps[e].astype(np.uint8), d["grids"][d["grid_at"][t]]), (name, e, t)
             assert int(changes[e]) == int(d["changes"][t]), (name, e, t)
             assert reward[e] == pytest.approx(float(d["rewards"][t]), rel=1e-6, abs=1e-7), (name, e, t)
             if tr.rep in ("narrow", "turtle"):

@@ -50,7 +50,8 @@ def test_problem_tables_known_constants():
 
 @pytest.mark.needs_reference
 @pytest.mark.parametrize("problem,shape", [("binary", (16, 16)), ("binary", (10, 14)), ("zelda", (7, 11)),
-                                           ("zelda", (16, 16))])
+                                           ("zelda", (16, 16)), ("sokoban", (5, 5)), ("sokoban", (6, 7)),
+                                           ("smb", (116, 16)), ("minecraft_3D_maze", (14, 14, 14))])
 def test_problem_tables_match_reference_classes(problem, shape):
     from oracle import refshim as R
     from oracle.gen_golden import ref_problem
