@@ -110,7 +110,8 @@ class BatchedPcgrlEnv:
         self.changed = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
-        self.scratch = torch.empty(max(int(nscratch), 0), dtype=torch.uint8, device=dev) if nscratch > 0 else None
+        # zero-initialised once: the solver kernels keep generation counters for their hash tables in it
+        self.scratch = torch.zeros(int(nscratch), dtype=torch.uint8, device=dev) if nscratch > 0 else None
         self._actions_dev = None
         self._pinned = {}
         self._epoch = 0

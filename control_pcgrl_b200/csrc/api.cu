@@ -10,6 +10,10 @@
 namespace pcgrl {
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
+cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
+cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported);
+int64_t sokoban_scratch_bytes();
+int64_t smb_scratch_bytes();
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
 
 static thread_local std::string g_err;
@@ -107,6 +111,10 @@ static int run(const KParams& p, int problem, void* stream) {
     cudaError_t e;
     if (problem == PCGRL_PROB_MINECRAFT_3D_MAZE)
         e = launch_maze3d(p, (cudaStream_t)stream, supported);
+    else if (problem == PCGRL_PROB_SOKOBAN)
+        e = launch_sokoban(p, (cudaStream_t)stream, supported);
+    else if (problem == PCGRL_PROB_SMB)
+        e = launch_smb(p, (cudaStream_t)stream, supported);
     else
         e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
     if (!supported) return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet");
@@ -133,7 +141,10 @@ int32_t pcgrl_config_check(pcgrl_config* cfg) {
 int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
     if (check(cfg)) return -1;
     (void)n_envs;
-    return 0;  // the bit-board problems keep all search state in registers / shared memory
+    // node pools / heaps / hash tables of the solver problems: one slice per resident search warp
+    if (cfg->problem == PCGRL_PROB_SOKOBAN) return sokoban_scratch_bytes();
+    if (cfg->problem == PCGRL_PROB_SMB) return smb_scratch_bytes();
+    return 0;  // binary / zelda / minecraft keep all search state in registers / shared memory
 }
 
 int64_t pcgrl_step_bytes(const pcgrl_config* c) {

@@ -269,64 +269,7 @@ struct Maze3DProb {
         }
 
         // ---- calc_num_regions (helper_3D.py:396-406): 6-neighbour AIR components by bit-board flood fill ---
-        uint16_t* avail = c.best;
-        uint16_t* f0 = c.best + R;
-        uint16_t* f1 = c.best + 2 * R;
-        int regions = 0;
-        {
-            int iso_cnt = 0;
-            for (int r = lane; r < R; r += 32) {
-                const int z = r / Y, y = r - z * Y;
-                const uint32_t a = c.row[r];
-                const uint32_t nb = (a << 1) | (a >> 1) | (y > 0 ? c.row[r - 1] : 0u) | (y < Y - 1 ? c.row[r + 1] : 0u) |
-                                    (z > 0 ? c.row[r - Y] : 0u) | (z < Z - 1 ? c.row[r + Y] : 0u);
-                const uint32_t iso = a & ~nb;                     // single-cell components
-                iso_cnt += __popc(iso);
-                avail[r] = (uint16_t)(a & ~iso);
-                f0[r] = 0;
-            }
-            regions = __reduce_add_sync(0xffffffffu, iso_cnt);
-            __syncwarp();
-        }
-        for (;;) {
-            int first = 0xFFFF;
-            for (int r = lane; r < R; r += 32)
-                if (avail[r]) {
-                    first = r;
-                    break;
-                }
-            first = __reduce_min_sync(0xffffffffu, first);
-            if (first == 0xFFFF) break;
-            ++regions;
-            if (lane == 0) {
-                const uint32_t a = avail[first], bit = a & (0u - a);
-                f0[first] = (uint16_t)bit;
-                avail[first] = (uint16_t)(a ^ bit);
-            }
-            __syncwarp();
-            uint16_t *cur = f0, *nxt = f1;
-            for (;;) {
-                uint32_t any = 0;
-                for (int r = lane; r < R; r += 32) {
-                    const int z = r / Y, y = r - z * Y;
-                    const uint32_t f = cur[r];
-                    const uint32_t nb = (f << 1) | (f >> 1) | (y > 0 ? cur[r - 1] : 0u) | (y < Y - 1 ? cur[r + 1] : 0u) |
-                                        (z > 0 ? cur[r - Y] : 0u) | (z < Z - 1 ? cur[r + Y] : 0u);
-                    const uint32_t a = avail[r], nf = nb & a;
-                    nxt[r] = (uint16_t)nf;
-                    avail[r] = (uint16_t)(a ^ nf);
-                    any |= nf;
-                }
-                __syncwarp();
-                uint16_t* t = cur;
-                cur = nxt;
-                nxt = t;
-                if (!__any_sync(0xffffffffu, any != 0)) break;
-            }
-            // the last frontier written is all zero, and so must f0 be for the next component
-            for (int r = lane; r < R; r += 32) f0[r] = 0;
-            __syncwarp();
-        }
+        const int regions = count_regions_rows(c.row, Z, Y, c.best, c.best + R, c.best + 2 * R, lane);
 
         if (lane == 0) {
             out[0] = regions;

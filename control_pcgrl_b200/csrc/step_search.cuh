@@ -15,6 +15,71 @@ namespace pcgrl {
 constexpr int SEARCH_WARPS = 8;
 constexpr int SEARCH_THREADS = SEARCH_WARPS * 32;
 constexpr int SEARCH_TILE = 64;   // envs per CTA iteration
+constexpr int SEARCH_MAX_CTAS = 320;   // persistent-grid cap that sizes the global scratch (>= 2 CTAs x 148 SMs)
+
+// Number of connected components of the set bits of a Z x Y x 16 bit-board (rows[z * Y + y] = mask over x),
+// 6-neighbour in 3D, 4-neighbour when Z == 1 (helper.py:200-210 / helper_3D.py:396-406 calc_num_regions).
+// Whole warp; avail / f0 / f1 are Z*Y-entry scratch boards.  Single-cell components are counted with one
+// popcount pass; the others are flood-filled one at a time, a level per pass over the rows.
+__device__ inline int count_regions_rows(const uint16_t* row, int Z, int Y, uint16_t* avail, uint16_t* f0,
+                                         uint16_t* f1, int lane) {
+    const int R = Z * Y;
+    int regions = 0;
+    {
+        int iso_cnt = 0;
+        for (int r = lane; r < R; r += 32) {
+            const int z = r / Y, y = r - z * Y;
+            const uint32_t a = row[r];
+            const uint32_t nb = (a << 1) | (a >> 1) | (y > 0 ? row[r - 1] : 0u) | (y < Y - 1 ? row[r + 1] : 0u) |
+                                (z > 0 ? row[r - Y] : 0u) | (z < Z - 1 ? row[r + Y] : 0u);
+            const uint32_t iso = a & ~nb;
+            iso_cnt += __popc(iso);
+            avail[r] = (uint16_t)(a & ~iso);
+            f0[r] = 0;
+        }
+        regions = __reduce_add_sync(0xffffffffu, iso_cnt);
+        __syncwarp();
+    }
+    for (;;) {
+        int first = 0xFFFF;
+        for (int r = lane; r < R; r += 32)
+            if (avail[r]) {
+                first = r;
+                break;
+            }
+        first = __reduce_min_sync(0xffffffffu, first);
+        if (first == 0xFFFF) break;
+        ++regions;
+        if (lane == 0) {
+            const uint32_t a = avail[first], bit = a & (0u - a);
+            f0[first] = (uint16_t)bit;
+            avail[first] = (uint16_t)(a ^ bit);
+        }
+        __syncwarp();
+        uint16_t *cur = f0, *nxt = f1;
+        for (;;) {
+            uint32_t any = 0;
+            for (int r = lane; r < R; r += 32) {
+                const int z = r / Y, y = r - z * Y;
+                const uint32_t f = cur[r];
+                const uint32_t nb = (f << 1) | (f >> 1) | (y > 0 ? cur[r - 1] : 0u) | (y < Y - 1 ? cur[r + 1] : 0u) |
+                                    (z > 0 ? cur[r - Y] : 0u) | (z < Z - 1 ? cur[r + Y] : 0u);
+                const uint32_t a = avail[r], nf = nb & a;
+                nxt[r] = (uint16_t)nf;
+                avail[r] = (uint16_t)(a ^ nf);
+                any |= nf;
+            }
+            __syncwarp();
+            uint16_t* t = cur;
+            cur = nxt;
+            nxt = t;
+            if (!__any_sync(0xffffffffu, any != 0)) break;
+        }
+        for (int r = lane; r < R; r += 32) f0[r] = 0;   // the seed board must be empty for the next component
+        __syncwarp();
+    }
+    return regions;
+}
 
 // Prob must provide:
 //   static constexpr int K;
@@ -70,7 +135,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_step_search(const KParams p,
 
 // host side: persistent launch sized from the occupancy the dynamic shared memory allows
 template <class Prob>
-static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int* ctas_out = nullptr) {
+static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int max_ctas_per_sm = 1 << 20) {
     static int n_sm = 0;
     cudaError_t e;
     if (!n_sm) {
@@ -87,14 +152,12 @@ static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int64_t tiles = (p.n_envs + SEARCH_TILE - 1) / SEARCH_TILE;
     if (tiles == 0) return cudaSuccess;
-    const int64_t cap = (int64_t)n_sm * per_sm;
+    if (per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
+    int64_t cap = (int64_t)n_sm * per_sm;
+    if (max_ctas_per_sm < (1 << 20) && cap > SEARCH_MAX_CTAS) cap = SEARCH_MAX_CTAS;   // scratch is sized for this
     const int ctas = (int)(tiles < cap ? tiles : cap);
-    if (ctas_out) *ctas_out = ctas;
     k_step_search<Prob><<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp);
     return cudaGetLastError();
 }
-
-// upper bound on resident search warps of one launch (sizes the global scratch of sokoban / smb)
-inline int search_max_warps(int n_sm, int max_ctas_per_sm) { return n_sm * max_ctas_per_sm * SEARCH_WARPS; }
 
 }  // namespace pcgrl

@@ -89,8 +89,13 @@ typedef struct pcgrl_state {
     float*   reward;       /* [N] out: loss(new stats) - loss(old stats), evaluated in fp64 */
     uint8_t* done;         /* [N] out: done == truncated (pcgrl_env.py:307-310) */
     uint8_t* changed;      /* [N] out, may be NULL: 1 if the map changed (stats were recomputed) */
-    int32_t* status;       /* [1] device error word, may be NULL: bit0 = an action was out of range */
-    void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0 */
+    int32_t* status;       /* [1] device error word, may be NULL.  bit0 (1) an action was out of range;
+                              bit1 (2) minecraft_3D_maze: the reference would raise IndexError on this map
+                              (helper_3D.py:531, a recorded x or y >= depth); bit2 (4) a search workspace
+                              overflowed; bit3 (8) sokoban: more crates than a packed solver state holds (15) */
+    void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0.  Must be zero-filled
+                              once before its first use (it holds hash-table generation counters) and must not
+                              be shared by launches that can run concurrently */
 } pcgrl_state;
 
 /* -- queries (host only, no CUDA calls) ------------------------------------------------------- */

@@ -122,6 +122,15 @@ def sokoban_grids():
             g.flat[cells[1:1 + k]] = 3
             g.flat[cells[1 + k:]] = 4
             out.append(g)
+    # harder: 7x7, 3-5 crates, open floor -- the BFS hits its 10 000-iteration cap and the A* passes decide
+    for _ in range(40):
+        k = int(rng.integers(3, 6))
+        g = (rng.random((7, 7)) < rng.choice([0.05, 0.15])).astype(np.uint8)
+        cells = rng.permutation(g.size)[:1 + 2 * k]
+        g.flat[cells[0]] = 2
+        g.flat[cells[1:1 + k]] = 3
+        g.flat[cells[1 + k:]] = 4
+        out.append(g)
     return out
 
 

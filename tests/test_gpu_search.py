@@ -69,3 +69,91 @@ def test_maze3d_full_size_properties():
     st = env.stats[:64].cpu().numpy()
     for i in range(64):
         assert st[i].tolist() == O.stats_vector("minecraft_3D_maze", O.get_stats("minecraft_3D_maze", maps[i]))
+
+
+def _sokoban_grids(rng, shape, n):
+    out = []
+    for i in range(n):
+        if i % 2 == 0:
+            out.append(rng.choice(5, size=shape, p=[0.45, 0.4, 0.05, 0.05, 0.05]).astype(np.int8))
+        else:   # solver-friendly: one player, k crates, k targets, sparse walls
+            k = int(rng.integers(1, 5))
+            g = (rng.random(shape) < rng.choice([0.0, 0.1, 0.2, 0.3])).astype(np.int8)
+            cells = rng.permutation(g.size)[:1 + 2 * k]
+            g.flat[cells[0]] = 2
+            g.flat[cells[1:1 + k]] = 3
+            g.flat[cells[1 + k:]] = 4
+            out.append(g)
+    return np.stack(out)
+
+
+def test_sokoban_random_grids_vs_oracle():
+    from oracle import pcgrl_oracle as O
+    rng = np.random.default_rng(78)
+    for shape, n in [((5, 5), 400), ((3, 9), 120), ((7, 6), 60)]:
+        grids = _sokoban_grids(rng, shape, n)
+        env = _mk("sokoban", "narrow", shape, 1)
+        got = env.compute_stats(grids).cpu().numpy()
+        env.check_status()
+        ran = 0
+        for i in range(n):
+            want = O.stats_vector("sokoban", O.get_stats("sokoban", grids[i]))
+            assert got[i].tolist() == want, (shape, i, grids[i].tolist(), got[i].tolist(), want)
+            ran += want[4] != shape[0] * shape[1] * (shape[0] + shape[1])
+        assert ran > n // 8       # the solver really ran on a good share of them
+
+
+def test_smb_random_grids_vs_oracle():
+    from oracle import pcgrl_oracle as O
+    rng = np.random.default_rng(79)
+    base = np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02])
+    base /= base.sum()
+    for shape, n in [((116, 16), 60), ((16, 116), 30), ((14, 30), 100), ((6, 9), 100)]:
+        grids = []
+        for i in range(n):
+            pr = base if i % 3 else rng.dirichlet(np.ones(7))
+            g = rng.choice(7, size=shape, p=pr).astype(np.int8)
+            if i % 4 == 1:
+                g[-2:, :] = np.where(rng.random((2, shape[1])) < 0.85, 1, 0)
+            grids.append(g)
+        grids = np.stack(grids)
+        env = _mk("smb", "narrow", shape, 1)
+        got = env.compute_stats(grids).cpu().numpy()
+        env.check_status()
+        for i in range(n):
+            want = O.stats_vector("smb", O.get_stats("smb", grids[i]))
+            assert got[i].tolist() == want, (shape, i, got[i].tolist(), want)
+
+
+@pytest.mark.parametrize("problem,rep,shape,n,n_steps", [("sokoban", "cellular", (5, 5), 65536, 6),
+                                                         ("sokoban", "narrow", (5, 5), 65536, 30),
+                                                         ("smb", "narrow", (116, 16), 4096, 10)])
+def test_search_full_size_properties(problem, rep, shape, n, n_steps):
+    """BASELINE config #4 sizes: incremental stats == recomputed stats, unchanged envs untouched, and a
+    sample of the batch against the CPU oracle."""
+    from oracle import pcgrl_oracle as O
+    env = _mk(problem, rep, shape, n, seed=9, random_init_probs=False,
+              action_kind="ca_tiles" if rep == "cellular" else None)
+    env.reset()
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    g = torch.Generator(device=env.device).manual_seed(4)
+    prev_stats = env.stats.clone()
+    for t in range(n_steps):
+        if rep == "cellular":
+            cdf = torch.tensor(np.cumsum(env.spec.init_probs), device=env.device, dtype=torch.float32)
+            u = torch.rand((n, env.row_stride), generator=g, device=env.device)
+            a = torch.searchsorted(cdf, u).clamp_(max=env.n_tiles - 1).to(torch.int8)
+            a[:, env.cells:] = 0
+        else:
+            a = torch.randint(0, env.n_tiles, (n,), generator=g, device=env.device, dtype=torch.int32)
+        reward, done = env.step(a)
+        ch = env.changed.bool()
+        assert torch.equal(env.stats[~ch], prev_stats[~ch])
+        if (~ch).any():
+            assert float(reward[~ch].abs().max()) == 0.0
+        prev_stats = env.stats.clone()
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    env.check_status()
+    maps, st = env.maps[:48].cpu().numpy(), env.stats[:48].cpu().numpy()
+    for i in range(48):
+        assert st[i].tolist() == O.stats_vector(problem, O.get_stats(problem, maps[i])), i
