@@ -26,7 +26,8 @@
 
 namespace pcgrl {
 
-constexpr int MAZE_QCAP = 1024;   // FIFO ring capacity (entries); measured maximum with push filtering: 50
+constexpr int MAZE_QCAP = 256;    // FIFO ring capacity (entries); measured maximum with push filtering: 50
+constexpr int MAZE_WARPS = 4;     // small CTAs, several per SM: finer-grained tile barriers
 
 struct MazeLayout {
     int best, q_cl, nj, order, q_nj, col, row, total, order_cap, best_bytes;
@@ -36,7 +37,6 @@ __host__ __device__ inline MazeLayout maze_layout(int Z, int Y, int X, int row_s
     const int cells = Z * Y * X;
     int bb = 2 * cells;
     if (bb < row_stride) bb = row_stride;      // the raw grid is staged here first
-    if (bb < 6 * Z * Y) bb = 6 * Z * Y;        // ... and the flood-fill boards live here last
     bb = (bb + 15) / 16 * 16;
     L.best_bytes = bb;
     L.order_cap = (Z / 2 + 1) * Y * X;
@@ -57,6 +57,7 @@ struct Maze3DProb {
 
     struct Ctx {
         int Z, Y, X, cells, R;
+        uint32_t magic_xy, magic_x;
         uint16_t *best, *nj, *order, *q_nj, *col, *row;
         uint32_t* q_cl;
         int best_bytes, order_cap;
@@ -68,6 +69,8 @@ struct Maze3DProb {
         c.Z = p.d0; c.Y = p.d1; c.X = p.d2;
         c.cells = p.cells;
         c.R = c.Z * c.Y;
+        c.magic_xy = div_magic(c.X * c.Y);
+        c.magic_x = div_magic(c.X);
         const MazeLayout L = maze_layout(c.Z, c.Y, c.X, p.row_stride);
         c.best = (uint16_t*)(ws + L.best);
         c.q_cl = (uint32_t*)(ws + L.q_cl);
@@ -152,7 +155,7 @@ struct Maze3DProb {
             const int nj_e = c.q_nj[head & (MAZE_QCAP - 1)];
             ++head;
             const int cell = cl & 0xFFF, ln = cl >> 12;
-            const int z = cell / XY, rem = cell - z * XY, y = rem / c.X, x = rem - y * c.X;
+            const int z = div_by(cell, c.magic_xy), rem = cell - z * XY, y = div_by(rem, c.magic_x), x = rem - y * c.X;
             const uint16_t b = c.best[cell];
             const bool first = !(b & 0x8000u);
             if (lane == 0) {
@@ -251,7 +254,8 @@ struct Maze3DProb {
             uint32_t mark = 0;
             for (int i = lane; i < n; i += 32) {                                          // :531
                 const int cell = c.order[i];
-                const int cz = cell / (X * Y), rem = cell - cz * X * Y, cy = rem / X, cx = rem - cy * X;
+                const int cz = div_by(cell, c.magic_xy), rem = cell - cz * X * Y, cy = div_by(rem, c.magic_x),
+                          cx = rem - cy * X;
                 mark |= (1u << cx) | (1u << cy) | (1u << cz);
             }
             mark = __reduce_or_sync(0xffffffffu, mark);
@@ -268,8 +272,8 @@ struct Maze3DProb {
             if (overflow) break;
         }
 
-        // ---- calc_num_regions (helper_3D.py:396-406): 6-neighbour AIR components by bit-board flood fill ---
-        const int regions = count_regions_rows(c.row, Z, Y, c.best, c.best + R, c.best + 2 * R, lane);
+        // ---- calc_num_regions (helper_3D.py:396-406): 6-neighbour AIR components by union-find over runs ---
+        const int regions = count_regions_rows(c.row, Z, Y, X, c.best, lane);
 
         if (lane == 0) {
             out[0] = regions;
@@ -284,7 +288,7 @@ cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported) {
     supported = p.ndim == 3 && p.d0 <= 16 && p.d1 <= 16 && p.d2 <= 16 && p.d0 >= 1;
     if (!supported) return cudaSuccess;
     const MazeLayout L = maze_layout(p.d0, p.d1, p.d2, p.row_stride);
-    return launch_search<Maze3DProb>(p, s, L.total);
+    return launch_search<Maze3DProb, MAZE_WARPS>(p, s, L.total);
 }
 
 }  // namespace pcgrl

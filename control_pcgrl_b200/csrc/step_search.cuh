@@ -7,78 +7,90 @@
 //     load, bit-board construction, flood fill, child generation), warp-uniform where the reference's
 //     queue order has to be reproduced step by step.
 #pragma once
+#include <atomic>
 #include "pcgrl_device.cuh"
 #include "step_common.cuh"
 
 namespace pcgrl {
 
-constexpr int SEARCH_WARPS = 8;
-constexpr int SEARCH_THREADS = SEARCH_WARPS * 32;
+constexpr int SEARCH_WARPS = 8;   // default warps per CTA (a problem may ask for more)
 constexpr int SEARCH_TILE = 64;   // envs per CTA iteration
+constexpr int SEARCH_SLOTS = 64;  // concurrent launches that can share the tile counters below
+// Dynamic tile scheduling: CTAs pull tile indices from g_tile_ctr[slot]; the last CTA to leave resets the
+// slot, so nothing has to be zeroed from the host between launches.  The host hands out slots round-robin.
+static __device__ unsigned int g_tile_ctr[SEARCH_SLOTS];
+static __device__ unsigned int g_done_ctr[SEARCH_SLOTS];
 constexpr int SEARCH_MAX_CTAS = 320;   // persistent-grid cap that sizes the global scratch (>= 2 CTAs x 148 SMs)
 
-// Number of connected components of the set bits of a Z x Y x 16 bit-board (rows[z * Y + y] = mask over x),
-// 6-neighbour in 3D, 4-neighbour when Z == 1 (helper.py:200-210 / helper_3D.py:396-406 calc_num_regions).
-// Whole warp; avail / f0 / f1 are Z*Y-entry scratch boards.  Single-cell components are counted with one
-// popcount pass; the others are flood-filled one at a time, a level per pass over the rows.
-__device__ inline int count_regions_rows(const uint16_t* row, int Z, int Y, uint16_t* avail, uint16_t* f0,
-                                         uint16_t* f1, int lane) {
-    const int R = Z * Y;
-    int regions = 0;
-    {
-        int iso_cnt = 0;
-        for (int r = lane; r < R; r += 32) {
-            const int z = r / Y, y = r - z * Y;
-            const uint32_t a = row[r];
-            const uint32_t nb = (a << 1) | (a >> 1) | (y > 0 ? row[r - 1] : 0u) | (y < Y - 1 ? row[r + 1] : 0u) |
-                                (z > 0 ? row[r - Y] : 0u) | (z < Z - 1 ? row[r + Y] : 0u);
-            const uint32_t iso = a & ~nb;
-            iso_cnt += __popc(iso);
-            avail[r] = (uint16_t)(a & ~iso);
-            f0[r] = 0;
-        }
-        regions = __reduce_add_sync(0xffffffffu, iso_cnt);
-        __syncwarp();
-    }
+// floor(n / d) for n < 2^16 and d <= 2^8 as one multiply-high: magic = ceil(2^32 / d)
+__host__ __device__ inline uint32_t div_magic(int d) { return (uint32_t)((0x100000000ull + d - 1) / d); }
+__device__ __forceinline__ int div_by(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }  // magic == 0 <=> d == 1
+
+// ------------------------------------------------------------------------------------------------
+// calc_num_regions (helper.py:200-210 / helper_3D.py:396-406) as connected-component labelling with a
+// shared-memory union-find over *runs*: rows[z * Y + y] is the bit mask over x of passable cells; a run is
+// a maximal horizontal stretch of set bits, identified by the cell index of its first cell.  Every run is
+// united with the runs it touches in the row above (y - 1) and in the plane below (z - 1); the number of
+// regions is the number of roots.  6-neighbour in 3D, 4-neighbour when Z == 1.  Whole warp, lanes stride
+// the rows; parent[] needs Z*Y*X u16 entries.  Lock-free: the larger root is hooked under the smaller one
+// with a 16-bit compare-and-swap and retried on interference.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int run_start(uint32_t a, int b) {
+    const uint32_t below = ~a & ((1u << b) - 1u);     // zero bits under b
+    return 32 - __clz(below);                         // first bit of the run that contains b
+}
+__device__ inline void uf_union(volatile uint16_t* parent, int a, int b) {
     for (;;) {
-        int first = 0xFFFF;
-        for (int r = lane; r < R; r += 32)
-            if (avail[r]) {
-                first = r;
-                break;
-            }
-        first = __reduce_min_sync(0xffffffffu, first);
-        if (first == 0xFFFF) break;
-        ++regions;
-        if (lane == 0) {
-            const uint32_t a = avail[first], bit = a & (0u - a);
-            f0[first] = (uint16_t)bit;
-            avail[first] = (uint16_t)(a ^ bit);
+        int pa, pb;
+        while ((pa = parent[a]) != a) a = pa;
+        while ((pb = parent[b]) != b) b = pb;
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
         }
-        __syncwarp();
-        uint16_t *cur = f0, *nxt = f1;
-        for (;;) {
-            uint32_t any = 0;
-            for (int r = lane; r < R; r += 32) {
-                const int z = r / Y, y = r - z * Y;
-                const uint32_t f = cur[r];
-                const uint32_t nb = (f << 1) | (f >> 1) | (y > 0 ? cur[r - 1] : 0u) | (y < Y - 1 ? cur[r + 1] : 0u) |
-                                    (z > 0 ? cur[r - Y] : 0u) | (z < Z - 1 ? cur[r + Y] : 0u);
-                const uint32_t a = avail[r], nf = nb & a;
-                nxt[r] = (uint16_t)nf;
-                avail[r] = (uint16_t)(a ^ nf);
-                any |= nf;
-            }
-            __syncwarp();
-            uint16_t* t = cur;
-            cur = nxt;
-            nxt = t;
-            if (!__any_sync(0xffffffffu, any != 0)) break;
-        }
-        for (int r = lane; r < R; r += 32) f0[r] = 0;   // the seed board must be empty for the next component
-        __syncwarp();
+        const unsigned short old = atomicCAS((unsigned short*)parent + a, (unsigned short)a, (unsigned short)b);
+        if (old == (unsigned short)a) return;
     }
-    return regions;
+}
+__device__ inline int count_regions_rows(const uint16_t* row, int Z, int Y, int X, uint16_t* parent, int lane) {
+    const int R = Z * Y;
+    const uint32_t magic_y = div_magic(Y);
+    for (int r = lane; r < R; r += 32) {
+        const uint32_t a = row[r];
+        for (uint32_t s = a & ~(a << 1); s; s &= s - 1) {
+            const int id = r * X + __ffs(s) - 1;
+            parent[id] = (uint16_t)id;
+        }
+    }
+    __syncwarp();
+    for (int r = lane; r < R; r += 32) {
+        const int z = div_by(r, magic_y), y = r - z * Y;
+        const uint32_t a = row[r];
+        if (!a) continue;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            if (dir == 0 ? y == 0 : z == 0) continue;
+            const int rp = dir == 0 ? r - 1 : r - Y;
+            const uint32_t ap = row[rp];
+            const uint32_t t = a & ap;                          // vertically adjacent passable pairs
+            for (uint32_t s = t & ~(t << 1); s; s &= s - 1) {   // one union per stretch of such pairs
+                const int bpos = __ffs(s) - 1;
+                uf_union(parent, r * X + run_start(a, bpos), rp * X + run_start(ap, bpos));
+            }
+        }
+    }
+    __syncwarp();
+    int roots = 0;
+    for (int r = lane; r < R; r += 32) {
+        const uint32_t a = row[r];
+        for (uint32_t s = a & ~(a << 1); s; s &= s - 1) {
+            const int id = r * X + __ffs(s) - 1;
+            roots += parent[id] == id;
+        }
+    }
+    return __reduce_add_sync(0xffffffffu, roots);
 }
 
 // Prob must provide:
@@ -86,30 +98,36 @@ __device__ inline int count_regions_rows(const uint16_t* row, int Z, int Y, uint
 //   struct Ctx;                                         per-warp context (pointers into its workspaces)
 //   static __device__ Ctx make_ctx(const KParams&, uint8_t* warp_smem, int global_warp);
 //   static __device__ void stats(const KParams&, Ctx&, const int8_t* grid, int lane, int32_t* out /*smem [K]*/);
-template <class Prob>
-__global__ void __launch_bounds__(SEARCH_THREADS) k_step_search(const KParams p, const int smem_per_warp) {
+template <class Prob, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, const int smem_per_warp, const int slot) {
     constexpr int K = Prob::K;
     constexpr int TILE = SEARCH_TILE;
+    constexpr int SEARCH_THREADS = WARPS * 32;
     extern __shared__ __align__(16) uint8_t dyn_smem[];
     __shared__ int32_t s_stats[TILE * K];
     __shared__ int16_t s_list[TILE];
     __shared__ int16_t s_slot[TILE];
     __shared__ uint8_t s_flag[TILE];
     __shared__ int s_count, s_next;
+    __shared__ unsigned int s_tile;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int8_t* grids_in = (p.mode == MODE_STATS) ? p.stats_grids : p.grids;
-    typename Prob::Ctx ctx = Prob::make_ctx(p, dyn_smem + (size_t)warp * smem_per_warp, blockIdx.x * SEARCH_WARPS + warp);
+    typename Prob::Ctx ctx = Prob::make_ctx(p, dyn_smem + (size_t)warp * smem_per_warp, blockIdx.x * WARPS + warp);
     const int64_t n_tiles = (p.n_envs + TILE - 1) / TILE;
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * TILE;
-        const int tile_n = (int)min((int64_t)TILE, p.n_envs - base);
+    for (;;) {
         __syncthreads();   // previous tile's phase D is done with the shared lists
         if (tid == 0) {
+            s_tile = atomicAdd(&g_tile_ctr[slot], 1u);
             s_count = 0;
             s_next = 0;
         }
+        __syncthreads();
+        const int64_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const int64_t base = tile * TILE;
+        const int tile_n = (int)min((int64_t)TILE, p.n_envs - base);
         for (int e = tid; e < TILE; e += SEARCH_THREADS) {
             s_slot[e] = -1;
             s_flag[e] = 0;
@@ -131,24 +149,33 @@ __global__ void __launch_bounds__(SEARCH_THREADS) k_step_search(const KParams p,
         __syncthreads();
         phase_d<SEARCH_THREADS, K>(p, base, tile_n, s_slot, s_stats);
     }
+    if (tid == 0) {   // last CTA out re-arms the counters for the next launch that gets this slot
+        __threadfence();
+        if (atomicAdd(&g_done_ctr[slot], 1u) == gridDim.x - 1) {
+            g_tile_ctr[slot] = 0;
+            g_done_ctr[slot] = 0;
+            __threadfence();
+        }
+    }
 }
 
 // host side: persistent launch sized from the occupancy the dynamic shared memory allows
-template <class Prob>
+template <class Prob, int WARPS = SEARCH_WARPS>
 static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int max_ctas_per_sm = 1 << 20) {
     static int n_sm = 0;
+    static std::atomic<unsigned> next_slot{0};
+    constexpr int SEARCH_THREADS = WARPS * 32;
     cudaError_t e;
     if (!n_sm) {
         int dev = 0;
         if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
         if ((e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     }
-    const int dyn = smem_per_warp * SEARCH_WARPS;
-    if ((e = cudaFuncSetAttribute(k_step_search<Prob>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)
-        return e;
+    const int dyn = smem_per_warp * WARPS;
+    auto kern = k_step_search<Prob, WARPS>;
+    if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess) return e;
     int per_sm = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_step_search<Prob>, SEARCH_THREADS, dyn)) != cudaSuccess)
-        return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SEARCH_THREADS, dyn)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int64_t tiles = (p.n_envs + SEARCH_TILE - 1) / SEARCH_TILE;
     if (tiles == 0) return cudaSuccess;
@@ -156,7 +183,8 @@ static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_
     int64_t cap = (int64_t)n_sm * per_sm;
     if (max_ctas_per_sm < (1 << 20) && cap > SEARCH_MAX_CTAS) cap = SEARCH_MAX_CTAS;   // scratch is sized for this
     const int ctas = (int)(tiles < cap ? tiles : cap);
-    k_step_search<Prob><<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp);
+    const int slot = (int)(next_slot.fetch_add(1) % SEARCH_SLOTS);
+    kern<<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp, slot);
     return cudaGetLastError();
 }
 

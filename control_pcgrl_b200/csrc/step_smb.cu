@@ -246,8 +246,9 @@ struct SmbProb {
         const uint8_t* g = c.stage;
         // ---- map statistics (smb_prob.py:134-139) --------------------------------------------------------------
         int dist_floor = 0, tubes = 0, enemies = 0, empty = 0, noise = 0;
+        const uint32_t magic_w = div_magic(W);
         for (int i = lane; i < p.cells; i += 32) {
-            const int y = i / W, x = i - y * W, t = g[i];
+            const int y = div_by(i, magic_w), x = i - y * W, t = g[i];
             empty += t == 0;
             if (t == 2) {                                        // helper.py:40-46 distance of an enemy to the floor
                 ++enemies;

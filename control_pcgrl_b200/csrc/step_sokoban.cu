@@ -54,16 +54,17 @@ struct SokobanProb {
         uint32_t* dead;      // [8] bit p = static deadlock cell
         uint8_t* tpos;       // [16] target positions in scan order
         uint8_t* cpos;       // [256] scratch list (crates, then corners)
-        uint16_t* rows;      // [4 * 16] passable rows + flood-fill boards
+        uint16_t* rows;      // [16] passable rows, then [256] union-find parents
         // global scratch slice
         uint32_t* hdr;
         uint4* state;
         uint32_t *meta, *heap, *table;
         int nt;              // #targets == #crates while solving
+        uint32_t magic_bw;
     };
 
     __host__ __device__ static int smem_bytes(int row_stride) {
-        return (row_stride + 15) / 16 * 16 + 32 + 32 + 16 + 256 + 2 * 64;
+        return (row_stride + 15) / 16 * 16 + 32 + 32 + 16 + 256 + 2 * (16 + 256);
     }
 
     __device__ static Ctx make_ctx(const KParams& p, uint8_t* ws, int global_warp) {
@@ -84,6 +85,7 @@ struct SokobanProb {
         c.heap = (uint32_t*)(g + SokScratch::heap);
         c.table = (uint32_t*)(g + SokScratch::table);
         c.nt = 0;
+        c.magic_bw = div_magic(c.BW);
         return c;
     }
 
@@ -119,12 +121,12 @@ struct SokobanProb {
         uint32_t remaining = (1u << c.nt) - 1u;
         int total = 0;
         for (int i = 0; i < c.nt; ++i) {
-            const int cp = get_byte(s, 1 + i), cx = cp % c.BW, cy = cp / c.BW;
+            const int cp = get_byte(s, 1 + i), cy = div_by(cp, c.magic_bw), cx = cp - cy * c.BW;
             int best = c.BW + c.BH, bi = -1, bd = 0;
             for (uint32_t r = remaining; r; r &= r - 1) {
                 const int j = __ffs(r) - 1;
-                const int tp = c.tpos[j];
-                const int d = abs(cx - tp % c.BW) + abs(cy - tp / c.BW);
+                const int tp = c.tpos[j], ty = div_by(tp, c.magic_bw);
+                const int d = abs(cx - (tp - ty * c.BW)) + abs(cy - ty);
                 if (bi < 0) {          // bestMatch defaults to the first remaining target
                     bi = j;
                     bd = d;
@@ -342,7 +344,7 @@ struct SokobanProb {
             rows[y] = (uint16_t)m;
         }
         __syncwarp();
-        const int regions = count_regions_rows(rows, 1, H, rows + 16, rows + 32, rows + 48, lane);
+        const int regions = count_regions_rows(rows, 1, H, W, rows + 16, lane);
 
         int dist_win = W * H * (W + H), sol_len = 0;                    // sokoban_prob.py:171
         const bool run = n_player == 1 && n_crate == n_target && n_crate > 0 && regions == 1;   // :174-179
@@ -357,7 +359,7 @@ struct SokobanProb {
                 const int pidx = w * 32 + lane;
                 int t = 1;
                 if (pidx < BW * BH) {
-                    const int y = pidx / BW, x = pidx - y * BW;
+                    const int y = div_by(pidx, c.magic_bw), x = pidx - y * BW;
                     if (x > 0 && y > 0 && x < BW - 1 && y < BH - 1) t = c.stage[(y - 1) * W + (x - 1)];
                 }
                 const unsigned sm = __ballot_sync(0xffffffffu, t == 1);
