@@ -8,13 +8,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PCGRL_ABI_VERSION = 1
+PCGRL_ABI_VERSION = 2
 MAX_STATS = 16
 MAX_TILES = 16
 
 PROB_IDS = {"binary": 0, "zelda": 1, "sokoban": 2, "smb": 3, "minecraft_3D_maze": 4}
 REP_IDS = {"narrow": 0, "turtle": 1, "wide": 2, "cellular": 3}
 ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS = range(5)
+REWARD_CONTROL, REWARD_RANGE = 0, 1
 
 LIB_NAME = "libpcgrl_sm100.so"
 # PCGRL_B200_LIB lets kernel experiments load an alternative build of the same ABI (scripts/ab_variants.sh)
@@ -27,7 +28,7 @@ class Config(C.Structure):
         ("action_kind", C.c_int32), ("ndim", C.c_int32), ("dims", C.c_int32 * 3), ("n_tiles", C.c_int32),
         ("n_stats", C.c_int32), ("row_stride", C.c_int32), ("max_iterations", C.c_int32),
         ("max_changes", C.c_int32), ("act_h", C.c_int32), ("act_w", C.c_int32),
-        ("targets_per_env", C.c_int32), ("init_random_probs", C.c_int32),
+        ("targets_per_env", C.c_int32), ("init_random_probs", C.c_int32), ("reward_mode", C.c_int32),
         ("init_probs", C.c_float * MAX_TILES), ("weights", C.c_double * MAX_STATS),
     ]
 

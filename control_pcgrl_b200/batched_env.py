@@ -30,7 +30,8 @@ def _ptr(t):
 
 class BatchedPcgrlEnv:
     def __init__(self, cfg, n_envs: int, device="cuda:0", env_offset: int = 0, seed: int = 0,
-                 action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True):
+                 action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True,
+                 reward_mode: str = "control"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.PcgrlError("control_pcgrl_b200 needs a CUDA device (there is no CPU fallback)")
@@ -90,10 +91,21 @@ class BatchedPcgrlEnv:
         cc.act_h, cc.act_w = (self.obs_window[0], self.obs_window[1]) if ak == _lib.ACT_WIDE_FLAT else (0, 0)
         cc.targets_per_env = 1 if self.ctrl_metrics else 0
         cc.init_random_probs = 1 if random_init_probs else 0
+        # "control": ControlWrapper's loss delta (what step() pays at this commit); "range": the legacy
+        # Problem.get_reward sum of get_range_reward terms (helper.py:550-560), bands in `targets`
+        if reward_mode not in ("control", "range"):
+            raise ValueError(f"reward_mode {reward_mode!r}")
+        if reward_mode == "range" and not self.spec.range_bands:
+            raise ValueError(f"the reference defines no legacy get_reward for {self.problem}")
+        self.reward_mode = reward_mode
+        cc.reward_mode = _lib.REWARD_RANGE if reward_mode == "range" else _lib.REWARD_CONTROL
         for i, pr in enumerate(self.spec.init_probs):
             cc.init_probs[i] = pr
         for k, name in enumerate(self.stat_names):
-            cc.weights[k] = float(self.metric_weights.get(name, 0)) if name in self.all_metrics else 0.0
+            if reward_mode == "range":
+                cc.weights[k] = float(self.spec.range_weights.get(name, 0)) if name in self.spec.range_bands else 0.0
+            else:
+                cc.weights[k] = float(self.metric_weights.get(name, 0)) if name in self.all_metrics else 0.0
         _lib.check(self.lib.pcgrl_config_check(cc), "pcgrl_config_check")
         self._cc = cc
 
@@ -129,6 +141,8 @@ class BatchedPcgrlEnv:
 
     # ------------------------------------------------------------------ targets
     def _target_rows(self, trgs):
+        if self.reward_mode == "range":
+            return np.array([self.spec.range_bands.get(name, (0.0, 0.0)) for name in self.stat_names], dtype=np.float64)
         rows = np.full((self.K, 2), np.nan, dtype=np.float64)
         for k, name in enumerate(self.stat_names):
             t = trgs.get(name, self.static_trgs.get(name, 0))

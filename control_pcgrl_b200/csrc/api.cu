@@ -50,6 +50,8 @@ static int check(const pcgrl_config* c) {
                     (r == PCGRL_REP_CELLULAR && (a == PCGRL_ACT_CA_TILES || a == PCGRL_ACT_CA_LOGITS));
     if (!ok) return fail(PCGRL_E_ARG, "action_kind does not fit the representation");
     if (a == PCGRL_ACT_WIDE_FLAT && (c->act_h < 1 || c->act_w < 1)) return fail(PCGRL_E_ARG, "act_h/act_w required");
+    if (c->reward_mode != PCGRL_REWARD_CONTROL && c->reward_mode != PCGRL_REWARD_RANGE)
+        return fail(PCGRL_E_ARG, "unknown reward_mode");
     return 0;
 }
 
@@ -71,6 +73,7 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
     p.act_w = c->act_w;
     p.targets_per_env = c->targets_per_env;
     p.init_random_probs = c->init_random_probs;
+    p.reward_mode = c->reward_mode;
     double tot = 0;
     for (int t = 0; t < c->n_tiles; ++t) tot += c->init_probs[t] > 0 ? c->init_probs[t] : 0;
     double run = 0;

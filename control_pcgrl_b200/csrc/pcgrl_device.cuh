@@ -32,6 +32,7 @@ struct KParams {
     int32_t act_h, act_w;
     int32_t targets_per_env;
     int32_t init_random_probs;
+    int32_t reward_mode;
     float   init_cdf[PCGRL_MAX_TILES];
     double  weights[PCGRL_MAX_STATS];
     int64_t n_envs, env_offset;
@@ -93,6 +94,26 @@ __device__ __forceinline__ double control_loss(const int32_t* st, const double* 
         loss += -d * wk;
     }
     return loss;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Legacy Problem.get_reward: sum_k w_k * get_range_reward(new_k, old_k, lo_k, hi_k)  (envs/helper.py:550-560;
+// the bands may be +-infinity, e.g. "the longer the better" = (inf, inf), binary_prob.py:170-178).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double range_reward(double nv, double ov, double lo, double hi) {
+    if (nv >= lo && nv <= hi && ov >= lo && ov <= hi) return 0.0;
+    if (ov <= hi && nv <= hi) return fmin(nv, lo) - fmin(ov, lo);
+    if (ov >= lo && nv >= lo) return fmax(ov, hi) - fmax(nv, hi);
+    if (nv > hi && ov < lo) return hi - nv + ov - lo;
+    if (nv < lo && ov > hi) return hi - ov + nv - lo;
+    return 0.0;   // unreachable for lo <= hi (the reference would return None)
+}
+__device__ __forceinline__ double range_reward_sum(const int32_t* nw, const int32_t* od, const double* band,
+                                                   const double* w, int K) {
+    double r = 0.0;
+    for (int k = 0; k < K; ++k)
+        if (w[k] != 0.0) r += w[k] * range_reward((double)nw[k], (double)od[k], band[2 * k], band[2 * k + 1]);
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------

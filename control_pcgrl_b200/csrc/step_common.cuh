@@ -268,7 +268,9 @@ __device__ __forceinline__ void phase_d(const KParams& p, int64_t base, int tile
 #pragma unroll
             for (int k = 0; k < K; ++k) od[k] = st[k];
             const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
-            const double r = control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
+            const double r = p.reward_mode == PCGRL_REWARD_RANGE
+                                 ? range_reward_sum(nw, od, trg, p.weights, K)
+                                 : control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
             p.reward[gid] = (float)r;
         }
 #pragma unroll

@@ -73,7 +73,15 @@ class _ProblemProxy:
         return False
 
     def get_reward(self, new_stats, old_stats):
-        return None
+        """Legacy Problem.get_reward.  At this commit only BinaryProblem is registered with its own get_reward
+        (binary_prob.py:170-178); the Ctrl problems return None (e.g. zelda_ctrl_prob.py:79) and the 3D maze's
+        is commented out.  The batched kernels compute the same sum with reward_mode="range"."""
+        spec = self._o._b.spec
+        if spec.name != "binary":
+            return None
+        from .problems import get_range_reward
+        return sum(get_range_reward(new_stats[k], old_stats[k], *spec.range_bands[k]) * spec.range_weights[k]
+                   for k in spec.range_bands)
 
 
 class _RepProxy:

@@ -10,6 +10,24 @@ from collections import OrderedDict
 from dataclasses import dataclass, field
 
 
+INF = float("inf")
+
+
+def get_range_reward(new_value, old_value, low, high):
+    """envs/helper.py:550-560 -- the legacy piecewise distance-to-band reward (public helper of the reference)."""
+    if low <= new_value <= high and low <= old_value <= high:
+        return 0
+    if old_value <= high and new_value <= high:
+        return min(new_value, low) - min(old_value, low)
+    if old_value >= low and new_value >= low:
+        return max(old_value, high) - max(new_value, high)
+    if new_value > high and old_value < low:
+        return high - new_value + old_value - low
+    if new_value < low and old_value > high:
+        return high - old_value + new_value - low
+    return None
+
+
 @dataclass
 class ProblemSpec:
     name: str
@@ -21,6 +39,10 @@ class ProblemSpec:
     static_trgs: "OrderedDict[str, object]" = field(default_factory=OrderedDict)
     cond_bounds: dict = field(default_factory=dict)
     reward_weights: dict = field(default_factory=dict)   # the Problem's own _reward_weights (keys matter)
+    # legacy Problem.get_reward (helper.get_range_reward): stat -> (low, high) band, and the weights the
+    # non-ctrl Problem class hard-codes.  Empty = the reference defines no such reward for this problem.
+    range_bands: dict = field(default_factory=dict)
+    range_weights: dict = field(default_factory=dict)
 
     @property
     def n_tiles(self):
@@ -40,7 +62,10 @@ def binary_spec(map_shape):
         init_probs=[0.5, 0.5], border_tile="solid", ndim=2,
         static_trgs=OrderedDict([("regions", 1), ("path-length", max_path)]),
         cond_bounds={"regions": (0, float(w * math.ceil(h / 2))), "path-length": (0, max_path)},
-        reward_weights={"regions": 100, "path-length": 100})
+        reward_weights={"regions": 100, "path-length": 100},
+        # binary_prob.py:170-178 (weights :37-40)
+        range_bands={"regions": (1, 1), "path-length": (125, 125)},
+        range_weights={"regions": 100, "path-length": 100})
 
 
 def zelda_spec(map_shape):
@@ -58,7 +83,12 @@ def zelda_spec(map_shape):
                      "key": (0, w * h - 2), "door": (0, w * h - 2), "regions": (0, w * h / 2),
                      "path-length": (0, max_path)},
         reward_weights={"player": 3, "key": 3, "door": 3, "regions": 5, "enemies": 1, "nearest-enemy": 1,
-                        "path-length": 1})
+                        "path-length": 1},
+        # zelda_prob.py:135-153 (ZeldaProblem; _max_enemies 5, _target_enemy_dist 4, weights :33-41)
+        range_bands={"player": (1, 1), "key": (1, 1), "door": (1, 10), "enemies": (2, 5), "regions": (1, 1),
+                     "nearest-enemy": (4, INF), "path-length": (INF, INF)},
+        range_weights={"player": 3, "key": 3, "door": 3, "regions": 5, "enemies": 1, "nearest-enemy": 2,
+                       "path-length": 1})
 
 
 def sokoban_spec(map_shape):
@@ -75,7 +105,12 @@ def sokoban_spec(map_shape):
         cond_bounds={"player": (1, w * h), "crate": (1, w * h / 2 - max(w, h)), "target": (1, w * h),
                      "ratio": (0, w * h), "dist-win": (0, w * h * (w + h)), "sol-length": (0, 2 * max_path),
                      "regions": (0, w * h / 2)},
-        reward_weights={"player": 3, "crate": 1, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1})
+        reward_weights={"player": 3, "crate": 1, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1},
+        # sokoban_prob.py:185-229 (SokobanProblem; _max_crates 3, weights :44-52)
+        range_bands={"player": (1, 1), "crate": (1, 3), "target": (1, 3), "regions": (1, 1), "ratio": (-INF, -INF),
+                     "dist-win": (-INF, -INF), "sol-length": (INF, INF)},
+        range_weights={"player": 3, "crate": 2, "target": 2, "regions": 5, "ratio": 2, "dist-win": 0.0,
+                       "sol-length": 1})
 
 
 def smb_spec(map_shape):
@@ -94,7 +129,12 @@ def smb_spec(map_shape):
                      "noise": (0, w * h), "jumps": (0, w), "jumps-dist": (0, w * h), "dist-win": (0, w),
                      "sol-length": (0, max_sol)},
         reward_weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
-                        "jumps-dist": 2, "dist-win": 5, "sol-length": 1})
+                        "jumps-dist": 2, "dist-win": 5, "sol-length": 1},
+        # smb_prob.py:156-176 (sol-length is not part of the legacy sum)
+        range_bands={"dist-floor": (0, 0), "disjoint-tubes": (0, 0), "enemies": (10, 30), "empty": (900, INF),
+                     "noise": (0, 0), "jumps": (20, INF), "jumps-dist": (0, 0), "dist-win": (0, 0)},
+        range_weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
+                       "jumps-dist": 2, "dist-win": 5})
 
 
 def minecraft_3d_maze_spec(map_shape):

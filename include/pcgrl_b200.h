@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCGRL_ABI_VERSION 1
+#define PCGRL_ABI_VERSION 2
 
 /* problems: envs/probs/__init__.py:31-58 (the five BASELINE.json names) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_SMB = 3,
@@ -42,6 +42,14 @@ enum {
     PCGRL_ACT_CA_TILES = 3,    /* cellular: int8[N, row_stride] already-argmaxed next map                    */
     PCGRL_ACT_CA_LOGITS = 4    /* cellular: float32[N, C, cells] logits; argmax over C, lowest index wins
                                   (reps/ca_rep.py:31-44, wrappers.py:157-165)                                */
+};
+/* how `reward` is computed from the old and new stats */
+enum {
+    PCGRL_REWARD_CONTROL = 0,  /* ControlWrapper: loss(new) - loss(old), loss = -sum w |trg - val|
+                                  (control_wrappers.py:216-244, 318-345) -- what step() pays at this commit */
+    PCGRL_REWARD_RANGE = 1     /* legacy Problem.get_reward: sum w * get_range_reward(new, old, lo, hi)
+                                  (envs/helper.py:550-560; e.g. probs/binary/binary_prob.py:170-178); `targets`
+                                  rows are read as the (lo, hi) of each stat and may hold +-infinity */
 };
 enum { PCGRL_E_ARG = -1, PCGRL_E_CUDA = -2, PCGRL_E_UNSUPPORTED = -3 };
 
@@ -66,6 +74,7 @@ typedef struct pcgrl_config {
     int32_t targets_per_env;  /* 1: targets is [N,K,2]; 0: targets is [1,K,2] shared by all envs */
     int32_t init_random_probs;/* reset: 1 = draw per-episode tile probabilities U(0,1)^C normalised
                                  (pcgrl_env.py:162-164), 0 = use init_probs as given */
+    int32_t reward_mode;      /* PCGRL_REWARD_* */
     float   init_probs[PCGRL_MAX_TILES]; /* tile init distribution, normalised by the library */
     double  weights[PCGRL_MAX_STATS];    /* ControlWrapper.metric_weights per stat (0 = not in all_metrics),
                                             control_wrappers.py:41-45,78-84 */
@@ -85,7 +94,8 @@ typedef struct pcgrl_state {
     int32_t* changes;      /* [N] PcgrlEnv._changes */
     int32_t* stats;        /* [N, K] current _rep_stats; read (old) and written (new) by step */
     const double* targets; /* [N or 1, K, 2] (lo, hi): hi = NaN -> scalar target lo, else the integer range
-                              np.arange(lo, hi) (control_wrappers.py:336-343) */
+                              np.arange(lo, hi) (control_wrappers.py:336-343).  With PCGRL_REWARD_RANGE: the
+                              (lo, hi) band of get_range_reward for each stat */
     float*   reward;       /* [N] out: loss(new stats) - loss(old stats), evaluated in fp64 */
     uint8_t* done;         /* [N] out: done == truncated (pcgrl_env.py:307-310) */
     uint8_t* changed;      /* [N] out, may be NULL: 1 if the map changed (stats were recomputed) */

@@ -196,6 +196,44 @@ def maze3d_grids():
     return out
 
 
+def legacy_reward_fixture():
+    """Random (new, old) stat pairs -> the reference's own Problem.get_reward (the non-ctrl classes)."""
+    R.install()
+    from control_pcgrl.envs.probs.binary.binary_prob import BinaryProblem
+    from control_pcgrl.envs.probs.zelda.zelda_prob import ZeldaProblem
+    from control_pcgrl.envs.probs.sokoban.sokoban_prob import SokobanProblem
+    from control_pcgrl.envs.probs.smb.smb_prob import SMBProblem
+    rng = np.random.default_rng(41)
+    arrays = {}
+    for problem, cls, shape, hi in [("binary", BinaryProblem, (16, 16), [130, 140]),
+                                    ("zelda", ZeldaProblem, (7, 11), [3, 3, 12, 8, 6, 30, 60]),
+                                    ("sokoban", SokobanProblem, (5, 5), [3, 6, 6, 4, 260, 30, 6]),
+                                    ("smb", SMBProblem, (116, 16), [40, 8, 40, 1856, 60, 40, 30, 20, 60])]:
+        cfg = R.make_cfg(problem, "narrow", shape, weights={})
+        pobj = cls(cfg=cfg)
+        names = STAT_NAMES[problem]
+        new = np.stack([rng.integers(0, h + 1, size=400) for h in hi], axis=1)
+        old = np.stack([rng.integers(0, h + 1, size=400) for h in hi], axis=1)
+        if problem == "zelda":
+            new[:, 6] -= 2
+            old[:, 6] -= 2          # path-length can be -1 / -2
+        if problem == "sokoban":
+            new[:, 6] = np.abs(new[:, 1] - new[:, 2])
+            old[:, 6] = np.abs(old[:, 1] - old[:, 2])
+        out = []
+        for a, b in zip(new, old):
+            sn = {k: int(v) for k, v in zip(names, a)}
+            so = {k: int(v) for k, v in zip(names, b)}
+            if problem == "sokoban":
+                sn["solution"] = [0] * sn["sol-length"]
+                so["solution"] = [0] * so["sol-length"]
+            out.append(float(pobj.get_reward(sn, so)))
+        arrays[f"{problem}_new"], arrays[f"{problem}_old"], arrays[f"{problem}_reward"] = new, old, np.array(out)
+    path = os.path.join(OUT, "legacy_reward.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path)
+
+
 def save_stats_fixture(problem, grids, name=None):
     by_shape = {}
     for g in grids:
@@ -329,6 +367,7 @@ def main(which=None):
     SOK_AP = [0.62, 0.12, 0.04, 0.11, 0.11]        # biased so the solver preconditions hold now and then
     SMB_P = list(np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02]) / 0.95)
     jobs.update({
+        "legacy_reward": legacy_reward_fixture,
         "stats_sokoban": lambda: save_stats_fixture("sokoban", sokoban_grids()),
         "stats_smb": lambda: save_stats_fixture("smb", smb_grids()),
         "stats_maze3d": lambda: save_stats_fixture("minecraft_3D_maze", maze3d_grids(), "maze3d"),

@@ -158,6 +158,35 @@ def range_reward(new, old, low, high):
     return None
 
 
+_INF = float("inf")
+# Legacy Problem.get_reward tables: stat -> (low, high) band of get_range_reward and the weight the
+# (non-ctrl) Problem class hard-codes.  binary_prob.py:170-178 (:37-40); zelda_prob.py:135-153 (:33-41,
+# _max_enemies 5, _target_enemy_dist 4); sokoban_prob.py:185-229 (:44-52, _max_crates 3);
+# smb_prob.py:156-176 (:25-35).  minecraft_3D_maze's get_reward is commented out upstream.
+RANGE_BANDS = {
+    "binary": {"regions": (1, 1), "path-length": (125, 125)},
+    "zelda": {"player": (1, 1), "key": (1, 1), "door": (1, 10), "enemies": (2, 5), "regions": (1, 1),
+              "nearest-enemy": (4, _INF), "path-length": (_INF, _INF)},
+    "sokoban": {"player": (1, 1), "crate": (1, 3), "target": (1, 3), "regions": (1, 1), "ratio": (-_INF, -_INF),
+                "dist-win": (-_INF, -_INF), "sol-length": (_INF, _INF)},
+    "smb": {"dist-floor": (0, 0), "disjoint-tubes": (0, 0), "enemies": (10, 30), "empty": (900, _INF),
+            "noise": (0, 0), "jumps": (20, _INF), "jumps-dist": (0, 0), "dist-win": (0, 0)},
+}
+RANGE_WEIGHTS = {
+    "binary": {"regions": 100, "path-length": 100},
+    "zelda": {"player": 3, "key": 3, "door": 3, "regions": 5, "enemies": 1, "nearest-enemy": 2, "path-length": 1},
+    "sokoban": {"player": 3, "crate": 2, "target": 2, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1},
+    "smb": {"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2, "jumps-dist": 2,
+            "dist-win": 5},
+}
+
+
+def legacy_reward(problem, new, old):
+    """Problem.get_reward of the non-ctrl problem classes: sum of weighted get_range_reward terms."""
+    return sum(range_reward(new[k], old[k], *band) * RANGE_WEIGHTS[problem][k]
+               for k, band in RANGE_BANDS[problem].items())
+
+
 # --------------------------------------------------------------------------------------------
 # per-problem get_stats
 # --------------------------------------------------------------------------------------------
@@ -402,8 +431,9 @@ class OracleEnv:
     RNG stream is not part of the contract)."""
 
     def __init__(self, problem, rep, map_shape, weights=None, controls=None, max_board_scans=3,
-                 change_percentage=None, constants=None):
+                 change_percentage=None, constants=None, reward_mode="control"):
         self.problem, self.rep = problem, rep
+        self.reward_mode = reward_mode
         self.map_shape = tuple(map_shape)
         self.n_tiles = len(TILES[problem])
         c = constants or problem_constants(problem, self.map_shape)
@@ -441,8 +471,11 @@ class OracleEnv:
         done = self.iteration > self.max_iterations                             # :307
         if self.max_changes is not None:
             done = done or self.changes > self.max_changes                      # :308-309
+        old_stats = self.stats
         if changed:
             self.stats = get_stats(self.problem, self.grid)                     # :314-323
+        if self.reward_mode == "range":                                         # legacy Problem.get_reward
+            return legacy_reward(self.problem, self.stats, old_stats), bool(done), changed
         loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)
         reward = loss - self.last_loss                                          # control_wrappers.py:227-229
         self.last_loss = loss

@@ -76,3 +76,15 @@ def test_trace_matches_reference(name):
     tr = Trace(name)
     for e in range(tr.n_envs):
         replay_oracle(tr, e)
+
+
+def test_legacy_range_reward_matches_reference():
+    """Problem.get_reward of the reference's non-ctrl classes (fixture: oracle/gen_golden.py legacy_reward)."""
+    import os
+    from tests.golden_util import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "legacy_reward.npz"))
+    for problem in ("binary", "zelda", "sokoban", "smb"):
+        names = O.STAT_NAMES[problem]
+        for a, b, want in zip(z[f"{problem}_new"], z[f"{problem}_old"], z[f"{problem}_reward"]):
+            got = O.legacy_reward(problem, dict(zip(names, a.tolist())), dict(zip(names, b.tolist())))
+            assert got == want, (problem, a, b, got, want)
