@@ -307,9 +307,10 @@ def main():
         k_e2e = max(3, min(a.steps, 200))
         HP = min(k_e2e + 3, max(8, int(2e9 // bytes_a)))
         if rep == "cellular":
-            host_acts = [act_pool[i % POOL].cpu().numpy() for i in range(HP)]
+            host_acts = [act_pool[i % POOL].cpu().pin_memory() for i in range(HP)]
         else:
-            host_acts = [rng.integers(0, n_act, size=shape_a).astype(dt_a) for _ in range(HP)]
+            host_acts = [torch.from_numpy(rng.integers(0, n_act, size=shape_a).astype(dt_a)).pin_memory()
+                         for _ in range(HP)]
         for i in range(3):
             env.step_host(host_acts[i % HP])
         barrier()
@@ -332,7 +333,8 @@ def main():
         d2h = n_envs * (4 + 1 + 4 * env.K)
         e2e = {"value": world * n_envs * k_e2e / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e,
-               "api": "BatchedPcgrlEnv.step_host -> pcgrl_step_host (pinned actions H2D; reward,done,stats D2H; sync)"}
+               "api": "BatchedPcgrlEnv.step_host -> pcgrl_step_host (pinned actions H2D; reward,done,stats D2H to pinned "
+                      "host buffers; sync; binary/zelda shards pipelined in chunks over 3 streams)"}
 
     # ---- optional NCCL episode-stat reduction (off the step path; exercised once) ----------------
     red = reduce_episode_stats(env.stats, names=env.stat_names)

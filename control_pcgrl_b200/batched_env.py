@@ -275,14 +275,27 @@ class BatchedPcgrlEnv:
             self._pinned[name] = b
         return b
 
-    def step_host(self, actions: np.ndarray, want_stats=True):
+    def host_action_buffer(self, name="actions"):
+        """A pinned host tensor of the action layout; fill it and pass it to step_host to skip the staging copy."""
+        shape, dt = self.action_shape_dtype()
+        tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float32: torch.float32}[dt]
+        return torch.empty(shape, dtype=tdt, pin_memory=True) if name is None else self._pinned_buf(name, shape, tdt)
+
+    def step_host(self, actions, want_stats=True):
         """End-to-end step with HOST buffers (the call timed as `e2e`): actions are copied H2D from pinned
         memory, the fused kernel runs, reward / done / stats are copied back, and the stream is synchronised.
+        Large binary / zelda shards are cut into chunks whose upload, kernel and download overlap on helper
+        streams (pcgrl_step_host).  `actions`: numpy array (staged through a pinned buffer) or an already
+        pinned torch tensor of the action layout (used in place).
         Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats i32[N,K] or None)."""
         shape, dt = self.action_shape_dtype()
         tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float32: torch.float32}[dt]
-        a_pin = self._pinned_buf("actions", shape, tdt)
-        a_pin.numpy()[...] = np.asarray(actions, dtype=dt).reshape(shape)
+        if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() and \
+                actions.dtype == tdt and actions.is_contiguous() and actions.numel() == int(np.prod(shape)):
+            a_pin = actions
+        else:
+            a_pin = self._pinned_buf("actions", shape, tdt)
+            a_pin.numpy()[...] = np.asarray(actions, dtype=dt).reshape(shape)
         if self._actions_dev is None:
             self._actions_dev = torch.empty(shape, dtype=tdt, device=self.device)
         r = self._pinned_buf("reward", (self.n_envs,), torch.float32)

@@ -210,3 +210,43 @@ def test_host_step_and_facade():
         if t in d["obs_step"]:
             np.testing.assert_array_equal(ob, d["obs"][list(d["obs_step"]).index(t)])
     assert fenv.action_space.n == 2
+
+
+@pytest.mark.parametrize("problem,rep,shape,controls", [("binary", "narrow", (16, 16), None),
+                                                        ("binary", "wide", (16, 16), ["regions", "path-length"]),
+                                                        ("zelda", "turtle", (7, 11), None)])
+def test_pipelined_host_step_equals_device_step(problem, rep, shape, controls, monkeypatch):
+    """pcgrl_step_host cuts big shards into chunks pipelined over helper streams; every chunking must give
+    exactly what one whole-shard pcgrl_step gives (ragged last chunk, per-env targets, auto-reset ordering)."""
+    n = 70_001
+    kw = dict(obs_window=shape) if rep == "wide" else {}
+    a = _mk(problem, rep, shape, n, controls=controls, seed=3, auto_reset=True, max_board_scans=0.05, **kw)
+    b = _mk(problem, rep, shape, n, controls=controls, seed=3, auto_reset=True, max_board_scans=0.05, **kw)
+    if controls:
+        g = torch.Generator(device=a.device).manual_seed(1)
+        a.sample_uniform_targets(generator=g)
+        b.targets.copy_(a.targets)
+    a.reset()
+    b.reset()
+    assert torch.equal(a.grids, b.grids)
+    n_act = {"narrow": a.n_tiles, "turtle": 4 + a.n_tiles, "wide": shape[0] * shape[1] * a.n_tiles}[rep]
+    rng = np.random.default_rng(0)
+    pinned = a.host_action_buffer(None)
+    for t, chunks in enumerate(["1", "2", "5", "7", "", "64", "3", "4"] * 3):
+        if chunks:
+            monkeypatch.setenv("PCGRL_HOST_CHUNKS", chunks)
+        else:
+            monkeypatch.delenv("PCGRL_HOST_CHUNKS", raising=False)
+        act = rng.integers(0, n_act, size=n).astype(np.int32)
+        if t % 2:
+            pinned.numpy()[...] = act
+            r, d, s = a.step_host(pinned)
+        else:
+            r, d, s = a.step_host(act)
+        rb, db = b.step(torch.from_numpy(act).to(b.device))
+        # b.step's auto-reset already ran; its reward/done still hold the finishing step's outputs
+        np.testing.assert_array_equal(r, rb.cpu().numpy())
+        np.testing.assert_array_equal(d, db.cpu().numpy())
+        assert torch.equal(a.grids, b.grids) and torch.equal(a.stats, b.stats) and torch.equal(a.pos, b.pos)
+        assert torch.equal(a.iteration, b.iteration) and torch.equal(a.changes, b.changes)
+    a.check_status()
