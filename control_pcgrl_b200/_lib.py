@@ -8,13 +8,13 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PCGRL_ABI_VERSION = 2
+PCGRL_ABI_VERSION = 3
 MAX_STATS = 16
 MAX_TILES = 16
 
 PROB_IDS = {"binary": 0, "zelda": 1, "sokoban": 2, "smb": 3, "minecraft_3D_maze": 4}
 REP_IDS = {"narrow": 0, "turtle": 1, "wide": 2, "cellular": 3}
-ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS = range(5)
+ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS, ACT_PATCH = range(6)
 REWARD_CONTROL, REWARD_RANGE = 0, 1
 
 LIB_NAME = "libpcgrl_sm100.so"
@@ -30,6 +30,8 @@ class Config(C.Structure):
         ("max_changes", C.c_int32), ("act_h", C.c_int32), ("act_w", C.c_int32),
         ("targets_per_env", C.c_int32), ("init_random_probs", C.c_int32), ("reward_mode", C.c_int32),
         ("init_probs", C.c_float * MAX_TILES), ("weights", C.c_double * MAX_STATS),
+        ("act_window", C.c_int32 * 3), ("static_prob", C.c_float), ("n_static_walls", C.c_int32),
+        ("wall_tile", C.c_int32), ("static_eval_mode", C.c_int32),
     ]
 
 
@@ -38,7 +40,7 @@ class State(C.Structure):
         ("n_envs", C.c_int64), ("env_offset", C.c_int64), ("grids", C.c_void_p), ("pos", C.c_void_p),
         ("n_step", C.c_void_p), ("iteration", C.c_void_p), ("changes", C.c_void_p), ("stats", C.c_void_p),
         ("targets", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("changed", C.c_void_p),
-        ("status", C.c_void_p), ("scratch", C.c_void_p),
+        ("status", C.c_void_p), ("scratch", C.c_void_p), ("static_mask", C.c_void_p),
     ]
 
 
@@ -46,7 +48,7 @@ class ObsArgs(C.Structure):
     _fields_ = [
         ("crop", C.c_int32), ("obs_dims", C.c_int32 * 3), ("n_ctrl", C.c_int32),
         ("ctrl_idx", C.c_int32 * MAX_STATS), ("ctrl_range", C.c_double * MAX_STATS),
-        ("out_kind", C.c_int32), ("out", C.c_void_p),
+        ("out_kind", C.c_int32), ("out", C.c_void_p), ("static_channel", C.c_int32),
     ]
 
 

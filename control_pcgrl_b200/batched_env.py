@@ -68,11 +68,28 @@ class BatchedPcgrlEnv:
         self.param_ranges = {k: abs(self.cond_bounds[k][1] - self.cond_bounds[k][0]) for k in self.ctrl_metrics}
 
         rep = self.representation
+        # representation wrappers (envs/reps/wrappers.py wrap_rep :717-722)
+        self.act_window = c.act_window
+        if self.act_window is not None:
+            # MultiActionRepresentation only runs on the narrow rep upstream (turtle has no n_step, wide no _pos)
+            if rep != "narrow":
+                raise ValueError("act_window (MultiActionRepresentation) is only supported on the narrow representation")
+            if len(self.act_window) != self.ndim:
+                raise ValueError("act_window must have one entry per map axis (wrappers.py:425-426)")
+            if action_kind not in (None, "patch"):
+                raise ValueError("act_window needs action_kind 'patch'")
+            action_kind = "patch"
+        self.static_tile_wrapper = c.static_tile_wrapper
+        if self.static_tile_wrapper and rep not in ("narrow", "turtle"):
+            raise ValueError("static_tile_wrapper (StaticTileRepresentation) only runs on narrow / turtle upstream")
+        self.static_prob = float(c.static_prob or 0)
+        self.n_static_walls = int(c.n_static_walls or 0)
+        self._static_eval_mode = False
         if action_kind is None:
             action_kind = {"narrow": "int32", "turtle": "int32", "wide": "wide_flat", "cellular": "ca_logits"}[rep]
         self.action_kind = action_kind
         ak = {"int32": _lib.ACT_INT32, "wide_coords": _lib.ACT_WIDE_COORDS, "wide_flat": _lib.ACT_WIDE_FLAT,
-              "ca_tiles": _lib.ACT_CA_TILES, "ca_logits": _lib.ACT_CA_LOGITS}[action_kind]
+              "ca_tiles": _lib.ACT_CA_TILES, "ca_logits": _lib.ACT_CA_LOGITS, "patch": _lib.ACT_PATCH}[action_kind]
 
         cc = _lib.Config()
         cc.abi_version = _lib.PCGRL_ABI_VERSION
@@ -90,6 +107,13 @@ class BatchedPcgrlEnv:
         # ActionMap takes (h, w) from the observation space == obs_window (wrappers.py:283-287, SURVEY A-7)
         cc.act_h, cc.act_w = (self.obs_window[0], self.obs_window[1]) if ak == _lib.ACT_WIDE_FLAT else (0, 0)
         cc.targets_per_env = 1 if self.ctrl_metrics else 0
+        if action_kind == "patch":
+            for i in range(3):
+                cc.act_window[i] = self.act_window[i] if i < self.ndim else 1
+        if self.static_tile_wrapper:
+            cc.static_prob = self.static_prob
+            cc.n_static_walls = self.n_static_walls
+            cc.wall_tile = 1          # Problem._wall_tile = tiles[1] (envs/probs/problem.py:41)
         cc.init_random_probs = 1 if random_init_probs else 0
         # "control": ControlWrapper's loss delta (what step() pays at this commit); "range": the legacy
         # Problem.get_reward sum of get_range_reward terms (helper.py:550-560), bands in `targets`
@@ -121,6 +145,9 @@ class BatchedPcgrlEnv:
         self.done = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.changed = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        # StaticTileRepresentation.static_tiles over the map cells (border implicit), envs/reps/wrappers.py:277
+        self.static_mask = torch.zeros((N, self.row_stride), dtype=torch.uint8, device=dev) \
+            if self.static_tile_wrapper else None
         nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
         # zero-initialised once: the solver kernels keep generation counters for their hash tables in it
         self.scratch = torch.zeros(int(nscratch), dtype=torch.uint8, device=dev) if nscratch > 0 else None
@@ -137,6 +164,7 @@ class BatchedPcgrlEnv:
         st.iteration, st.changes, st.stats = _ptr(self.iteration), _ptr(self.changes), _ptr(self.stats)
         st.targets, st.reward, st.done = _ptr(self.targets), _ptr(self.reward), _ptr(self.done)
         st.changed, st.status, st.scratch = _ptr(self.changed), _ptr(self.status), _ptr(self.scratch)
+        st.static_mask = _ptr(self.static_mask)
         self._st = st
 
     # ------------------------------------------------------------------ targets
@@ -210,10 +238,42 @@ class BatchedPcgrlEnv:
         return out
 
     # ------------------------------------------------------------------ reset / step
-    def reset(self, grids=None, pos=None, mask=None):
+    # StaticTileRepresentation's setters (envs/reps/wrappers.py:268-275, used by rl/evaluate.py:128-129)
+    def set_eval_mode(self, eval_mode: bool):
+        self._static_eval_mode = bool(eval_mode)
+        self._cc.static_eval_mode = 1 if eval_mode else 0
+
+    def set_static_prob(self, static_prob):
+        self.static_prob = float(static_prob or 0)
+        self._cc.static_prob = self.static_prob
+
+    def set_n_static_walls(self, n_static_walls):
+        self.n_static_walls = int(n_static_walls or 0)
+        self._cc.n_static_walls = self.n_static_walls
+
+    @property
+    def static_tiles(self):
+        """[N, *map_shape] uint8 view of the frozen-tile masks (interior of StaticTileRepresentation.static_tiles)."""
+        if self.static_mask is None:
+            return None
+        return self.static_mask[:, :self.cells].view(self.n_envs, *self.map_shape)
+
+    def reset(self, grids=None, pos=None, mask=None, static_tiles=None):
         """Start episodes (all envs, or those where mask != 0).  grids: [N,*map_shape] initial maps
-        (PcgrlCtrlEnv.set_map semantics) or None for random maps; pos: [N,ndim] start positions."""
+        (PcgrlCtrlEnv.set_map semantics) or None for random maps; pos: [N,ndim] start positions;
+        static_tiles: [N,*map_shape] frozen-tile masks to use (with static_tile_wrapper; random resets draw
+        their own from static_prob / n_static_walls)."""
         src = self._pack_grids(grids) if grids is not None else None
+        if static_tiles is not None:
+            if self.static_mask is None:
+                raise ValueError("static_tiles needs cfg.static_tile_wrapper")
+            sm = torch.as_tensor(np.asarray(static_tiles) if not torch.is_tensor(static_tiles) else static_tiles)
+            sm = (sm.to(self.device) != 0).to(torch.uint8).reshape(self.n_envs, self.cells)
+            if mask is None:
+                self.static_mask[:, :self.cells] = sm
+            else:
+                sel = mask.to(self.device).bool()
+                self.static_mask[sel, :self.cells] = sm[sel]
         sp = None
         if pos is not None:
             p = torch.as_tensor(np.asarray(pos) if not torch.is_tensor(pos) else pos).to(self.device, torch.int32)
@@ -254,7 +314,8 @@ class BatchedPcgrlEnv:
         want = {"int32": ((self.n_envs,), torch.int32), "wide_flat": ((self.n_envs,), torch.int32),
                 "wide_coords": ((self.n_envs, self.ndim + 1), torch.int32),
                 "ca_tiles": ((self.n_envs, self.row_stride), torch.int8),
-                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), torch.float32)}[self.action_kind]
+                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), torch.float32),
+                "patch": ((self.n_envs, int(np.prod(self.act_window or (1,)))), torch.int32)}[self.action_kind]
         if actions.dtype != want[1]:
             raise TypeError(f"actions dtype {actions.dtype} != {want[1]} for action_kind {self.action_kind}")
         a = actions.reshape(want[0]) if actions.numel() == int(np.prod(want[0])) else None
@@ -266,7 +327,8 @@ class BatchedPcgrlEnv:
         return {"int32": ((self.n_envs,), np.int32), "wide_flat": ((self.n_envs,), np.int32),
                 "wide_coords": ((self.n_envs, self.ndim + 1), np.int32),
                 "ca_tiles": ((self.n_envs, self.row_stride), np.int8),
-                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), np.float32)}[self.action_kind]
+                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), np.float32),
+                "patch": ((self.n_envs, int(np.prod(self.act_window or (1,)))), np.int32)}[self.action_kind]
 
     def _pinned_buf(self, name, shape, dtype):
         b = self._pinned.get(name)
@@ -327,6 +389,7 @@ class BatchedPcgrlEnv:
         crop = self.representation in ("narrow", "turtle")
         dims = self.obs_window if crop else self.map_shape
         ch = (self.n_tiles + 1 if crop else self.n_tiles) + 2 * len(self.ctrl_metrics)
+        ch += 1 if self.static_mask is not None else 0      # 'static_builds' plane (wrappers.py:451-453)
         return (*dims, ch)
 
     def observe(self, out: torch.Tensor | None = None, dtype=torch.float32):
@@ -349,6 +412,7 @@ class BatchedPcgrlEnv:
             oa.ctrl_range[i] = float(self.param_ranges[k])
         oa.out_kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}[out.dtype]
         oa.out = out.data_ptr()
+        oa.static_channel = 1 if self.static_mask is not None else 0
         _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")
         return out
 
@@ -369,7 +433,8 @@ class BatchedPcgrlEnv:
     def state_dict(self):
         """Everything needed to reconstruct the env state (checkpoint row)."""
         return {k: getattr(self, k).clone() for k in
-                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets")}
+                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask")
+                if getattr(self, k) is not None}
 
     def load_state_dict(self, sd):
         for k, v in sd.items():

@@ -104,4 +104,10 @@ def normalise(cfg) -> SimpleNamespace:
                            weights=weights, controls=controls,
                            max_board_scans=_get(cfg, "max_board_scans", 3.0),
                            change_percentage=_get(cfg, "change_percentage", None),
-                           env_name=_get(cfg, "env_name", f"{problem}-{rep}-v0"))
+                           env_name=_get(cfg, "env_name", f"{problem}-{rep}-v0"),
+                           # representation wrappers (envs/reps/wrappers.py wrap_rep :717-722)
+                           act_window=(lambda a: None if a is None else tuple(int(v) for v in a))(
+                               _get(cfg, "act_window", None)),
+                           static_tile_wrapper=bool(_get(cfg, "static_tile_wrapper", False)),
+                           static_prob=_get(cfg, "static_prob", None),
+                           n_static_walls=_get(cfg, "n_static_walls", None))

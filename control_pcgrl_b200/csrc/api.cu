@@ -48,10 +48,24 @@ static int check(const pcgrl_config* c) {
     if (c->n_stats != k_of[c->problem]) return fail(PCGRL_E_ARG, "n_stats does not match the problem");
     const int r = c->representation, a = c->action_kind;
     const bool ok = ((r == PCGRL_REP_NARROW || r == PCGRL_REP_TURTLE) && a == PCGRL_ACT_INT32) ||
+                    (r == PCGRL_REP_NARROW && a == PCGRL_ACT_PATCH) ||
                     (r == PCGRL_REP_WIDE && (a == PCGRL_ACT_WIDE_COORDS || a == PCGRL_ACT_WIDE_FLAT)) ||
                     (r == PCGRL_REP_CELLULAR && (a == PCGRL_ACT_CA_TILES || a == PCGRL_ACT_CA_LOGITS));
     if (!ok) return fail(PCGRL_E_ARG, "action_kind does not fit the representation");
     if (a == PCGRL_ACT_WIDE_FLAT && (c->act_h < 1 || c->act_w < 1)) return fail(PCGRL_E_ARG, "act_h/act_w required");
+    if (a == PCGRL_ACT_PATCH) {
+        for (int i = 0; i < 3; ++i) {
+            const int dim = i < c->ndim ? c->dims[i] : 1;
+            if (c->act_window[i] < 1 || c->act_window[i] > dim)
+                return fail(PCGRL_E_ARG, "act_window must be within [1, dim] on every axis (1 on unused axes)");
+        }
+    } else if (c->act_window[0] > 1 || c->act_window[1] > 1 || c->act_window[2] > 1) {
+        return fail(PCGRL_E_ARG, "act_window needs action_kind PCGRL_ACT_PATCH (narrow representation)");
+    }
+    if (c->static_prob < 0.f || c->static_prob > 1.f || c->n_static_walls < 0)
+        return fail(PCGRL_E_ARG, "static_prob must be in [0,1] and n_static_walls >= 0");
+    if (c->n_static_walls > 0 && (c->wall_tile < 0 || c->wall_tile >= c->n_tiles))
+        return fail(PCGRL_E_ARG, "wall_tile out of range");
     if (c->reward_mode != PCGRL_REWARD_CONTROL && c->reward_mode != PCGRL_REWARD_RANGE)
         return fail(PCGRL_E_ARG, "unknown reward_mode");
     return 0;
@@ -76,6 +90,14 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
     p.targets_per_env = c->targets_per_env;
     p.init_random_probs = c->init_random_probs;
     p.reward_mode = c->reward_mode;
+    const bool patch = c->action_kind == PCGRL_ACT_PATCH;
+    p.aw0 = patch ? c->act_window[0] : 1;
+    p.aw1 = patch ? c->act_window[1] : 1;
+    p.aw2 = patch && c->ndim == 3 ? c->act_window[2] : 1;
+    p.static_prob = c->static_prob;
+    p.n_static_walls = c->n_static_walls;
+    p.wall_tile = c->wall_tile;
+    p.static_eval_mode = c->static_eval_mode;
     double tot = 0;
     for (int t = 0; t < c->n_tiles; ++t) tot += c->init_probs[t] > 0 ? c->init_probs[t] : 0;
     double run = 0;
@@ -99,6 +121,7 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
         p.changed = st->changed;
         p.status = st->status;
         p.scratch = st->scratch;
+        p.static_mask = st->static_mask;
     }
 }
 
@@ -179,6 +202,8 @@ int64_t pcgrl_step_bytes(const pcgrl_config* c) {
     int64_t A = 4;
     if (c->action_kind == PCGRL_ACT_WIDE_COORDS) A = 4 * (c->ndim + 1);
     if (c->action_kind == PCGRL_ACT_CA_TILES) A = G;
+    if (c->action_kind == PCGRL_ACT_PATCH)
+        A = 4 * (int64_t)c->act_window[0] * c->act_window[1] * (c->ndim == 3 ? c->act_window[2] : 1);
     if (c->action_kind == PCGRL_ACT_CA_LOGITS) A = 4 * (int64_t)c->n_tiles * G;
     return 2 * G + A + 8 * K + 5 + (c->targets_per_env ? 16 * K : 0);
 }
@@ -302,9 +327,12 @@ int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const vo
         sub.reward = st->reward + off;
         sub.done = st->done + off;
         sub.changed = st->changed ? st->changed + off : nullptr;
+        sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
         int64_t a_stride = a_env;
         if (!actions_host) {   // actions already on the device: per-env stride from the action layout
             a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)
+                     : cfg->action_kind == PCGRL_ACT_PATCH
+                         ? 4 * (int64_t)cfg->act_window[0] * cfg->act_window[1] * (cfg->ndim == 3 ? cfg->act_window[2] : 1)
                      : cfg->action_kind == PCGRL_ACT_CA_TILES ? cfg->row_stride
                      : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : 4;
         }

@@ -25,6 +25,7 @@ struct ObsParams {
     const int32_t* pos;
     const int32_t* stats;
     const double* targets;
+    const uint8_t* static_mask;   // NULL: no static_builds plane
     void* out;
 };
 
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
     const int64_t pix_per_env = (int64_t)p.o0 * p.o1 * p.o2;
     const int64_t total = p.n_envs * pix_per_env;
     const int n_map_ch = p.crop ? p.n_tiles + 1 : p.n_tiles;
-    const int n_ch = 2 * p.n_ctrl + n_map_ch;
+    const int n_ch = 2 * p.n_ctrl + n_map_ch + (p.static_mask ? 1 : 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t env = i / pix_per_env;
         int r = (int)(i - env * pix_per_env);
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
         r /= p.o2;
         const int q1 = r % p.o1;
         const int q0 = r / p.o1;
-        int hot;
+        int hot, frozen = 0;
         if (p.crop) {
             const int32_t* pos = p.pos + env * 3;
             const int s0 = pos[0] + q0 - p.o0 / 2, s1 = pos[1] + q1 - p.o1 / 2;
@@ -50,6 +51,19 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
                 hot = p.grids[env * p.row_stride + (s0 * p.d1 + s1) * p.d2 + s2] + 1;
             else
                 hot = 0;
+            if (p.static_mask) {
+                // 'static_builds' (wrappers.py:451-459): the (dims+2) BORDERED mask goes through the same pad and
+                // crop as the map, so window cell o shows bordered cell pos + o - obs//2 = map cell (that - 1);
+                // border cells are always frozen (envs/reps/wrappers.py:310-312), beyond the border is padding (0)
+                const int b0 = s0 - 1, b1 = s1 - 1, b2 = (p.ndim == 3) ? s2 - 1 : 0;
+                const bool in_bordered = b0 >= -1 && b0 <= p.d0 && b1 >= -1 && b1 <= p.d1 &&
+                                         (p.ndim != 3 || (b2 >= -1 && b2 <= p.d2));
+                if (in_bordered) {
+                    const bool inner = (unsigned)b0 < (unsigned)p.d0 && (unsigned)b1 < (unsigned)p.d1 &&
+                                       (unsigned)b2 < (unsigned)p.d2;
+                    frozen = inner ? p.static_mask[env * p.row_stride + (b0 * p.d1 + b1) * p.d2 + b2] != 0 : 1;
+                }
+            }
         } else {
             hot = p.grids[env * p.row_stride + (q0 * p.d1 + q1) * p.d2 + q2];
         }
@@ -64,6 +78,7 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
         }
         o += 2 * p.n_ctrl;
         for (int c = 0; c < n_map_ch; ++c) o[c] = (T)(c == hot ? 1 : 0);
+        if (p.static_mask) o[n_map_ch] = (T)frozen;
     }
 }
 
@@ -91,6 +106,11 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     p.pos = st.pos;
     p.stats = st.stats;
     p.targets = st.targets;
+    p.static_mask = nullptr;
+    if (a.static_channel) {
+        if (!a.crop || !st.static_mask) return cudaErrorInvalidValue;
+        p.static_mask = st.static_mask;
+    }
     p.out = a.out;
     if (!a.crop && (p.o0 != p.d0 || p.o1 != p.d1 || p.o2 != p.d2)) return cudaErrorInvalidValue;
     if (a.out_kind == 0 && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional

@@ -52,6 +52,11 @@ struct KParams {
     // stats-only mode
     const int8_t* stats_grids;
     int32_t* stats_out;
+    // representation wrappers (envs/reps/wrappers.py): action patch, frozen tiles
+    int32_t aw0, aw1, aw2;        // MultiActionRepresentation patch size per axis (all 1 when off)
+    uint8_t* static_mask;         // [N, row_stride] or NULL
+    float   static_prob;
+    int32_t n_static_walls, wall_tile, static_eval_mode;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -12,12 +12,56 @@ __device__ __forceinline__ int cell_index(const KParams& p, int a0, int a1, int 
     return (a0 * p.d1 + a1) * p.d2 + a2;
 }
 
-// Apply one non-cellular action to env `gid`.  Returns change (0/1); updates pos / n_step in HBM.
+// Apply one non-cellular action to env `gid`; updates pos / n_step in HBM.
+// Returns bit0 = change (what PcgrlEnv counts in _changes), bit1 = the grid was actually modified.  The two
+// differ only under StaticTileRepresentation (envs/reps/wrappers.py:358-376): an edit of a frozen cell is
+// undone (`np.where(static_tiles < 1, new, old)`), but `change = np.any(old_state != new_state)` compares
+// against the pre-undo array, so it still counts as a change (and the reference recomputes identical stats).
 __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
     int8_t* grid = p.grids + gid * p.row_stride;
     int32_t* pos = p.pos + gid * 3;
-    int change = 0;
-    if (p.rep == PCGRL_REP_NARROW) {
+    const uint8_t* frozen = p.static_mask ? p.static_mask + gid * p.row_stride : nullptr;
+    int change = 0, wrote = 0;
+    if (p.rep == PCGRL_REP_NARROW && p.action_kind == PCGRL_ACT_PATCH) {
+        // MultiActionRepresentation.update (envs/reps/wrappers.py:466-528): the patch action.reshape(act_window)
+        // replaces map[pos - l_pad : pos + r_pad + 1], l_pad = floor((a-1)/2), r_pad = ceil((a-1)/2) (:404-411);
+        // change = any cell differs; then pos = act_coords[n_step % len], n_step += 1 (:517-518)
+        const int np_ = p.aw0 * p.aw1 * p.aw2;
+        const int32_t* a = (const int32_t*)p.actions + gid * np_;
+        const int l0 = (p.aw0 - 1) / 2, l1 = (p.aw1 - 1) / 2, l2 = (p.aw2 - 1) / 2;
+        const int t0 = pos[0] - l0, t1 = pos[1] - l1, t2 = pos[2] - l2;
+        if (t0 < 0 || t1 < 0 || t2 < 0 || t0 + p.aw0 > p.d0 || t1 + p.aw1 > p.d1 || t2 + p.aw2 > p.d2) {
+            if (p.status) atomicOr(p.status, 1);   // the reference asserts the patch lies inside the map (:498-501)
+        } else {
+            int idx = 0;
+            for (int i0 = 0; i0 < p.aw0; ++i0)
+                for (int i1 = 0; i1 < p.aw1; ++i1)
+                    for (int i2 = 0; i2 < p.aw2; ++i2, ++idx) {
+                        const int v = a[idx];
+                        if ((unsigned)v >= (unsigned)p.n_tiles) {
+                            if (p.status) atomicOr(p.status, 1);
+                            continue;
+                        }
+                        const int c = cell_index(p, t0 + i0, t1 + i1, t2 + i2);
+                        if (grid[c] != v) {
+                            change = 1;
+                            if (!frozen || !frozen[c]) {
+                                grid[c] = (int8_t)v;
+                                wrote = 1;
+                            }
+                        }
+                    }
+        }
+        // get_act_coords (:445-463): np.meshgrid(*ranges).T.reshape(-1, ndim) -- row-major in 2D; in 3D the
+        // LAST axis is the slowest, then axis 0, then axis 1 (meshgrid's 'xy' indexing swaps the first two)
+        const int n0 = p.d0 - p.aw0 + 1, n1 = p.d1 - p.aw1 + 1, n2 = p.d2 - p.aw2 + 1;
+        const int ns = p.n_step[gid];
+        const int k = ns % (n0 * n1 * n2);
+        pos[1] = l1 + k % n1;
+        pos[0] = l0 + (k / n1) % n0;
+        pos[2] = l2 + k / (n1 * n0);
+        p.n_step[gid] = ns + 1;
+    } else if (p.rep == PCGRL_REP_NARROW) {
         // reps/narrow_rep.py:89-102: write at _pos, then _pos = coords[n_step % N], then n_step += 1
         const int a = ((const int32_t*)p.actions)[gid];
         const int c = cell_index(p, pos[0], pos[1], pos[2]);
@@ -26,7 +70,8 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
         } else {
             const int old = grid[c];
             change = old != a;
-            if (change) grid[c] = (int8_t)a;
+            wrote = change && !(frozen && frozen[c]);
+            if (wrote) grid[c] = (int8_t)a;
         }
         const int ns = p.n_step[gid];
         const int k = ns % p.cells;
@@ -47,7 +92,8 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
             const int t = a - 4;
             const int old = grid[c];
             change = old != t;
-            if (change) grid[c] = (int8_t)t;
+            wrote = change && !(frozen && frozen[c]);
+            if (wrote) grid[c] = (int8_t)t;
         } else if (p.status) {
             atomicOr(p.status, 1);
         }
@@ -76,13 +122,14 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
             const int c = cell_index(p, q0, q1, q2);
             const int old = grid[c];
             change = old != v;
+            wrote = change;   // the reference's wide / cellular reps do not run under StaticTileRepresentation
             if (change) grid[c] = (int8_t)v;
             pos[0] = q0;
             pos[1] = q1;
             pos[2] = q2;
         }
     }
-    return change;
+    return change | (wrote << 1);
 }
 
 // Episode start for env `gid` (thread-per-env): grid from src or Philox, counters, start position.
@@ -131,8 +178,61 @@ __device__ static void reset_env(const KParams& p, int64_t gid) {
             *(uint4*)(grid + c0) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
+    if (!p.src_grids && p.static_mask && (p.static_prob > 0.f || p.n_static_walls > 0)) {
+        // StaticTileRepresentation.reset (envs/reps/wrappers.py:275-312).  Only the random-reset generator: with
+        // caller-supplied maps the caller owns the mask (the reference's RNG stream is not part of the contract).
+        uint8_t* sm = p.static_mask + gid * p.row_stride;
+        float ps = 0.f;
+        if (p.static_prob > 0.f) {   // :279-289 per-episode probability U(0,1) * static_prob (or fixed when evaluating)
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch, 0xB0000000u), key);
+            ps = p.static_eval_mode ? p.static_prob : u01(r.x) * p.static_prob;
+        }
+        for (int c0 = 0; c0 < p.row_stride; c0 += 16) {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if (ps > 0.f)
+                for (int q = 0; q < 4; ++q) {
+                    const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
+                                                             0x40000000u + (uint32_t)(c0 / 4 + q)), key);
+                    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+                    for (int j = 0; j < 4; ++j)
+                        if (c0 + q * 4 + j < p.cells && u01(rr[j]) < ps) w[q] |= 1u << (8 * j);
+                }
+            *(uint4*)(sm + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // :291-308 random wall segments.  Restated with the reference's indexing: every start coordinate is drawn
+        // from the length of the wall's own axis, the frozen cells are wall_pos in BORDERED coordinates (= map
+        // coordinates wall_pos - 1) while the wall tiles are written to _map at wall_pos itself, i.e. one cell
+        // further along every axis; numpy slicing clips whatever falls outside.
+        const int dims[3] = {p.d0, p.d1, p.d2};
+        for (int wi = 0; wi < p.n_static_walls; ++wi) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
+                                                     0xA0000000u + 2u * wi), key);
+            const uint4 r2 = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch,
+                                                      0xA0000001u + 2u * wi), key);
+            const int dim = (int)(r.x % (uint32_t)p.ndim);
+            const int L = dims[dim];
+            if (L < 3) continue;   // integers(1, L - 1) needs L >= 3
+            const int len = 1 + (int)(r.y % (uint32_t)(L - 2));
+            int wp[3] = {(int)(r.z % (uint32_t)L), (int)(r.w % (uint32_t)L), (int)(r2.x % (uint32_t)L)};
+            wp[dim] = (int)(r2.y % (uint32_t)(L - len));
+            if (p.ndim == 2) wp[2] = 0;
+            for (int i = 0; i < len; ++i) {
+                int m[3] = {wp[0], wp[1], wp[2]};
+                m[dim] += i;
+                if (m[0] < p.d0 && m[1] < p.d1 && m[2] < p.d2) sm[cell_index(p, m[0], m[1], m[2])] = 1;
+                const int t0 = m[0] + 1, t1 = m[1] + 1, t2 = p.ndim == 3 ? m[2] + 1 : 0;
+                if (t0 < p.d0 && t1 < p.d1 && t2 < p.d2) grid[cell_index(p, t0, t1, t2)] = (int8_t)p.wall_tile;
+            }
+        }
+    }
     int32_t* pos = p.pos + gid * 3;
     pos[0] = pos[1] = pos[2] = 0;
+    if (p.rep == PCGRL_REP_NARROW && p.action_kind == PCGRL_ACT_PATCH) {
+        // the scan starts at act_coords[0] = the inner left pads (envs/reps/wrappers.py:404-411, 445-463)
+        pos[0] = (p.aw0 - 1) / 2;
+        pos[1] = (p.aw1 - 1) / 2;
+        pos[2] = (p.aw2 - 1) / 2;
+    }
     if (p.src_pos) {
         pos[0] = p.src_pos[gid * 3 + 0];
         pos[1] = p.src_pos[gid * 3 + 1];
@@ -207,7 +307,8 @@ __device__ __forceinline__ void phase_a(const KParams& p, int64_t base, int tile
         if (e < tile_n) {
             const int64_t gid = base + e;
             if (p.mode == MODE_STEP) {
-                int change = (p.rep == PCGRL_REP_CELLULAR) ? (int)s_flag[e] : apply_action(p, gid);
+                const int cw = (p.rep == PCGRL_REP_CELLULAR) ? 3 * (int)s_flag[e] : apply_action(p, gid);
+                const int change = cw & 1;
                 const int it = p.iteration[gid] + 1;   // pcgrl_env.py:279
                 const int ch = p.changes[gid] + change;
                 p.iteration[gid] = it;
@@ -216,7 +317,8 @@ __device__ __forceinline__ void phase_a(const KParams& p, int64_t base, int tile
                 if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
                 p.done[gid] = done;
                 if (p.changed) p.changed[gid] = change != 0;
-                need = change != 0;                    // :314 stats only when the map changed
+                need = (cw & 2) != 0;                  // :314 stats only when the map changed (an undone edit of a
+                                                       // frozen tile leaves map, stats and loss as they were)
                 if (!need) p.reward[gid] = 0.f;
             } else if (p.mode == MODE_RESET) {
                 need = p.mask == nullptr || p.mask[gid] != 0;

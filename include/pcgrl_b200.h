@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCGRL_ABI_VERSION 2
+#define PCGRL_ABI_VERSION 3
 
 /* problems: envs/probs/__init__.py:31-58 (the five BASELINE.json names) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_SMB = 3,
@@ -40,8 +40,11 @@ enum {
     PCGRL_ACT_WIDE_FLAT = 2,   /* wide: int32[N] flat ActionMap index over (act_h, act_w, C); writes _map[x, y]
                                   (wrappers.py:304-323)                                                      */
     PCGRL_ACT_CA_TILES = 3,    /* cellular: int8[N, row_stride] already-argmaxed next map                    */
-    PCGRL_ACT_CA_LOGITS = 4    /* cellular: float32[N, C, cells] logits; argmax over C, lowest index wins
+    PCGRL_ACT_CA_LOGITS = 4,   /* cellular: float32[N, C, cells] logits; argmax over C, lowest index wins
                                   (reps/ca_rep.py:31-44, wrappers.py:157-165)                                */
+    PCGRL_ACT_PATCH = 5        /* narrow + MultiActionRepresentation (cfg.act_window): int32[N, prod(act_window)]
+                                  tile codes of the whole patch, C order of action.reshape(act_window)
+                                  (envs/reps/wrappers.py:397-545; MultiDiscrete([C] * prod), :438-443)        */
 };
 /* how `reward` is computed from the old and new stats */
 enum {
@@ -78,6 +81,14 @@ typedef struct pcgrl_config {
     float   init_probs[PCGRL_MAX_TILES]; /* tile init distribution, normalised by the library */
     double  weights[PCGRL_MAX_STATS];    /* ControlWrapper.metric_weights per stat (0 = not in all_metrics),
                                             control_wrappers.py:41-45,78-84 */
+    /* -- representation wrappers (envs/reps/wrappers.py wrap_rep :717-722), ABI 3 -------------------------- */
+    int32_t act_window[3];    /* MultiActionRepresentation: size of the action patch per map axis
+                                 (cfg.act_window, wrappers.py:413-417); {0,0,0} = off.  Needs PCGRL_ACT_PATCH */
+    float   static_prob;      /* StaticTileRepresentation, random resets only: upper bound of the per-episode
+                                 frozen-tile probability (wrappers.py:279-289); 0 = none */
+    int32_t n_static_walls;   /* random resets only: number of frozen random wall segments (wrappers.py:291-308) */
+    int32_t wall_tile;        /* tile code written along those walls (Problem._wall_tile, pcgrl_env.py:58) */
+    int32_t static_eval_mode; /* 1: use static_prob itself instead of U(0,1)*static_prob (set_eval_mode, :268) */
 } pcgrl_config;
 
 /* Device-resident state of N envs + the per-step inputs/outputs.
@@ -106,6 +117,11 @@ typedef struct pcgrl_state {
     void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0.  Must be zero-filled
                               once before its first use (it holds hash-table generation counters) and must not
                               be shared by launches that can run concurrently */
+    uint8_t* static_mask;  /* [N, row_stride] or NULL (ABI 3): StaticTileRepresentation.static_tiles over the map
+                              cells (the always-frozen border is implicit).  A frozen cell keeps its tile: the
+                              edit is undone, yet still counted as a change (envs/reps/wrappers.py:358-376).
+                              Written by random resets when cfg.static_prob / n_static_walls ask for it; with
+                              caller-supplied src_grids it is left as the caller set it */
 } pcgrl_state;
 
 /* -- queries (host only, no CUDA calls) ------------------------------------------------------- */
@@ -144,7 +160,8 @@ int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats
  *   crop == 0 : the whole map, C one-hot channels (wide / cellular stacks)
  *   n_ctrl controlled metrics prepend 2*n_ctrl constant planes (trg/range, value/range); ctrl_idx[i] is the
  *   stat index, ctrl_range[i] = |hi - lo| of cond_bounds.
- *   out_kind: 0 = uint8, 1 = float32, 2 = float64 (the reference's np.eye dtype).  Output layout [N, *obs_dims, channels] (channels last). */
+ *   out_kind: 0 = uint8, 1 = float32, 2 = float64 (the reference's np.eye dtype).  Output layout [N, *obs_dims, channels] (channels last):
+ *   [2*n_ctrl target planes | C+1 or C one-hot | static_builds]. */
 typedef struct pcgrl_obs_args {
     int32_t crop;
     int32_t obs_dims[3];
@@ -153,6 +170,9 @@ typedef struct pcgrl_obs_args {
     double  ctrl_range[PCGRL_MAX_STATS];
     int32_t out_kind;
     void*   out;
+    int32_t static_channel;   /* ABI 3, crop only: append the 'static_builds' plane after the one-hot channels
+                                 (wrappers.py:451-453): the BORDERED frozen-tile mask cropped with the map's
+                                 padding, i.e. sampled one cell up-left of the map channels (border = 1) */
 } pcgrl_obs_args;
 int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgrl_obs_args* obs, void* stream);
 

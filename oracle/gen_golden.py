@@ -254,13 +254,18 @@ def save_stats_fixture(problem, grids, name=None):
 # ------------------------------------------------------------------------------------------ traces
 def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None, n_envs=4, seed=0,
               max_board_scans=3, change_percentage=None, raw_only=False, n_steps=None, init_p=None,
-              targets=None, obs_every=97, action_p=None, grid_every=1):
+              targets=None, obs_every=97, action_p=None, grid_every=1, act_window=None, static_prob=None):
     rng = np.random.default_rng(seed)
     cfg = R.make_cfg(problem, rep, map_shape, obs_window=obs_window, weights=weights, controls=controls,
                      max_board_scans=max_board_scans, change_percentage=change_percentage)
+    # representation wrappers (envs/reps/wrappers.py wrap_rep :717-722)
+    if act_window is not None:
+        cfg.act_window = list(act_window)
+    if static_prob is not None:
+        cfg.static_tile_wrapper, cfg.static_prob = True, static_prob
     n_tiles = len(TILES[problem])
     rec = dict(grid0=[], pos0=[], actions=[], rewards=[], dones=[], stats=[], pos=[], grids=[], stats0=[],
-               obs=[], obs_step=[], obs0=[], changes=[], trg=[], grids_step=[])
+               obs=[], obs_step=[], obs0=[], changes=[], trg=[], grids_step=[], static=[])
     for e in range(n_envs):
         env = R.make_wrapped_env(cfg, raw_only=raw_only)
         if init_p is None:
@@ -276,6 +281,13 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
         ob, _ = env.reset()
         u = env.unwrapped
         rep_obj = u._rep.unwrapped
+        static_e = np.zeros((0,), dtype=np.uint8)
+        if static_prob is not None:
+            w = u._rep
+            while not hasattr(w, "static_tiles"):
+                w = w.rep
+            inner = tuple(slice(1, -1) for _ in map_shape)
+            static_e = np.array(w.static_tiles[inner], dtype=np.uint8)      # interior of the bordered mask
         pos0 = [int(v) for v in rep_obj._pos] if rep in ("narrow", "turtle") else [0] * len(map_shape)
         stats0 = [int(u._rep_stats[k]) for k in STAT_NAMES[problem]]
         acts, rews, dones, stats, poss, grids, obs_l, obs_s, chg, grid_s = [], [], [], [], [], [], [], [], [], []
@@ -289,6 +301,15 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
                     if t % 6 == 2:
                         a[(slice(None), *[rng.integers(s) for s in map_shape])] = rng.random(n_tiles)
                 act_store = a
+            elif act_window is not None:
+                a = rng.integers(0, n_tiles, size=int(np.prod(act_window)))
+                if t % 4 == 3:      # sometimes a no-op patch (the current tiles) or a single-cell edit
+                    tl = [int(rep_obj._pos[i]) - (act_window[i] - 1) // 2 for i in range(len(map_shape))]
+                    cur = rep_obj._map[tuple(slice(tl[i], tl[i] + act_window[i]) for i in range(len(map_shape)))]
+                    a = np.array(cur, dtype=np.int64).reshape(-1)
+                    if t % 8 == 7:
+                        a[rng.integers(a.size)] = rng.integers(n_tiles)
+                act_store = np.array(a)
             elif rep == "wide" and raw_only:
                 a = [int(rng.integers(s)) for s in map_shape] + [int(rng.integers(n_tiles))]
                 act_store = np.array(a)
@@ -316,6 +337,7 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
         rec["stats"].append(stats); rec["pos"].append(poss); rec["grids"].append(np.stack(grids))
         rec["obs"].append(np.stack(obs_l) if obs_l else np.zeros((0,))); rec["obs_step"].append(obs_s)
         rec["changes"].append(chg); rec["trg"].append(trg_e); rec["grids_step"].append(grid_s)
+        rec["static"].append(static_e)
     arrays = {"n_envs": np.array(n_envs)}
     for k, v in rec.items():
         if k == "obs0":
@@ -331,6 +353,8 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
     arrays["meta_weight_vals"] = np.array(list(weights.values()), dtype=np.float64)
     arrays["meta_raw_only"] = np.array(raw_only)
     arrays["meta_targets"] = np.array(targets or [], dtype=str)
+    arrays["meta_act_window"] = np.array(act_window or [], dtype=np.int64)
+    arrays["meta_static"] = np.array(static_prob is not None)
     path = os.path.join(OUT, f"trace_{name}.npz")
     np.savez_compressed(path, **arrays)
     print("wrote", path, "steps", [arrays[f"rewards_{e}"].shape[0] for e in range(n_envs)], "bytes", os.path.getsize(path))
@@ -393,6 +417,33 @@ def main(which=None):
         "trace_maze3d_cellular": lambda: run_trace("maze3d_cellular", "minecraft_3D_maze", "cellular", (6, 6, 6),
                                                    (6, 6, 6), MC_W, seed=19, raw_only=True, n_envs=2, n_steps=30,
                                                    init_p=[0.5, 0.5]),
+    })
+    # representation wrappers: MultiActionRepresentation (narrow only upstream) and StaticTileRepresentation
+    # (narrow / turtle only upstream)
+    ZP = [0.58, 0.3, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02]
+    jobs.update({
+        "trace_binary_patch33": lambda: run_trace("binary_patch33", "binary", "narrow", (16, 16), (32, 32), BINARY_W,
+                                                  seed=30, act_window=(3, 3), n_envs=3, max_board_scans=1, grid_every=7),
+        "trace_binary_patch42_chg": lambda: run_trace("binary_patch42_chg", "binary", "narrow", (16, 16), (32, 32),
+                                                      BINARY_W, seed=31, act_window=(4, 2), n_envs=3,
+                                                      change_percentage=0.4, grid_every=7),
+        "trace_zelda_squeegee": lambda: run_trace("zelda_squeegee", "zelda", "narrow", (7, 11), (22, 22), ZELDA_W,
+                                                  seed=32, act_window=(7, 1), n_envs=2, init_p=ZP, grid_every=3),
+        "trace_maze3d_patch": lambda: run_trace("maze3d_patch", "minecraft_3D_maze", "narrow", (6, 6, 6), (6, 6, 6), MC_W,
+                                                seed=33, raw_only=True, n_envs=2, act_window=(2, 3, 2), grid_every=20,
+                                                init_p=[0.5, 0.5]),
+        "trace_binary_static_narrow": lambda: run_trace("binary_static_narrow", "binary", "narrow", (16, 16), (32, 32),
+                                                        BINARY_W, seed=34, static_prob=0.8, n_envs=4, grid_every=11,
+                                                        change_percentage=0.5),
+        "trace_zelda_static_turtle": lambda: run_trace("zelda_static_turtle", "zelda", "turtle", (7, 11), (22, 22),
+                                                       ZELDA_W, seed=35, static_prob=0.9, n_envs=3, init_p=ZP,
+                                                       grid_every=5, obs_every=31),
+        "trace_binary_static_patch": lambda: run_trace("binary_static_patch", "binary", "narrow", (16, 16), (32, 32),
+                                                       BINARY_W, seed=36, static_prob=0.7, act_window=(3, 3), n_envs=3,
+                                                       max_board_scans=1, grid_every=7),
+        "trace_sokoban_static_narrow": lambda: run_trace("sokoban_static_narrow", "sokoban", "narrow", (5, 5), (10, 10),
+                                                         SOK_W, seed=37, static_prob=0.6, init_p=SOK_AP, action_p=SOK_AP,
+                                                         n_envs=3, obs_every=17),
     })
     for k, fn in jobs.items():
         if which and k not in which:

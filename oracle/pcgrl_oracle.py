@@ -348,8 +348,30 @@ def narrow_coords(map_shape):
     return np.argwhere(np.ones(map_shape, dtype=bool))
 
 
+def multiaction_coords(map_shape, act_window):
+    """envs/reps/wrappers.py:445-463 MultiActionRepresentation.get_act_coords (+ :404-411 inner pads).
+
+    Positions the patch can be centred on: per axis arange(floor((a-1)/2), dim - ceil((a-1)/2)), combined as
+    np.meshgrid(*ranges).T.reshape(-1, ndim): row-major in 2D; in 3D meshgrid's default 'xy' indexing makes the
+    LAST axis the slowest, then axis 0, then axis 1.
+    """
+    nd = len(map_shape)
+    lo = [(int(a) - 1) // 2 for a in act_window]
+    hi = [int(d) - (int(a) - 1 - (int(a) - 1) // 2) for d, a in zip(map_shape, act_window)]
+    rng = [range(lo[i], hi[i]) for i in range(nd)]
+    if nd == 2:
+        return np.array([[i, j] for i in rng[0] for j in rng[1]], dtype=np.int64)
+    return np.array([[i, j, k] for k in rng[2] for i in rng[0] for j in rng[1]], dtype=np.int64)
+
+
 def rep_update(rep, grid, state, action):
     """One representation update, in place.  Returns `change` (0/1).
+
+    Representation wrappers (envs/reps/wrappers.py), when present in `state`:
+      act_window  MultiActionRepresentation.update :466-528 (narrow only): the patch action.reshape(act_window)
+                  replaces map[pos - l_pad : pos + r_pad + 1]; change = any cell differs
+      static      StaticTileRepresentation.update :358-376: np.where(static < 1, new, old) undoes edits of frozen
+                  cells, while `change` stays what the inner update saw on the pre-undo array
 
     state: dict with 'pos' (list, [y,x] or [z,y,x]) and 'n_step' (narrow only).
     narrow  reps/narrow_rep.py:89-102  (position refreshed with n_step *before* the increment)
@@ -357,6 +379,30 @@ def rep_update(rep, grid, state, action):
     wide    reps/wide_rep.py:35-40     (action = [*coords, tile])
     cellular reps/ca_rep.py:31-44      (action[C,*dims] -> argmax over axis 0, lowest index wins)
     """
+    static = state.get("static")
+    if static is not None:
+        old = grid.copy()
+        inner = dict(state)
+        inner["static"] = None
+        change = rep_update(rep, grid, inner, action)
+        for k in ("pos", "n_step"):
+            if k in inner:
+                state[k] = inner[k]
+        if change > 0:
+            grid[...] = np.where(static < 1, grid, old)
+        return change
+    if rep == "narrow" and state.get("act_window") is not None:
+        aw = [int(a) for a in state["act_window"]]
+        patch = np.asarray(action).reshape(aw)
+        tl = [state["pos"][i] - (aw[i] - 1) // 2 for i in range(len(aw))]
+        assert all(t >= 0 for t in tl) and all(tl[i] + aw[i] <= grid.shape[i] for i in range(len(aw)))
+        sl = tuple(slice(tl[i], tl[i] + aw[i]) for i in range(len(aw)))
+        change = int(np.any(grid[sl] != patch))
+        grid[sl] = patch
+        coords = state["coords"]
+        state["pos"] = [int(v) for v in coords[state["n_step"] % len(coords)]]
+        state["n_step"] += 1
+        return change
     if rep == "narrow":
         p = tuple(state["pos"])
         change = int(grid[p] != action)
@@ -404,6 +450,21 @@ def cropped_onehot(grid, pos, obs_window, n_tiles):
     return np.eye(n_tiles + 1)[idx]
 
 
+def static_builds_crop(static, pos, obs_window):
+    """wrappers.py:451-459 + 407-437: the 'static_builds' observation is the BORDERED mask (dims + 2, border = 1,
+    envs/reps/wrappers.py:277,310-312) padded and cropped exactly like the (unbordered) map, so it is sampled one
+    cell up-left of the map channels; beyond the border it is padding (0)."""
+    ow = tuple(int(v) for v in obs_window)
+    bordered = np.ones(tuple(d + 2 for d in static.shape), dtype=np.int64)
+    bordered[tuple(slice(1, -1) for _ in static.shape)] = static
+    out = np.zeros(ow, dtype=np.float64)
+    for o in np.ndindex(*ow):
+        src = tuple(pos[i] + o[i] - ow[i] // 2 for i in range(len(ow)))
+        if all(0 <= src[i] < bordered.shape[i] for i in range(len(ow))):
+            out[o] = bordered[src]
+    return out
+
+
 def full_onehot(grid, n_tiles):
     """ActionMapImagePCGRLWrapper (wrappers.py:502-526): one-hot of the whole map, no OOB channel."""
     return np.eye(n_tiles)[np.asarray(grid, dtype=np.int64)]
@@ -431,8 +492,9 @@ class OracleEnv:
     RNG stream is not part of the contract)."""
 
     def __init__(self, problem, rep, map_shape, weights=None, controls=None, max_board_scans=3,
-                 change_percentage=None, constants=None, reward_mode="control"):
+                 change_percentage=None, constants=None, reward_mode="control", act_window=None):
         self.problem, self.rep = problem, rep
+        self.act_window = None if act_window is None else tuple(int(a) for a in act_window)
         self.reward_mode = reward_mode
         self.map_shape = tuple(map_shape)
         self.n_tiles = len(TILES[problem])
@@ -446,15 +508,17 @@ class OracleEnv:
         cells = int(np.prod(self.map_shape))
         self.max_iterations = cells * max_board_scans + 1                       # pcgrl_env.py:241
         self.max_changes = None if change_percentage is None else max(int(change_percentage * cells), 1)
-        self.coords = narrow_coords(self.map_shape)
+        self.coords = narrow_coords(self.map_shape) if self.act_window is None else \
+            multiaction_coords(self.map_shape, self.act_window)
 
-    def reset(self, grid, pos=None, targets=None):
+    def reset(self, grid, pos=None, targets=None, static=None):
         if targets:
             self.targets.update(targets)                                        # control_wrappers.py:170-178
         self.grid = np.array(grid, dtype=np.int64).reshape(self.map_shape)
         self.iteration = 0
         self.changes = 0
-        self.state = {"coords": self.coords, "n_step": 0,
+        self.state = {"coords": self.coords, "n_step": 0, "act_window": self.act_window,
+                      "static": None if static is None else np.array(static, dtype=np.int64).reshape(self.map_shape),
                       "pos": [0] * len(self.map_shape) if pos is None else [int(v) for v in pos]}
         if self.rep == "narrow":
             self.state["pos"] = [int(v) for v in self.coords[0]]               # narrow_rep.py:43-50

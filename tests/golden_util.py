@@ -32,6 +32,10 @@ class Trace:
         self.weights = {str(k): float(v) for k, v in zip(z["meta_weight_keys"], z["meta_weight_vals"])}
         self.raw_only = bool(z["meta_raw_only"])
         self.target_names = [str(s) for s in z["meta_targets"]]
+        # representation wrappers (newer traces): MultiActionRepresentation patch size, StaticTileRepresentation
+        aw = z["meta_act_window"] if "meta_act_window" in z else np.zeros((0,))
+        self.act_window = tuple(int(v) for v in aw) or None
+        self.static = bool(z["meta_static"]) if "meta_static" in z else False
         self.n_envs = int(z["n_envs"])
         self.envs = []
         for e in range(self.n_envs):
@@ -41,6 +45,7 @@ class Trace:
             # newer traces keep the grid only every few steps: grid_at[t] -> index into d["grids"]
             steps = z[f"grids_step_{e}"] if f"grids_step_{e}" in z else np.arange(len(d["rewards"]))
             d["grid_at"] = {int(t): i for i, t in enumerate(steps)}
+            d["static"] = z[f"static_{e}"] if self.static else None
             self.envs.append(d)
 
     def targets(self, e):
@@ -51,5 +56,8 @@ TRACES = ["binary_narrow", "binary_narrow_chg", "binary_turtle", "binary_wide_ct
           "zelda_turtle", "zelda_narrow", "zelda_wide_raw"]
 TRACES_SEARCH = ["sokoban_narrow", "sokoban_turtle", "sokoban_cellular", "smb_narrow", "smb_narrow_small",
                  "smb_turtle_small", "maze3d_narrow", "maze3d_turtle", "maze3d_wide_raw", "maze3d_cellular"]
+# representation wrappers of envs/reps/wrappers.py: action patches, frozen tiles
+TRACES_WRAPPED = ["binary_patch33", "binary_patch42_chg", "zelda_squeegee", "maze3d_patch", "binary_static_narrow",
+                  "zelda_static_turtle", "binary_static_patch", "sokoban_static_narrow"]
 # traces that stop before the episode ends (n_steps cap in oracle/gen_golden.py)
 TRACES_OPEN_ENDED = ("binary_cellular", "smb_narrow", "maze3d_narrow", "maze3d_cellular")

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.golden_util import TRACES, TRACES_SEARCH, Trace, load_stats
+from tests.golden_util import TRACES, TRACES_SEARCH, TRACES_WRAPPED, Trace, load_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -15,7 +15,9 @@ def _mk(problem, rep, map_shape, n, **kw):
     import control_pcgrl_b200 as P
     cfg = P.make_config(problem, rep, map_shape=map_shape, **{k: v for k, v in kw.items()
                                                               if k in ("obs_window", "weights", "controls",
-                                                                       "max_board_scans", "change_percentage")})
+                                                                       "max_board_scans", "change_percentage",
+                                                                       "act_window", "static_tile_wrapper",
+                                                                       "static_prob", "n_static_walls")})
     extra = {k: v for k, v in kw.items() if k in ("action_kind", "auto_reset", "seed", "env_offset")}
     return P.BatchedPcgrlEnv(cfg, n, **extra)
 
@@ -38,7 +40,7 @@ def test_stats_kernel_matches_reference_fixtures(name, problem):
     assert total > 100
 
 
-@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH)
+@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH + TRACES_WRAPPED)
 def test_trace_replay_matches_reference(name):
     tr = Trace(name)
     n = tr.n_envs
@@ -49,12 +51,15 @@ def test_trace_replay_matches_reference(name):
         kind = "ca_logits"
     env = _mk(tr.problem, tr.rep, tr.map_shape, n, obs_window=tr.obs_window, weights=tr.weights,
               controls=tr.controls, max_board_scans=tr.max_board_scans, change_percentage=tr.change_percentage,
-              action_kind=kind)
+              action_kind=kind, act_window=tr.act_window, static_tile_wrapper=tr.static)
     if tr.target_names:
         env.set_trgs({k: np.array([tr.targets(e)[k] for e in range(n)]) for k in tr.target_names})
     grids0 = np.stack([tr.envs[e]["grid0"] for e in range(n)])
     pos0 = np.stack([tr.envs[e]["pos0"] for e in range(n)])
-    env.reset(grids=grids0, pos=pos0 if tr.rep == "turtle" else None)
+    static0 = np.stack([tr.envs[e]["static"] for e in range(n)]) if tr.static else None
+    env.reset(grids=grids0, pos=pos0 if tr.rep == "turtle" else None, static_tiles=static0)
+    if tr.rep == "narrow":
+        assert env.pos.cpu().numpy()[:, :len(tr.map_shape)].tolist() == pos0.tolist()
     st0 = env.stats.cpu().numpy()
     for e in range(n):
         assert st0[e].tolist() == [int(v) for v in tr.envs[e]["stats0"]], (name, e)
@@ -250,3 +255,83 @@ def test_pipelined_host_step_equals_device_step(problem, rep, shape, controls, m
         assert torch.equal(a.grids, b.grids) and torch.equal(a.stats, b.stats) and torch.equal(a.pos, b.pos)
         assert torch.equal(a.iteration, b.iteration) and torch.equal(a.changes, b.changes)
     a.check_status()
+
+
+def test_static_tiles_random_reset_and_frozen_cells():
+    """StaticTileRepresentation (envs/reps/wrappers.py:234-376) at scale: the random-reset generator
+    (static_prob / n_static_walls) and the invariant that a frozen cell never changes while its attempted
+    edits are still counted as changes."""
+    n = 16384
+    env = _mk("binary", "narrow", (16, 16), n, seed=5, static_tile_wrapper=True, static_prob=0.6, n_static_walls=3)
+    env.reset()
+    sm = env.static_tiles.clone()
+    g0 = env.maps.clone()
+    frac = sm.float().mean(dim=(1, 2))                       # per-episode probability U(0,1) * 0.6, plus walls
+    assert 0.25 < float(frac.mean()) < 0.40 and float(frac.max()) < 0.75
+    assert float(frac.std()) > 0.1                           # the probability is drawn per episode
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    # walls: frozen cells at wall_pos - 1, wall tiles (solid) one cell further along both axes
+    env2 = _mk("binary", "narrow", (16, 16), n, seed=5, static_tile_wrapper=True, static_prob=0.0, n_static_walls=1)
+    env2.reset()
+    sm2, g2 = env2.static_tiles, env2.maps
+    cnt = sm2.sum(dim=(1, 2))
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= 14      # integers(1, 15) cells in one straight segment
+    rows, cols = sm2.any(dim=2).sum(dim=1), sm2.any(dim=1).sum(dim=1)
+    assert bool(((rows == 1) | (cols == 1)).all())
+    shifted = torch.zeros_like(sm2)
+    shifted[:, 1:, 1:] = sm2[:, :-1, :-1]
+    assert bool((g2[shifted.bool()] == 1).all())
+    # rollout: frozen cells keep their tile, changes still count attempts
+    gen = torch.Generator(device=env.device).manual_seed(1)
+    attempts = torch.zeros(n, dtype=torch.int32, device=env.device)
+    for t in range(300):
+        a = torch.randint(0, 2, (n,), generator=gen, device=env.device, dtype=torch.int32)
+        pos = env.pos.clone()
+        cur = env.maps[torch.arange(n, device=env.device), pos[:, 0].long(), pos[:, 1].long()]
+        attempts += (cur.int() != a).int()
+        prev_stats = env.stats.clone()
+        reward, _ = env.step(a)
+        froz = sm[torch.arange(n, device=env.device), pos[:, 0].long(), pos[:, 1].long()].bool()
+        undone = froz & (cur.int() != a)
+        assert torch.equal(env.stats[undone], prev_stats[undone]) and bool((reward[undone] == 0).all())
+    assert torch.equal(env.changes, attempts)
+    assert torch.equal(env.maps[sm.bool()], g0[sm.bool()])
+    assert not torch.equal(env.maps, g0)
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    obs = env.observe(dtype=torch.uint8)
+    assert obs.shape == (n, 32, 32, 4)
+    env.check_status()
+
+
+@pytest.mark.parametrize("problem,shape,aw", [("binary", (16, 16), (2, 2)), ("binary", (16, 16), (16, 1)),
+                                              ("binary", (16, 16), (16, 16)), ("zelda", (7, 11), (3, 4))])
+def test_action_patch_rollout_vs_oracle(problem, shape, aw):
+    """MultiActionRepresentation (cfg.act_window) on random rollouts against the oracle, incl. the squeegee and
+    whole-map patches of configs/experiment/{action_patch,squeegee}.yaml."""
+    from oracle import pcgrl_oracle as O
+    n, steps = 24, 40
+    rng = np.random.default_rng(7)
+    nt = len(O.TILES[problem])
+    grids = rng.integers(0, nt, size=(n, *shape)).astype(np.int8)
+    env = _mk(problem, "narrow", shape, n, act_window=aw)
+    env.reset(grids=grids)
+    oracles = []
+    for e in range(n):
+        o = O.OracleEnv(problem, "narrow", shape, weights=dict(env.metric_weights), act_window=aw)
+        o.reset(grids[e])
+        oracles.append(o)
+    for t in range(steps):
+        a = rng.integers(0, nt, size=(n, int(np.prod(aw)))).astype(np.int32)
+        if t % 3 == 2:
+            for e, o in enumerate(oracles):   # no-op patches
+                tl = [o.pos[i] - (aw[i] - 1) // 2 for i in range(2)]
+                a[e] = o.grid[tl[0]:tl[0] + aw[0], tl[1]:tl[1] + aw[1]].reshape(-1)
+        reward, done = env.step(torch.from_numpy(a).to(env.device))
+        reward, stats, maps, pos = reward.cpu().numpy(), env.stats.cpu().numpy(), env.maps.cpu().numpy(), env.pos.cpu().numpy()
+        for e, o in enumerate(oracles):
+            r, d, _ = o.step(a[e])
+            assert stats[e].tolist() == O.stats_vector(problem, o.stats), (t, e)
+            assert np.array_equal(maps[e], o.grid) and pos[e, :2].tolist() == o.pos, (t, e)
+            assert reward[e] == pytest.approx(r, rel=1e-6, abs=1e-7)
+    assert env.changes.cpu().numpy().tolist() == [o.changes for o in oracles]
+    env.check_status()

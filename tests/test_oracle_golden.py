@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import pcgrl_oracle as O
-from tests.golden_util import TRACES, TRACES_OPEN_ENDED, TRACES_SEARCH, Trace, load_stats
+from tests.golden_util import TRACES, TRACES_OPEN_ENDED, TRACES_SEARCH, TRACES_WRAPPED, Trace, load_stats
 
 
 @pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
@@ -37,8 +37,9 @@ def test_known_answers():
 def replay_oracle(tr: Trace, e: int):
     d = tr.envs[e]
     env = O.OracleEnv(tr.problem, tr.rep, tr.map_shape, weights=tr.weights, controls=tr.controls,
-                      max_board_scans=tr.max_board_scans, change_percentage=tr.change_percentage)
-    st0 = env.reset(d["grid0"], pos=d["pos0"], targets=tr.targets(e))
+                      max_board_scans=tr.max_board_scans, change_percentage=tr.change_percentage,
+                      act_window=tr.act_window)
+    st0 = env.reset(d["grid0"], pos=d["pos0"], targets=tr.targets(e), static=d["static"])
     assert O.stats_vector(tr.problem, st0) == [int(v) for v in d["stats0"]]
     n_tiles = len(O.TILES[tr.problem])
     h, w = tr.obs_window[:2]
@@ -46,7 +47,7 @@ def replay_oracle(tr: Trace, e: int):
         a = d["actions"][t]
         if tr.rep == "wide" and not tr.raw_only:
             a = O.actionmap_unravel(a, h, w, n_tiles)
-        elif tr.rep in ("narrow", "turtle"):
+        elif tr.rep in ("narrow", "turtle") and tr.act_window is None:
             a = int(a)
         r, done, _ = env.step(a)
         assert done == bool(d["dones"][t]), (tr.name, e, t)
@@ -63,6 +64,9 @@ def replay_oracle(tr: Trace, e: int):
                 got = O.cropped_onehot(env.grid, env.pos, tr.obs_window, n_tiles)
             else:
                 got = O.full_onehot(env.grid, n_tiles)
+            if tr.static:
+                sb = O.static_builds_crop(d["static"], env.pos, tr.obs_window)
+                got = np.concatenate([got, sb[..., None]], axis=-1)
             if tr.controls:
                 ch = O.target_channels(got.shape[:-1], tr.controls, env.targets, env.stats, env.cond_bounds)
                 got = np.concatenate([ch, got], axis=-1)
@@ -71,7 +75,7 @@ def replay_oracle(tr: Trace, e: int):
     assert bool(d["dones"][-1]) or tr.name in TRACES_OPEN_ENDED
 
 
-@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH)
+@pytest.mark.parametrize("name", TRACES + TRACES_SEARCH + TRACES_WRAPPED)
 def test_trace_matches_reference(name):
     tr = Trace(name)
     for e in range(tr.n_envs):
