@@ -11,6 +11,12 @@
 #ifndef PCGRL_OPT_WORKERS
 #define PCGRL_OPT_WORKERS 0    // 1: only ceil(M/rounds) threads take part in the stats phase
 #endif
+#ifndef PCGRL_OPT_IMAD_SUB
+#define PCGRL_OPT_IMAD_SUB 1   // 1: remove a subset from a board with x - n (IMAD, FMA pipe) instead of x ^ n (LOP3, ALU pipe)
+#endif
+#ifndef PCGRL_OPT_BORROW
+#define PCGRL_OPT_BORROW 1     // 1: lowest-cell extraction through x - 1 (minus_one) fused into its consumers
+#endif
 #if PCGRL_OPT_SHR_IMAD
 #define PCGRL_SHR1(x) __umulhi((x), 0x80000000u)
 #else
@@ -198,6 +204,52 @@ struct Board {
         }
 #pragma unroll
         for (int i = 0; i < NW; ++i) out[i] = x[i] & neg[i];
+    }
+    // t = x - 1 as one multi-word integer (borrow rippling up through sub.cc / subc.cc); returns true iff x != 0.
+    // With it the lowest set cell of x is x & ~t and x without that cell is x & t -- one LOP3 per word each, which
+    // ptxas fuses with the consumer (fars |= x & ~t), instead of the negate / and / xor sequence of lowest().
+    __device__ static __forceinline__ bool minus_one(const uint32_t (&x)[NW], uint32_t (&t)[NW]) {
+        uint32_t b;
+        if constexpr (NW == 1) {
+            t[0] = x[0] - 1u;
+            return x[0] != 0u;
+        } else if constexpr (NW == 2) {
+            asm("sub.cc.u32 %0, %3, 1;\n\tsubc.cc.u32 %1, %4, 0;\n\tsubc.u32 %2, 0, 0;"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(b) : "r"(x[0]), "r"(x[1]));
+            return b == 0u;
+        } else if constexpr (NW == 4) {
+            asm("sub.cc.u32 %0, %5, 1;\n\tsubc.cc.u32 %1, %6, 0;\n\tsubc.cc.u32 %2, %7, 0;\n\tsubc.cc.u32 %3, %8, 0;\n\t"
+                "subc.u32 %4, 0, 0;"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(b)
+                : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]));
+            return b == 0u;
+        } else if constexpr (NW == 8) {
+            asm("sub.cc.u32 %0, %9, 1;\n\tsubc.cc.u32 %1, %10, 0;\n\tsubc.cc.u32 %2, %11, 0;\n\t"
+                "subc.cc.u32 %3, %12, 0;\n\tsubc.cc.u32 %4, %13, 0;\n\tsubc.cc.u32 %5, %14, 0;\n\t"
+                "subc.cc.u32 %6, %15, 0;\n\tsubc.cc.u32 %7, %16, 0;\n\tsubc.u32 %8, 0, 0;"
+                : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(b)
+                : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+            return b == 0u;
+        } else {
+            uint32_t borrow = 1, nz = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                t[i] = x[i] - borrow;
+                borrow = (x[i] < borrow) ? 1u : 0u;
+                nz |= x[i];
+            }
+            return nz != 0u;
+        }
+    }
+    // x \ n for n a subset of x, as x - n: an IMAD on the FMA pipe instead of a LOP3 on the (saturated) ALU pipe
+    __device__ static __forceinline__ uint32_t minus_subset(uint32_t x, uint32_t n) {
+#if PCGRL_OPT_IMAD_SUB
+        uint32_t r;
+        asm("mad.lo.u32 %0, %1, 0xFFFFFFFF, %2;" : "=r"(r) : "r"(n), "r"(x));
+        return r;
+#else
+        return x ^ n;
+#endif
     }
     __device__ static __forceinline__ uint32_t any(const uint32_t (&x)[NW]) {
         uint32_t r = 0;

@@ -24,6 +24,12 @@ namespace pcgrl {
 #ifndef PCGRL_THREADS
 #define PCGRL_THREADS 128
 #endif
+#ifndef PCGRL_WARP_BATCH
+#define PCGRL_WARP_BATCH 0  // 1: warps claim batches of 32 changed envs; 0: per-thread claims
+#endif
+#ifndef PCGRL_BATCH_K
+#define PCGRL_BATCH_K 0     // lanes of a warp that must be waiting for a transition before the warp takes it
+#endif
 #ifndef PCGRL_TILE8
 #define PCGRL_TILE8 256   // envs per CTA when a board is <= 8 words (binary 16x16); A/B: 2 envs per thread is best
 #endif
@@ -92,19 +98,36 @@ struct BinaryMachine {
         phase = 0;
         level = 0;
     }
-    // one board expansion (or one transition); returns true when out[] holds the K stats
-    __device__ __forceinline__ bool advance(int* out) {
+    // one board expansion; returns false (and changes nothing) when the frontier has died
+    __device__ __forceinline__ bool expand() {
         uint32_t n[NW];
-        if (B::expand_and(front, avail, n)) {
+        if (!B::expand_and(front, avail, n)) return false;
 #pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                avail[i] ^= n[i];
-                front[i] = n[i];
-            }
-            ++level;
-            return false;
+        for (int i = 0; i < NW; ++i) {
+            avail[i] = B::minus_subset(avail[i], n[i]);
+            front[i] = n[i];
         }
+        ++level;
+        return true;
+    }
+    // the frontier died: next component / next phase; returns true when out[] holds the K stats
+    __device__ __forceinline__ bool transition(int* out) {
         if (phase == 0) {
+#if PCGRL_OPT_BORROW
+            uint32_t t[NW];
+            B::minus_one(front, t);           // far tile of the component just swept (nothing on entry)
+#pragma unroll
+            for (int i = 0; i < NW; ++i) fars[i] |= front[i] & ~t[i];
+            if (B::minus_one(avail, t)) {     // first tile of the next component
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    front[i] = avail[i] & ~t[i];
+                    avail[i] &= t[i];
+                }
+                ++ncomp;
+                return false;
+            }
+#else
             uint32_t lo[NW];
             B::lowest(front, lo);             // far tile of the component just swept (nothing on entry)
 #pragma unroll
@@ -119,6 +142,7 @@ struct BinaryMachine {
                 ++ncomp;
                 return false;
             }
+#endif
             phase = 1;  // joint second sweep from every far tile
             uint32_t any = 0;
 #pragma unroll
@@ -182,36 +206,36 @@ struct ZeldaMachine {
         dkey = -1;
         ddoor = -1;
     }
-    __device__ __forceinline__ bool advance(int* out) {
+    __device__ __forceinline__ bool expand() {
         uint32_t n[NW];
-        if (B::expand_and(front, avail, n)) {
+        if (!B::expand_and(front, avail, n)) return false;
 #pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                avail[i] ^= n[i];
-                front[i] = n[i];
-            }
-            ++level;
-            if (phase == 1) {
-                uint32_t t[NW];
-                load(4, t);
-                if (near == 0 && B::any_and(n, t)) near = level;
-                load(2, t);
-                if (B::any_and(n, t)) dkey = level;
-            } else if (phase == 2) {
-                uint32_t t[NW];
-                load(3, t);
-                if (B::any_and(n, t)) ddoor = level;
-            }
-            return false;
+        for (int i = 0; i < NW; ++i) {
+            avail[i] ^= n[i];
+            front[i] = n[i];
         }
+        ++level;
+        if (phase == 1) {
+            uint32_t t[NW];
+            load(4, t);
+            if (near == 0 && B::any_and(n, t)) near = level;
+            load(2, t);
+            if (B::any_and(n, t)) dkey = level;
+        } else if (phase == 2) {
+            uint32_t t[NW];
+            load(3, t);
+            if (B::any_and(n, t)) ddoor = level;
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool transition(int* out) {
         if (phase == 0) {  // region flood fill, one component at a time
-            uint32_t lo[NW];
-            B::lowest(avail, lo);
-            if (B::any(lo)) {
+            uint32_t t[NW];
+            if (B::minus_one(avail, t)) {
 #pragma unroll
                 for (int i = 0; i < NW; ++i) {
-                    front[i] = lo[i];
-                    avail[i] ^= lo[i];
+                    front[i] = avail[i] & ~t[i];
+                    avail[i] &= t[i];
                 }
                 ++regions;
                 return false;
@@ -374,14 +398,64 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     // lanes run out of work together instead of a few lanes dragging a mostly idle warp through a last round.
     {
         Machine m;
-        const int rounds = (M + THREADS - 1) / THREADS;
-        const int workers = PCGRL_OPT_WORKERS ? (rounds ? (M + rounds - 1) / rounds : 0) : THREADS;
-        int item = tid < workers ? atomicAdd(&s_next, 1) : M;
+#if PCGRL_WARP_BATCH
+        // Warp-synchronous batches: a warp claims 32 consecutive changed envs at a time and its lanes start their
+        // searches together, so at most ONE warp of the CTA runs a partly filled batch (with per-thread claims
+        // the few envs beyond THREADS were picked up by lanes scattered over every warp, each of which then ran
+        // a whole extra search at 1/32..7/32 lane occupancy).
+        for (;;) {
+            int b0 = 0;
+            if ((tid & 31) == 0) b0 = atomicAdd(&s_next, 32);
+            b0 = __shfl_sync(0xffffffffu, b0, 0);
+            if (b0 >= M) break;
+            const int item = b0 + (tid & 31);
+            if (item < M) {
+                m.init(s_bb + item * BBW);
+                int out[K];
+                for (;;) {
+                    if (m.expand()) continue;
+                    if (m.transition(out)) break;
+                }
+#pragma unroll
+                for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+            }
+            __syncwarp();
+        }
+#else
+        int item = atomicAdd(&s_next, 1);
         bool active = item < M;
         if (active) m.init(s_bb + item * BBW);
+#if PCGRL_BATCH_K > 0
+        // Expansions and transitions are different instruction streams; with 32 independent grids per warp some
+        // lane needs a transition on almost every trip, so an unbatched loop pays for both streams every trip
+        // with the transition stream running at 1/8 lane occupancy.  Lanes whose frontier died therefore WAIT
+        // (masked off during the expansions) until PCGRL_BATCH_K lanes of the warp are waiting, or nobody can
+        // expand; then all of them take their transition together.
+        bool pend = active;   // a fresh machine has an empty frontier: its first act is a transition
+        while (__any_sync(0xffffffffu, active)) {
+            if (active && !pend) pend = !m.expand();
+            const unsigned pb = __ballot_sync(0xffffffffu, pend);
+            const unsigned cb = __ballot_sync(0xffffffffu, active && !pend);
+            if (__popc(pb) >= PCGRL_BATCH_K || cb == 0) {
+                if (pend) {
+                    int out[K];
+                    while (m.transition(out)) {
+#pragma unroll
+                        for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                        item = atomicAdd(&s_next, 1);
+                        active = item < M;
+                        if (!active) break;
+                        m.init(s_bb + item * BBW);
+                    }
+                    pend = false;
+                }
+            }
+        }
+#else
         while (active) {
             int out[K];
-            if (m.advance(out)) {
+            if (m.expand()) continue;
+            if (m.transition(out)) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
                 item = atomicAdd(&s_next, 1);
@@ -389,6 +463,8 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
                 if (active) m.init(s_bb + item * BBW);
             }
         }
+#endif
+#endif
     }
     __syncthreads();
 
