@@ -24,6 +24,12 @@ namespace pcgrl {
 #ifndef PCGRL_THREADS
 #define PCGRL_THREADS 128
 #endif
+#ifndef PCGRL_STATIC_ITEMS
+#define PCGRL_STATIC_ITEMS 0
+#endif
+#ifndef PCGRL_EXPAND_R
+#define PCGRL_EXPAND_R 3
+#endif
 #ifndef PCGRL_WARP_BATCH
 #define PCGRL_WARP_BATCH 0  // 1: warps claim batches of 32 changed envs; 0: per-thread claims
 #endif
@@ -35,7 +41,7 @@ namespace pcgrl {
 #endif
 constexpr int THREADS = PCGRL_THREADS;
 // envs per CTA, bounded so the shared-memory bit-boards stay under the 48 KB static limit
-__host__ __device__ constexpr int tile_for(int bbw) { return bbw <= 8 ? PCGRL_TILE8 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
+__host__ __device__ constexpr int tile_for(int bbw) { return bbw == 8 ? PCGRL_TILE8 : bbw < 8 ? 256 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
 
 // ------------------------------------------------------------------------------------------------
 // Problem policies: planes (tile-code sets packed to bit-boards) + the per-thread stats state machine.
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     constexpr int K = Prob::K;
     constexpr int BBW = P * NW;  // board words per env
     constexpr int TILE = tile_for(BBW);
+    static_assert(TILE % 32 == 0 && THREADS % 32 == 0, "phase_a's warp ballots need every lane of a warp in the same trip");
 
     __shared__ uint32_t s_bb[TILE * BBW];
     __shared__ int32_t s_stats[TILE * K];
@@ -320,6 +327,8 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
     __shared__ uint8_t s_flag[TILE];   // cellular: map changed
     __shared__ int s_count, s_next;
 
+    // One CTA per tile.  (A persistent grid with a device-side tile counter, as in step_search.cuh, was A/B-tested
+    // here and ran 2 % slower: the extra barriers cost more than the partly filled last wave.)
     const int tid = threadIdx.x;
     const int64_t base = (int64_t)blockIdx.x * TILE;
     const int64_t n_total = p.n_envs;
@@ -422,7 +431,16 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
             __syncwarp();
         }
 #else
+#if PCGRL_STATIC_ITEMS
+        // static round-robin claims: the changed envs beyond THREADS all land in the lowest warp(s), so only those
+        // run a second, partly filled round (dynamic claims scatter them over lanes of every warp, and each such
+        // warp then runs a whole extra search at 1/32 lane occupancy)
+#define PCGRL_NEXT_ITEM(cur) ((cur) + THREADS)
+        int item = tid;
+#else
+#define PCGRL_NEXT_ITEM(cur) atomicAdd(&s_next, 1)
         int item = atomicAdd(&s_next, 1);
+#endif
         bool active = item < M;
         if (active) m.init(s_bb + item * BBW);
 #if PCGRL_BATCH_K > 0
@@ -454,11 +472,18 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
 #else
         while (active) {
             int out[K];
-            if (m.expand()) continue;
+            // PCGRL_EXPAND_R expansions per trip: the transition stream (a few lanes) is then paid once per R
+            // expansions of the warp instead of once per expansion; a lane whose frontier dies early idles for
+            // the rest of the trip
+            bool alive = m.expand();
+#pragma unroll
+            for (int r = 1; r < PCGRL_EXPAND_R; ++r)
+                if (alive) alive = m.expand();
+            if (alive) continue;
             if (m.transition(out)) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
-                item = atomicAdd(&s_next, 1);
+                item = PCGRL_NEXT_ITEM(item);
                 active = item < M;
                 if (active) m.init(s_bb + item * BBW);
             }

@@ -17,7 +17,7 @@ else
   for lib in gpurun_variants/lib*.so; do
     name=$(basename $lib .so)
     for rep in 1 2; do
-      PCGRL_B200_LIB=$PWD/$lib python bench.py --no-cpu-baseline --no-e2e "$@" 2>>gpurun_out/ab.err | python -c "
+      PCGRL_B200_LIB=$PWD/$lib timeout 90 python bench.py --no-cpu-baseline --no-e2e "$@" 2>>gpurun_out/ab.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('$name', 'value %.4g'%d['value'], 'ms/step %.4f'%d['ms_per_step'], 'kernel_ms %.4f'%d['roofline']['kernel_ms_per_launch'])"
     done

@@ -32,11 +32,12 @@ for r in rows:
         continue
     if hdr and r[0].isdigit():
         key = (cur_file, int(r[0]), r[1].strip()[:100])
-        a = agg.setdefault(key, [0, 0])
+        a = agg.setdefault(key, [0, 0, 0])
         a[0] += num(r[hdr.index("Instructions Executed")])
         a[1] += num(r[hdr.index("# Samples")])
+        a[2] += num(r[hdr.index("Thread Instructions Executed")])
 tot = sum(v[0] for v in agg.values()) or 1
 ts = sum(v[1] for v in agg.values()) or 1
 print("total warp-instructions", tot, "samples", ts)
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
-    print(f"{v[0] / tot * 100:5.1f}% inst {v[1] / ts * 100:5.1f}% samp  {k[0]}:{k[1]}  {k[2]}")
+    print(f"{v[0] / tot * 100:5.1f}% inst {v[1] / ts * 100:5.1f}% samp {v[2] / max(v[0], 1):5.1f} lanes  {k[0]}:{k[1]}  {k[2]}")
