@@ -8,11 +8,12 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PCGRL_ABI_VERSION = 3
+PCGRL_ABI_VERSION = 4
 MAX_STATS = 16
 MAX_TILES = 16
 
-PROB_IDS = {"binary": 0, "zelda": 1, "sokoban": 2, "smb": 3, "minecraft_3D_maze": 4}
+PROB_IDS = {"binary": 0, "zelda": 1, "sokoban": 2, "smb": 3, "minecraft_3D_maze": 4, "binary_holey": 5}
+HOLES_GIVEN, HOLES_FIXED, HOLES_RANDOM = 0, 1, 2
 REP_IDS = {"narrow": 0, "turtle": 1, "wide": 2, "cellular": 3}
 ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS, ACT_PATCH = range(6)
 REWARD_CONTROL, REWARD_RANGE = 0, 1
@@ -31,7 +32,7 @@ class Config(C.Structure):
         ("targets_per_env", C.c_int32), ("init_random_probs", C.c_int32), ("reward_mode", C.c_int32),
         ("init_probs", C.c_float * MAX_TILES), ("weights", C.c_double * MAX_STATS),
         ("act_window", C.c_int32 * 3), ("static_prob", C.c_float), ("n_static_walls", C.c_int32),
-        ("wall_tile", C.c_int32), ("static_eval_mode", C.c_int32),
+        ("wall_tile", C.c_int32), ("static_eval_mode", C.c_int32), ("hole_mode", C.c_int32),
     ]
 
 
@@ -40,7 +41,7 @@ class State(C.Structure):
         ("n_envs", C.c_int64), ("env_offset", C.c_int64), ("grids", C.c_void_p), ("pos", C.c_void_p),
         ("n_step", C.c_void_p), ("iteration", C.c_void_p), ("changes", C.c_void_p), ("stats", C.c_void_p),
         ("targets", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("changed", C.c_void_p),
-        ("status", C.c_void_p), ("scratch", C.c_void_p), ("static_mask", C.c_void_p),
+        ("status", C.c_void_p), ("scratch", C.c_void_p), ("static_mask", C.c_void_p), ("holes", C.c_void_p),
     ]
 
 
@@ -63,6 +64,8 @@ SYMBOLS = {
     "pcgrl_reset": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_uint64, C.c_uint64, C.c_void_p]),
     "pcgrl_stats": (C.c_int32, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "pcgrl_stats_holey": (C.c_int32, [C.POINTER(Config), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p,
+                                      C.c_void_p]),
     "pcgrl_observe": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.POINTER(ObsArgs), C.c_void_p]),
     "pcgrl_step_host": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

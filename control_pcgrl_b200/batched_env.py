@@ -21,7 +21,7 @@ import torch
 
 from . import _lib
 from .config import normalise
-from .problems import REPRESENTATION_ALIASES, get_spec
+from .problems import HOLEY_PROBLEMS, REPRESENTATION_ALIASES, get_spec
 
 
 def _ptr(t):
@@ -114,6 +114,10 @@ class BatchedPcgrlEnv:
             cc.static_prob = self.static_prob
             cc.n_static_walls = self.n_static_walls
             cc.wall_tile = 1          # Problem._wall_tile = tiles[1] (envs/probs/problem.py:41)
+        # holey problems (envs/pcgrl_holey_env.py, envs/probs/holey_prob.py): entrance / exit per env
+        self.holey = self.problem in HOLEY_PROBLEMS
+        self.fixed_holes = bool(c.fixed_holes)
+        cc.hole_mode = (_lib.HOLES_FIXED if self.fixed_holes else _lib.HOLES_RANDOM) if self.holey else _lib.HOLES_GIVEN
         cc.init_random_probs = 1 if random_init_probs else 0
         # "control": ControlWrapper's loss delta (what step() pays at this commit); "range": the legacy
         # Problem.get_reward sum of get_range_reward terms (helper.py:550-560), bands in `targets`
@@ -148,6 +152,8 @@ class BatchedPcgrlEnv:
         # StaticTileRepresentation.static_tiles over the map cells (border implicit), envs/reps/wrappers.py:277
         self.static_mask = torch.zeros((N, self.row_stride), dtype=torch.uint8, device=dev) \
             if self.static_tile_wrapper else None
+        # (entrance_y, entrance_x, exit_y, exit_x) in bordered coordinates (holey_prob.py:41-42)
+        self.holes = torch.zeros((N, 4), dtype=torch.int32, device=dev) if self.holey else None
         nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
         # zero-initialised once: the solver kernels keep generation counters for their hash tables in it
         self.scratch = torch.zeros(int(nscratch), dtype=torch.uint8, device=dev) if nscratch > 0 else None
@@ -165,6 +171,7 @@ class BatchedPcgrlEnv:
         st.targets, st.reward, st.done = _ptr(self.targets), _ptr(self.reward), _ptr(self.done)
         st.changed, st.status, st.scratch = _ptr(self.changed), _ptr(self.status), _ptr(self.scratch)
         st.static_mask = _ptr(self.static_mask)
+        st.holes = _ptr(self.holes)
         self._st = st
 
     # ------------------------------------------------------------------ targets
@@ -258,12 +265,27 @@ class BatchedPcgrlEnv:
             return None
         return self.static_mask[:, :self.cells].view(self.n_envs, *self.map_shape)
 
-    def reset(self, grids=None, pos=None, mask=None, static_tiles=None):
+    def reset(self, grids=None, pos=None, mask=None, static_tiles=None, holes=None):
         """Start episodes (all envs, or those where mask != 0).  grids: [N,*map_shape] initial maps
         (PcgrlCtrlEnv.set_map semantics) or None for random maps; pos: [N,ndim] start positions;
         static_tiles: [N,*map_shape] frozen-tile masks to use (with static_tile_wrapper; random resets draw
-        their own from static_prob / n_static_walls)."""
+        their own from static_prob / n_static_walls); holes: [N,4] (entrance_y, entrance_x, exit_y, exit_x) in
+        bordered coordinates for a holey problem (the reference's _hole_queue, holey_prob.py:43-44), else the
+        kernel draws them (or uses the fixed pair with cfg.fixed_holes)."""
         src = self._pack_grids(grids) if grids is not None else None
+        cc = self._cc
+        if holes is not None:
+            if not self.holey:
+                raise ValueError("holes are only meaningful for a holey problem")
+            hv = torch.as_tensor(np.asarray(holes) if not torch.is_tensor(holes) else holes)
+            hv = hv.to(self.device, torch.int32).reshape(self.n_envs, 4)
+            if mask is None:
+                self.holes.copy_(hv)
+            else:
+                sel = mask.to(self.device).bool()
+                self.holes[sel] = hv[sel]
+            cc = _lib.Config.from_buffer_copy(self._cc)
+            cc.hole_mode = _lib.HOLES_GIVEN
         if static_tiles is not None:
             if self.static_mask is None:
                 raise ValueError("static_tiles needs cfg.static_tile_wrapper")
@@ -283,7 +305,7 @@ class BatchedPcgrlEnv:
         if mask is not None:
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         self._epoch += 1
-        _lib.check(self.lib.pcgrl_reset(self._cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
+        _lib.check(self.lib.pcgrl_reset(cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
                                         self._stream()), "pcgrl_reset")
         self._synced_steps = 0 if mask is None else None
         return self.stats
@@ -370,8 +392,9 @@ class BatchedPcgrlEnv:
         return r.numpy(), d.numpy(), (s.numpy() if s is not None else None)
 
     # ------------------------------------------------------------------ stats / observations
-    def compute_stats(self, grids) -> torch.Tensor:
-        """Problem.get_stats for arbitrary grids [n, *map_shape] (evolution's terminal call)."""
+    def compute_stats(self, grids, holes=None) -> torch.Tensor:
+        """Problem.get_stats for arbitrary grids [n, *map_shape] (evolution's terminal call).  A holey problem
+        also needs holes [n, 4] (its get_stats reads entrance_coords / exit_coords)."""
         g = torch.as_tensor(np.asarray(grids) if not torch.is_tensor(grids) else grids)
         n = g.shape[0]
         g = g.to(device=self.device, dtype=torch.int8).reshape(n, self.cells)
@@ -381,6 +404,14 @@ class BatchedPcgrlEnv:
             g = buf
         g = g.contiguous()
         out = torch.empty((n, self.K), dtype=torch.int32, device=self.device)
+        if self.holey:
+            if holes is None:
+                raise ValueError("a holey problem needs holes [n, 4] for compute_stats")
+            hv = torch.as_tensor(np.asarray(holes) if not torch.is_tensor(holes) else holes)
+            hv = hv.to(self.device, torch.int32).reshape(n, 4).contiguous()
+            _lib.check(self.lib.pcgrl_stats_holey(self._cc, g.data_ptr(), hv.data_ptr(), out.data_ptr(), n,
+                                                  _ptr(self.scratch), self._stream()), "pcgrl_stats_holey")
+            return out
         _lib.check(self.lib.pcgrl_stats(self._cc, g.data_ptr(), out.data_ptr(), n, _ptr(self.scratch),
                                         self._stream()), "pcgrl_stats")
         return out
@@ -395,6 +426,10 @@ class BatchedPcgrlEnv:
     def observe(self, out: torch.Tensor | None = None, dtype=torch.float32):
         """The wrapped observation of every env: [N, *obs_dims, channels] (channels last), exactly what
         CroppedImagePCGRLWrapper / ActionMapImagePCGRLWrapper + ControlWrapper return per env."""
+        if self.holey:
+            # HoleyRepresentation.get_observation (envs/reps/wrappers.py:153-160) shows the bordered map with
+            # pos + 1; not on the GPU yet -- fail loudly rather than return the un-bordered crop
+            raise NotImplementedError("observations of holey problems are not implemented; use .maps / .holes")
         shape = (self.n_envs, *self.obs_shape())
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
@@ -433,7 +468,7 @@ class BatchedPcgrlEnv:
     def state_dict(self):
         """Everything needed to reconstruct the env state (checkpoint row)."""
         return {k: getattr(self, k).clone() for k in
-                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask")
+                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes")
                 if getattr(self, k) is not None}
 
     def load_state_dict(self, sd):

@@ -45,6 +45,7 @@ class Config:
     multiagent: MultiagentConfig = field(default_factory=MultiagentConfig)
     n_aux_tiles: int = 0
     train_reward_model: bool = False
+    fixed_holes: bool = False               # holey problems (binary_holey_prob.py:47-49)
     env_name: str = ""
 
     def __post_init__(self):
@@ -66,6 +67,8 @@ TASK_DEFAULTS = {
     "smb": dict(map_shape=(116, 16), obs_window=(32, 32),
                 weights={"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2,
                          "jumps-dist": 2, "dist-win": 5, "sol-length": 1}),
+    "binary_holey": dict(map_shape=(16, 16), obs_window=(32, 32),
+                         weights={"regions": 1, "path-length": 0, "connected-path-length": 1}),
     "minecraft_3D_maze": dict(map_shape=(15, 15, 15), obs_window=(30, 30, 30),
                               weights={"path-length": 100, "n_jump": 100, "regions": 0}),
 }
@@ -110,4 +113,6 @@ def normalise(cfg) -> SimpleNamespace:
                                _get(cfg, "act_window", None)),
                            static_tile_wrapper=bool(_get(cfg, "static_tile_wrapper", False)),
                            static_prob=_get(cfg, "static_prob", None),
-                           n_static_walls=_get(cfg, "n_static_walls", None))
+                           n_static_walls=_get(cfg, "n_static_walls", None),
+                           # HoleyProblem.adjust_param (binary_holey_prob.py:47-49)
+                           fixed_holes=bool(_get(cfg, "fixed_holes", _get(task, "fixed_holes", False))))

@@ -43,8 +43,10 @@ static int check(const pcgrl_config* c) {
         return fail(PCGRL_E_ARG, "unknown representation");
     const int cells = cells_of(c);
     if (c->row_stride < cells || c->row_stride % 16) return fail(PCGRL_E_ARG, "row_stride must be >= cells and a multiple of 16");
-    static const int k_of[] = {2, 7, 7, 9, 3};
-    if (c->problem < 0 || c->problem > PCGRL_PROB_MINECRAFT_3D_MAZE) return fail(PCGRL_E_ARG, "unknown problem");
+    static const int k_of[] = {2, 7, 7, 9, 3, 3};
+    if (c->problem < 0 || c->problem > PCGRL_PROB_BINARY_HOLEY) return fail(PCGRL_E_ARG, "unknown problem");
+    if (c->hole_mode < PCGRL_HOLES_GIVEN || c->hole_mode > PCGRL_HOLES_RANDOM) return fail(PCGRL_E_ARG, "unknown hole_mode");
+    if (c->problem == PCGRL_PROB_BINARY_HOLEY && c->ndim != 2) return fail(PCGRL_E_ARG, "binary_holey is a 2D problem");
     if (c->n_stats != k_of[c->problem]) return fail(PCGRL_E_ARG, "n_stats does not match the problem");
     const int r = c->representation, a = c->action_kind;
     const bool ok = ((r == PCGRL_REP_NARROW || r == PCGRL_REP_TURTLE) && a == PCGRL_ACT_INT32) ||
@@ -98,6 +100,7 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
     p.n_static_walls = c->n_static_walls;
     p.wall_tile = c->wall_tile;
     p.static_eval_mode = c->static_eval_mode;
+    p.hole_mode = c->hole_mode;
     double tot = 0;
     for (int t = 0; t < c->n_tiles; ++t) tot += c->init_probs[t] > 0 ? c->init_probs[t] : 0;
     double run = 0;
@@ -122,8 +125,11 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
         p.status = st->status;
         p.scratch = st->scratch;
         p.static_mask = st->static_mask;
+        p.holes = st->holes;
     }
 }
+
+static bool is_holey(const pcgrl_config* c) { return c->problem == PCGRL_PROB_BINARY_HOLEY; }
 
 static int check_state(const pcgrl_state* st) {
     if (!st) return fail(PCGRL_E_ARG, "state is NULL");
@@ -163,7 +169,8 @@ struct HostPipe {
 static thread_local HostPipe g_pipe[16];
 
 static int host_chunks(const pcgrl_config* cfg, int64_t n) {
-    if (cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA) return 1;
+    if (cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA && cfg->problem != PCGRL_PROB_BINARY_HOLEY)
+        return 1;
     if (const char* e = getenv("PCGRL_HOST_CHUNKS")) {
         const int v = atoi(e);
         if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(1, n / 256));
@@ -213,6 +220,7 @@ int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* a
     if (r) return r;
     if ((r = check_state(st))) return r;
     if (!actions) return fail(PCGRL_E_ARG, "actions is NULL");
+    if (is_holey(cfg) && !st->holes) return fail(PCGRL_E_ARG, "a holey problem needs pcgrl_state.holes");
     KParams p;
     fill(p, cfg, st);
     p.mode = MODE_STEP;
@@ -225,8 +233,10 @@ int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_
     int r = check(cfg);
     if (r) return r;
     if ((r = check_state(st))) return r;
+    if (is_holey(cfg) && !st->holes) return fail(PCGRL_E_ARG, "a holey problem needs pcgrl_state.holes");
     KParams p;
     fill(p, cfg, st);
+    if (!is_holey(cfg)) p.holes = nullptr;
     p.mode = MODE_RESET;
     p.mask = mask;
     p.src_grids = src_grids;
@@ -241,6 +251,7 @@ int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats
     int r = check(cfg);
     if (r) return r;
     if (!grids || !stats || n < 0) return fail(PCGRL_E_ARG, "bad grids/stats/n");
+    if (is_holey(cfg)) return fail(PCGRL_E_ARG, "a holey problem needs pcgrl_stats_holey (entrance / exit per grid)");
     KParams p;
     fill(p, cfg, nullptr);
     p.mode = MODE_STATS;
@@ -248,6 +259,23 @@ int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats
     p.stats_grids = grids;
     p.stats_out = stats;
     p.scratch = scratch;
+    return run(p, cfg->problem, stream);
+}
+
+int32_t pcgrl_stats_holey(const pcgrl_config* cfg, const int8_t* grids, const int32_t* holes, int32_t* stats,
+                          int64_t n, void* scratch, void* stream) {
+    int r = check(cfg);
+    if (r) return r;
+    if (!grids || !stats || !holes || n < 0) return fail(PCGRL_E_ARG, "bad grids/holes/stats/n");
+    if (!is_holey(cfg)) return fail(PCGRL_E_ARG, "pcgrl_stats_holey needs a holey problem");
+    KParams p;
+    fill(p, cfg, nullptr);
+    p.mode = MODE_STATS;
+    p.n_envs = n;
+    p.stats_grids = grids;
+    p.stats_out = stats;
+    p.scratch = scratch;
+    p.holes = const_cast<int32_t*>(holes);
     return run(p, cfg->problem, stream);
 }
 
@@ -328,6 +356,7 @@ int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const vo
         sub.done = st->done + off;
         sub.changed = st->changed ? st->changed + off : nullptr;
         sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
+        sub.holes = st->holes ? st->holes + off * 4 : nullptr;
         int64_t a_stride = a_env;
         if (!actions_host) {   // actions already on the device: per-env stride from the action layout
             a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)

@@ -63,6 +63,9 @@ struct KParams {
     uint8_t* static_mask;         // [N, row_stride] or NULL
     float   static_prob;
     int32_t n_static_walls, wall_tile, static_eval_mode;
+    // holey problems: [N,4] (entrance_y, entrance_x, exit_y, exit_x) in bordered coordinates
+    int32_t* holes;
+    int32_t hole_mode;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,12 @@ struct ZeldaProb {
     }
 };
 
+struct BinaryHoleyProb {
+    static constexpr int P = 2;  // plane 0 {empty}; plane 1 holds no tile: the machine keeps the exit cell there
+    static constexpr int K = 3;  // regions, path-length, connected-path-length
+    __host__ __device__ static constexpr uint32_t plane_mask(int p) { return p == 0 ? 0x1u : 0x0u; }
+};
+
 // binary: regions + double-sweep longest path over the {empty} plane.
 //   helper.calc_longest_path runs, per component, BFS(first tile) -> far tile -> BFS(far) and keeps the max.
 //   Exact restatement used here: (1) isolated cells are components with eccentricity 0: count them with a
@@ -82,7 +88,7 @@ struct BinaryMachine {
     uint32_t* base;  // shared-memory copy of the non-isolated passable cells (re-read for the joint sweep)
     int phase, level, ncomp;
 
-    __device__ __forceinline__ void init(uint32_t* bb /* [P][NW] in shared memory */) {
+    __device__ __forceinline__ void init(uint32_t* bb /* [P][NW] in shared memory */, const KParams&, int64_t) {
         uint32_t pass[NW], ones[NW], nb[NW];
 #pragma unroll
         for (int i = 0; i < NW; ++i) {
@@ -166,6 +172,98 @@ struct BinaryMachine {
     }
 };
 
+// binary_holey (envs/probs/binary/binary_holey_prob.py:59-93): the stats are taken on the BORDERED map
+// (pcgrl_holey_env.py:52-53) whose border is solid except for the entrance and the exit.  The board built by
+// phase B holds the level (one row per word); init() moves it one cell down-right into the border frame and
+// digs the two holes.  regions = flood fill over the bordered board; then ONE BFS from the entrance:
+// path-length = its last level (np.max of the dijkstra map), connected-path-length = the level that reaches
+// the exit (0 when it never does: the reference maps -1 to 0, :69-77).
+template <int NW, bool TWO>
+struct BinaryHoleyMachine {
+    static_assert(!TWO, "the bordered board keeps one row per word");
+    using Prob = BinaryHoleyProb;
+    using B = Board<NW, TWO>;
+    uint32_t avail[NW], front[NW];
+    uint32_t* bb;   // plane 0: bordered passable board, plane 1: the exit cell
+    int phase, level, regions, connected, ey, ex;
+
+    __device__ __forceinline__ void init(uint32_t* planes, const KParams& p, int64_t env) {
+        bb = planes;
+        const int32_t* h = p.holes + env * 4;
+        ey = h[0];
+        ex = h[1];
+        const int xy = h[2], xx = h[3];
+        uint32_t pass[NW], ones[NW], nb[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) pass[i] = i > 0 ? planes[i - 1] << 1 : 0u;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            uint32_t xm = 0;
+            if (i == xy && (unsigned)xx < 32u) xm = 1u << xx;
+            if (i == ey && (unsigned)ex < 32u) pass[i] |= 1u << ex;
+            pass[i] |= xm;
+            planes[i] = pass[i];
+            planes[NW + i] = xm;
+            ones[i] = 0xFFFFFFFFu;
+        }
+        B::expand_and(pass, ones, nb);
+        regions = 0;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            const uint32_t iso = pass[i] & ~nb[i];
+            regions += __popc(iso);
+            avail[i] = pass[i] & ~iso;
+            front[i] = 0;
+        }
+        phase = 0;
+        level = 0;
+        connected = 0;
+    }
+    __device__ __forceinline__ bool expand() {
+        uint32_t n[NW];
+        if (!B::expand_and(front, avail, n)) return false;
+#pragma unroll
+        for (int i = 0; i < NW; ++i) {
+            avail[i] = B::minus_subset(avail[i], n[i]);
+            front[i] = n[i];
+        }
+        ++level;
+        if (phase == 1) {
+            uint32_t hit = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) hit |= n[i] & bb[NW + i];
+            if (hit) connected = level;
+        }
+        return true;
+    }
+    __device__ __forceinline__ bool transition(int* out) {
+        if (phase == 0) {
+            uint32_t t[NW];
+            if (B::minus_one(avail, t)) {
+#pragma unroll
+                for (int i = 0; i < NW; ++i) {
+                    front[i] = avail[i] & ~t[i];
+                    avail[i] &= t[i];
+                }
+                ++regions;
+                return false;
+            }
+            phase = 1;   // BFS from the entrance over the whole bordered board
+            level = 0;
+#pragma unroll
+            for (int i = 0; i < NW; ++i) {
+                front[i] = (i == ey && (unsigned)ex < 32u) ? 1u << ex : 0u;
+                avail[i] = bb[i] & ~front[i];
+            }
+            return false;
+        }
+        out[0] = regions;
+        out[1] = level;
+        out[2] = connected;
+        return true;
+    }
+};
+
 // zelda: tile counts, regions over the walkable plane, then (player == 1) BFS from the player:
 // nearest-enemy = first level >= 1 that touches an enemy, d(player->key) = level that touches the key;
 // then (key == 1 && door == 1) BFS from the key over walkable+door: d(key->door).  Unreached = -1 each
@@ -183,7 +281,7 @@ struct ZeldaMachine {
 #pragma unroll
         for (int i = 0; i < NW; ++i) x[i] = bb[plane * NW + i];
     }
-    __device__ __forceinline__ void init(uint32_t* planes) {
+    __device__ __forceinline__ void init(uint32_t* planes, const KParams&, int64_t) {
         bb = planes;
         uint32_t walk[NW], t[NW], ones[NW], nb[NW];
         load(0, walk);
@@ -419,7 +517,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
             if (b0 >= M) break;
             const int item = b0 + (tid & 31);
             if (item < M) {
-                m.init(s_bb + item * BBW);
+                m.init(s_bb + item * BBW, p, base + s_list[item]);
                 int out[K];
                 for (;;) {
                     if (m.expand()) continue;
@@ -442,7 +540,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
         int item = atomicAdd(&s_next, 1);
 #endif
         bool active = item < M;
-        if (active) m.init(s_bb + item * BBW);
+        if (active) m.init(s_bb + item * BBW, p, base + s_list[item]);
 #if PCGRL_BATCH_K > 0
         // Expansions and transitions are different instruction streams; with 32 independent grids per warp some
         // lane needs a transition on almost every trip, so an unbatched loop pays for both streams every trip
@@ -463,7 +561,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
                         item = atomicAdd(&s_next, 1);
                         active = item < M;
                         if (!active) break;
-                        m.init(s_bb + item * BBW);
+                        m.init(s_bb + item * BBW, p, base + s_list[item]);
                     }
                     pend = false;
                 }
@@ -485,7 +583,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
                 for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
                 item = PCGRL_NEXT_ITEM(item);
                 active = item < M;
-                if (active) m.init(s_bb + item * BBW);
+                if (active) m.init(s_bb + item * BBW, p, base + s_list[item]);
             }
         }
 #endif
@@ -534,6 +632,13 @@ static cudaError_t dispatch_shape(const KParams& p, cudaStream_t s, bool& suppor
 
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported) {
     if (problem == PCGRL_PROB_BINARY) return dispatch_shape<BinaryMachine>(p, s, supported);
+    if (problem == PCGRL_PROB_BINARY_HOLEY) {
+        // the bordered board: H + 2 rows of W + 2 cells, one row per word
+        supported = p.ndim == 2 && p.d1 + 2 <= 32 && p.d0 + 2 <= 32;
+        if (!supported) return cudaSuccess;
+        if (p.d0 + 2 <= 18) return launch<BinaryHoleyMachine<18, false>, 18, false>(p, s);
+        return launch<BinaryHoleyMachine<32, false>, 32, false>(p, s);
+    }
     if (problem == PCGRL_PROB_ZELDA) return dispatch_shape<ZeldaMachine>(p, s, supported);
     supported = false;
     return cudaSuccess;

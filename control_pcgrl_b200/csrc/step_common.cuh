@@ -132,6 +132,80 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
     return change | (wrote << 1);
 }
 
+// HoleyProblem.gen_holes (envs/probs/holey_prob.py:32-60) for a 2D map.  Border cells are numbered in the
+// row-major order of get_border_idxs (:20-30): the top row (x = 1..W), then (y, 0), (y, W+1) for y = 1..H, then
+// the bottom row.
+__device__ __forceinline__ void border_cell(int k, int H, int W, int& y, int& x) {
+    if (k < W) {
+        y = 0;
+        x = 1 + k;
+    } else if (k < W + 2 * H) {
+        const int j = k - W;
+        y = 1 + (j >> 1);
+        x = (j & 1) ? W + 1 : 0;
+    } else {
+        y = H + 1;
+        x = 1 + (k - W - 2 * H);
+    }
+}
+// _valid_holes (:74-90), restated literally: the reference names the pair (x, y) although coords[0] is the row,
+// and compares with _width - 1 / _height - 1 although the bordered map is two cells larger.
+__device__ __forceinline__ bool valid_holes(int a0, int a1, int b0, int b1, int H, int W) {
+    auto pull = [&](int& x, int& y) {
+        if (x == 0) x = 1;
+        else if (x == W - 1) x = W - 2;
+        else if (y == 0) y = 1;
+        else if (y == H - 1) y = H - 2;
+    };
+    pull(a0, a1);
+    pull(b0, b1);
+    return max(abs(a0 - b0), abs(a1 - b1)) > 1;
+}
+__device__ static void gen_holes(const KParams& p, int64_t gid, uint64_t genv, uint2 key) {
+    int32_t* h = p.holes + gid * 4;
+    const int H = p.d0, W = p.d1;
+    if (p.hole_mode == PCGRL_HOLES_FIXED) {   // :47-49 entrance (1, 0); exit np.array((_width, _height + 1))
+        h[0] = 1;
+        h[1] = 0;
+        h[2] = W;
+        h[3] = H + 1;
+        return;
+    }
+    // np.random.choice(n_border, size=4, replace=False): four distinct cells by rejection (Philox; the
+    // reference's global numpy stream is not part of the parity contract)
+    const int nb = 2 * (H + W);
+    int pick[4], n = 0;
+    for (uint32_t c = 0; n < 4 && c < 16; ++c) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch, 0xD0000000u + c), key);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < 4 && n < 4; ++j) {
+            const int k = (int)(rr[j] % (uint32_t)nb);
+            bool dup = false;
+            for (int q = 0; q < n; ++q) dup |= pick[q] == k;
+            if (!dup) pick[n++] = k;
+        }
+    }
+    int ey, ex;
+    border_cell(pick[0], H, W, ey, ex);
+    h[0] = ey;
+    h[1] = ex;
+    for (int i = 1; i < n; ++i) {
+        int y, x;
+        border_cell(pick[i], H, W, y, x);
+        if (valid_holes(ey, ex, y, x, H, W)) {
+            h[2] = y;
+            h[3] = x;
+            return;
+        }
+    }
+    // no candidate accepted: the reference keeps the exit of the previous episode (:53-58); a first episode
+    // (exit never set: both coordinates 0, a corner no hole can occupy) falls back to the fixed exit
+    if (h[2] == 0 && h[3] == 0) {
+        h[2] = W;
+        h[3] = H + 1;
+    }
+}
+
 // Episode start for env `gid` (thread-per-env): grid from src or Philox, counters, start position.
 __device__ static void reset_env(const KParams& p, int64_t gid) {
     int8_t* grid = p.grids + gid * p.row_stride;
@@ -225,6 +299,7 @@ __device__ static void reset_env(const KParams& p, int64_t gid) {
             }
         }
     }
+    if (p.holes && p.hole_mode != PCGRL_HOLES_GIVEN) gen_holes(p, gid, genv, key);
     int32_t* pos = p.pos + gid * 3;
     pos[0] = pos[1] = pos[2] = 0;
     if (p.rep == PCGRL_REP_NARROW && p.action_kind == PCGRL_ACT_PATCH) {

@@ -46,6 +46,22 @@ class _ProblemProxy:
         self._prob = dict(zip(spec.tiles, spec.init_probs))
         self.eval_maps = []
         self.path_coords, self.path_length = [], None
+        self._hole_queue = []
+        self.fixed_holes = getattr(owner._b, "fixed_holes", False)
+
+    # HoleyProblem (envs/probs/holey_prob.py): the current entrance / exit, (y, x) in bordered coordinates
+    @property
+    def entrance_coords(self):
+        return self._o._b.holes[0, :2].cpu().numpy()
+
+    @property
+    def exit_coords(self):
+        return self._o._b.holes[0, 2:].cpu().numpy()
+
+    def queue_holes(self, holes):
+        """Holes to use on the next resets: a list of (entrance, exit) pairs (the reference's _hole_queue,
+        holey_prob.py:43-44, without the ray actor that feeds it)."""
+        self._hole_queue = list(holes)
 
     def get_tile_types(self):
         return self._tile_types
@@ -60,7 +76,14 @@ class _ProblemProxy:
         if arr.dtype.kind in "US":
             lut = {t: i for i, t in enumerate(self._tile_types)}
             arr = np.vectorize(lut.__getitem__, otypes=[np.int8])(arr)
-        st = self._o._b.compute_stats(arr[None].astype(np.int8))[0].tolist()
+        if self._o._b.holey:
+            # the holey problems are handed the BORDERED map (pcgrl_holey_env.py:52-53) and read
+            # self.entrance_coords / self.exit_coords (binary_holey_prob.py:62-63)
+            inner = arr[tuple(slice(1, -1) for _ in arr.shape)]
+            holes = np.concatenate([np.asarray(self.entrance_coords), np.asarray(self.exit_coords)])[None]
+            st = self._o._b.compute_stats(inner[None].astype(np.int8), holes=holes)[0].tolist()
+        else:
+            st = self._o._b.compute_stats(arr[None].astype(np.int8))[0].tolist()
         out = OrderedDict(zip(self._o._b.stat_names, st))
         if "path-length" in out:
             self.path_length = out["path-length"]
@@ -133,6 +156,15 @@ class _RepProxy:
         obs = {"map": self._map.copy()}
         if self._o._b.representation in ("narrow", "turtle"):
             obs["pos"] = np.array(self._pos)
+        if self._o._b.holey:
+            # HoleyRepresentation.get_observation (envs/reps/wrappers.py:153-160): the bordered map with the
+            # holes dug as empty tiles (:139-142), positions shifted by the border
+            self._update_bordered_map()
+            ey, ex, xy, xx = self._o._b.holes[0].tolist()
+            self._bordered_map[ey, ex] = self._bordered_map[xy, xx] = 0
+            obs["map"] = self._bordered_map.astype(np.uint8)
+            if "pos" in obs:
+                obs["pos"] = obs["pos"] + 1
         return obs
 
     def update(self, action, **kwargs):
@@ -201,9 +233,12 @@ class PcgrlEnv(spaces.GymEnv):
             self.action_space = spaces.MultiDiscrete([*dims, n_tiles])         # wide_rep.py:23-24
         else:
             self.action_space = spaces.Dict({"map": spaces.Box(0, n_tiles - 1, shape=dims, dtype=np.uint8)})
-        obs = {"map": spaces.Box(low=0, high=n_tiles - 1, dtype=np.uint8, shape=tuple(b.obs_window))}
+        # HoleyRepresentation.get_observation_space (envs/reps/wrappers.py:162-174): map two cells larger, pos + 1
+        grow = 2 if b.holey else 0
+        obs = {"map": spaces.Box(low=0, high=n_tiles - 1, dtype=np.uint8, shape=tuple(d + grow for d in b.obs_window))}
         if rep in ("narrow", "turtle"):                                        # representation.py:223-228
-            obs["pos"] = spaces.Box(low=np.zeros(len(dims)), high=np.array([d - 1 for d in dims]), dtype=np.uint8)
+            obs["pos"] = spaces.Box(low=np.zeros(len(dims)) + grow // 2,
+                                    high=np.array([d - 1 for d in dims]) + grow // 2, dtype=np.uint8)
         self.observation_space = spaces.Dict(obs)
 
     def seed(self, seed=None):
@@ -251,7 +286,11 @@ class PcgrlEnv(spaces.GymEnv):
         grids = None
         if not self._rep._random_start and self._rep._old_map is not None:
             grids = self._rep._old_map[None]
-        self._b.reset(grids=grids)
+        holes = None
+        if self._b.holey and self._prob._hole_queue:                             # holey_prob.py:43-44
+            (ent, ext), self._prob._hole_queue = self._prob._hole_queue[0], self._prob._hole_queue[1:]
+            holes = np.concatenate([np.asarray(ent), np.asarray(ext)])[None]
+        self._b.reset(grids=grids, holes=holes)
         self._rep_stats = self._stats_dict() if self._get_stats_on_step else None
         self.metrics = self._rep_stats
         return self._raw_obs(), {}
@@ -287,9 +326,19 @@ class PcgrlEnv(spaces.GymEnv):
     def render(self, *a, **k):
         raise NotImplementedError("rendering is out of scope for control_pcgrl_b200 (SURVEY.md row 19)")
 
+    # PcgrlHoleyEnv (envs/pcgrl_holey_env.py:47-53)
+    def get_empty_tile(self):
+        return 0
+
+    def _get_rep_map(self):
+        if not self._b.holey:
+            return self._rep._map
+        return self._rep.get_observation()["map"]
+
 
 PcgrlCtrlEnv = PcgrlEnv
 PcgrlEnv3D = PcgrlEnv
+PcgrlHoleyEnv = PcgrlEnv
 
 
 class _ObsWrapper(spaces.GymWrapper):

@@ -68,6 +68,23 @@ def binary_spec(map_shape):
         range_weights={"regions": 100, "path-length": 100})
 
 
+def binary_holey_spec(map_shape):
+    """binary/binary_holey_prob.py:12-42 on top of BinaryProblem's constructor: stats are taken
+    on the bordered map with an entrance and an exit dug into the border."""
+    s = binary_spec(map_shape)
+    mp = s.static_trgs["path-length"]
+    s.name = "binary_holey"
+    s.stat_names = ["regions", "path-length", "connected-path-length"]
+    s.static_trgs = OrderedDict([("regions", 1), ("path-length", mp + 2), ("connected-path-length", mp + 2)])
+    s.cond_bounds = {"regions": s.cond_bounds["regions"], "path-length": (0, mp + 2),
+                     "connected-path-length": (0, mp + 2)}
+    s.reward_weights = {"regions": 100, "path-length": 0, "connected-path-length": 100}
+    # binary_holey_prob.py:106-117: the third term is get_range_reward over *path-length* again, weighted by
+    # connected-path-length's weight -- not a per-stat sum, so the in-kernel range mode does not offer it
+    s.range_bands, s.range_weights = {}, {}
+    return s
+
+
 def zelda_spec(map_shape):
     """zelda/zelda_prob.py:20-45 + zelda/zelda_ctrl_prob.py:17-75."""
     h, w = map_shape[0], map_shape[1]
@@ -151,7 +168,7 @@ def minecraft_3d_maze_spec(map_shape):
 
 
 _SPECS = {"binary": binary_spec, "zelda": zelda_spec, "sokoban": sokoban_spec, "smb": smb_spec,
-          "minecraft_3D_maze": minecraft_3d_maze_spec}
+          "minecraft_3D_maze": minecraft_3d_maze_spec, "binary_holey": binary_holey_spec}
 
 
 def get_spec(problem: str, map_shape) -> ProblemSpec:
@@ -165,7 +182,8 @@ def register_spec(name, fn):
     _SPECS[name] = fn
 
 
-PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze"]
+PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze", "binary_holey"]
+HOLEY_PROBLEMS = ("binary_holey",)
 # envs/reps/__init__.py:11-23 (+ the stale 3D spellings)
 REPRESENTATION_ALIASES = {"narrow": "narrow", "turtle": "turtle", "wide": "wide", "cellular": "cellular",
                           "narrow3D": "narrow", "turtle3D": "turtle", "wide3D": "wide", "cellular3D": "cellular"}

@@ -26,11 +26,21 @@
 extern "C" {
 #endif
 
-#define PCGRL_ABI_VERSION 3
+#define PCGRL_ABI_VERSION 4
 
 /* problems: envs/probs/__init__.py:31-58 (the five BASELINE.json names) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_SMB = 3,
-       PCGRL_PROB_MINECRAFT_3D_MAZE = 4 };
+       PCGRL_PROB_MINECRAFT_3D_MAZE = 4,
+       /* SURVEY 8f rank 2 -- holey problems: stats on the bordered map with an entrance and an exit dug into the
+          border (envs/probs/binary/binary_holey_prob.py:59-93, envs/pcgrl_holey_env.py:44-53) */
+       PCGRL_PROB_BINARY_HOLEY = 5 };
+/* where reset takes the entrance / exit holes of a holey problem from (envs/probs/holey_prob.py:32-60 gen_holes) */
+enum {
+    PCGRL_HOLES_GIVEN = 0,   /* leave pcgrl_state.holes as the caller set them (the reference's _hole_queue) */
+    PCGRL_HOLES_FIXED = 1,   /* fixed_holes: entrance (1, 0), exit (W, H + 1)  (holey_prob.py:47-49) */
+    PCGRL_HOLES_RANDOM = 2   /* four distinct random border cells; entrance = the first, exit = the first of the
+                                other three that _valid_holes accepts, else the previous exit (:51-58) */
+};
 /* representations: envs/reps/__init__.py:11-23 */
 enum { PCGRL_REP_NARROW = 0, PCGRL_REP_TURTLE = 1, PCGRL_REP_WIDE = 2, PCGRL_REP_CELLULAR = 3 };
 /* action encodings */
@@ -89,6 +99,8 @@ typedef struct pcgrl_config {
     int32_t n_static_walls;   /* random resets only: number of frozen random wall segments (wrappers.py:291-308) */
     int32_t wall_tile;        /* tile code written along those walls (Problem._wall_tile, pcgrl_env.py:58) */
     int32_t static_eval_mode; /* 1: use static_prob itself instead of U(0,1)*static_prob (set_eval_mode, :268) */
+    /* -- holey problems, ABI 4 --------------------------------------------------------------------------- */
+    int32_t hole_mode;        /* PCGRL_HOLES_*; only read by resets of a holey problem */
 } pcgrl_config;
 
 /* Device-resident state of N envs + the per-step inputs/outputs.
@@ -122,6 +134,9 @@ typedef struct pcgrl_state {
                               edit is undone, yet still counted as a change (envs/reps/wrappers.py:358-376).
                               Written by random resets when cfg.static_prob / n_static_walls ask for it; with
                               caller-supplied src_grids it is left as the caller set it */
+    int32_t* holes;        /* [N, 4] (ABI 4), holey problems only, else NULL: (entrance_y, entrance_x, exit_y, exit_x)
+                              in BORDERED coordinates, i.e. the reference's entrance_coords / exit_coords
+                              (holey_prob.py:41-42).  Read by step; written by reset per cfg.hole_mode */
 } pcgrl_state;
 
 /* -- queries (host only, no CUDA calls) ------------------------------------------------------- */
@@ -153,6 +168,10 @@ int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_
  * grids [n, row_stride] int8 -> stats [n, K] int32. */
 int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats, int64_t n, void* scratch,
                     void* stream);
+/* Same for a holey problem: holes [n, 4] int32 as in pcgrl_state.holes (BinaryHoleyProblem.get_stats reads
+ * self.entrance_coords / self.exit_coords, binary_holey_prob.py:62-63). */
+int32_t pcgrl_stats_holey(const pcgrl_config* cfg, const int8_t* grids, const int32_t* holes, int32_t* stats,
+                          int64_t n, void* scratch, void* stream);
 
 /* Observation tensors (control_pcgrl/wrappers.py Cropped :407-437 + OneHotEncoding :232-257 + ToImage
  * :140-150, and ControlWrapper.observe_metric_trgs control_wrappers.py:189-214).

@@ -251,6 +251,78 @@ def save_stats_fixture(problem, grids, name=None):
     print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
 
 
+# ------------------------------------------------------------------------------------------ holey problems
+def ref_holey_problem(h, w):
+    """The reference's BinaryHoleyProblem cannot be constructed at this commit (its __init__ calls
+    BinaryProblem.__init__(self) without the cfg that now requires, binary_holey_prob.py:13-16, and
+    PcgrlHoleyEnv.__init__ passes (prob, rep) where PcgrlCtrlEnv takes (cfg, prob, rep),
+    pcgrl_holey_env.py:32-33), so the instance is made without running __init__ and given only the
+    attributes its get_stats / hole helpers read.  get_stats, _valid_holes, get_border_idxs and
+    gen_all_holes then run verbatim."""
+    R.install()
+    import sys as _sys
+    _sys.modules["ray"].get = lambda x: x
+    from control_pcgrl.envs.probs.binary.binary_holey_prob import BinaryHoleyProblem
+    p = object.__new__(BinaryHoleyProblem)
+    p._height, p._width = h, w
+    p._tile_types = ["empty", "solid"]
+    p._hole_queue, p.fixed_holes = [], False
+    p._border_idxs = p.get_border_idxs()
+    return p
+
+
+def binary_holey_fixture():
+    H = R.load_helpers()
+    rng = np.random.default_rng(77)
+    arrays = {}
+    for gi, (h, w, n) in enumerate([(16, 16, 400), (10, 14, 120), (6, 6, 120), (30, 30, 40), (3, 5, 60)]):
+        p = ref_holey_problem(h, w)
+        border = p._border_idxs
+        grids, holes, stats = [], [], []
+        for i in range(n):
+            dens = [0.1, 0.3, 0.45, 0.5, 0.55, 0.7, 0.9][i % 7]
+            g = (rng.random((h, w)) < dens).astype(np.int8)
+            if i % 11 == 0:
+                g[:] = 0
+            if i % 13 == 0:
+                g[:] = 1
+            if i % 17 == 0:   # a serpentine corridor: long entrance -> exit paths
+                g[:] = 1
+                for y in range(0, h, 2):
+                    g[y, :] = 0
+                    if y + 1 < h:
+                        g[y + 1, (w - 1) if (y // 2) % 2 == 0 else 0] = 0
+            if i % 5 == 0:    # the fixed holes of holey_prob.py:47-49
+                e, x = np.array([1, 0]), np.array((w, h + 1))
+                if x[0] > h + 1 or x[1] > w + 1:
+                    k = rng.choice(len(border), 2, replace=False)
+                    e, x = border[k[0]], border[k[1]]
+            else:
+                k = rng.choice(len(border), 2, replace=False)
+                e, x = border[k[0]], border[k[1]]
+            b = np.full((h + 2, w + 2), 1, dtype=np.int64)
+            b[1:-1, 1:-1] = g
+            b[e[0], e[1]] = 0
+            b[x[0], x[1]] = 0
+            p.entrance_coords, p.exit_coords = e, x
+            st = p.get_stats(H.h2.get_string_map(b, ["empty", "solid"]))
+            grids.append(g)
+            holes.append([e[0], e[1], x[0], x[1]])
+            stats.append([int(st[k2]) for k2 in STAT_NAMES["binary_holey"]])
+        arrays[f"grids_{gi}"] = np.stack(grids)
+        arrays[f"holes_{gi}"] = np.array(holes, dtype=np.int32)
+        arrays[f"stats_{gi}"] = np.array(stats, dtype=np.int64)
+        # _valid_holes / border order (pins the random-hole generator's validity rule)
+        pairs = rng.choice(len(border), (200, 2))
+        arrays[f"border_{gi}"] = border.astype(np.int32)
+        arrays[f"valid_pairs_{gi}"] = pairs.astype(np.int32)
+        arrays[f"valid_{gi}"] = np.array([bool(p._valid_holes(border[a], border[b2])) for a, b2 in pairs])
+    arrays["stat_names"] = np.array(STAT_NAMES["binary_holey"])
+    path = os.path.join(OUT, "stats_binary_holey.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
+
+
 # ------------------------------------------------------------------------------------------ traces
 def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None, n_envs=4, seed=0,
               max_board_scans=3, change_percentage=None, raw_only=False, n_steps=None, init_p=None,
@@ -445,6 +517,7 @@ def main(which=None):
                                                          SOK_W, seed=37, static_prob=0.6, init_p=SOK_AP, action_p=SOK_AP,
                                                          n_envs=3, obs_every=17),
     })
+    jobs["stats_binary_holey"] = binary_holey_fixture
     for k, fn in jobs.items():
         if which and k not in which:
             continue

@@ -29,6 +29,7 @@ TILES = {
     "sokoban": ["empty", "solid", "player", "crate", "target"],                     # sokoban_prob.py:26
     "smb": ["empty", "solid", "enemy", "brick", "question", "coin", "tube"],        # smb_prob.py:12
     "minecraft_3D_maze": ["AIR", "DIRT"],                                           # minecraft_3D_maze_prob.py:26
+    "binary_holey": ["empty", "solid"],                                             # binary_holey_prob.py:12-14
 }
 STAT_NAMES = {
     "binary": ["regions", "path-length"],
@@ -37,6 +38,7 @@ STAT_NAMES = {
     "smb": ["dist-floor", "disjoint-tubes", "enemies", "empty", "noise", "jumps", "jumps-dist",
             "dist-win", "sol-length"],
     "minecraft_3D_maze": ["regions", "path-length", "n_jump"],
+    "binary_holey": ["regions", "path-length", "connected-path-length"],
 }
 # tile init probabilities used by reset when no grid is supplied
 INIT_PROBS = {
@@ -221,7 +223,62 @@ def zelda_stats(grid):
     return st
 
 
-def get_stats(problem, grid):
+def bordered_with_holes(grid, holes, border_tile=1, empty_tile=0):
+    """The map Problem.get_stats sees in the holey envs (pcgrl_holey_env.py:52-53 `_get_rep_map` ->
+    `_bordered_map`): the level inside a one-tile border (reps/representation.py:162-164) into which the
+    entrance and the exit were dug as empty tiles (reps/wrappers.py:139-142).  holes = (entrance_y, entrance_x,
+    exit_y, exit_x) in bordered coordinates (holey_prob.py:41-42: coords[0] is y)."""
+    h, w = grid.shape
+    b = np.full((h + 2, w + 2), border_tile, dtype=np.int64)
+    b[1:-1, 1:-1] = grid
+    ey, ex, xy, xx = (int(v) for v in holes)
+    b[ey, ex] = empty_tile
+    b[xy, xx] = empty_tile
+    return b
+
+
+def binary_holey_stats(grid, holes):
+    """probs/binary/binary_holey_prob.py:59-93 on the bordered map: one BFS from the entrance;
+    path-length = its largest distance, connected-path-length = distance of the exit (0 when unreachable);
+    regions over the bordered map (the holes are empty tiles)."""
+    b = bordered_with_holes(grid, holes)
+    ey, ex, xy, xx = (int(v) for v in holes)
+    d = bfs_distances(b, [0], ex, ey)                                 # :62 run_dijkstra(x, y, ...)
+    connected = int(d[xy, xx])                                        # :63
+    return {"regions": count_regions(b, [0]), "path-length": int(d.max()),          # :65-66, :89
+            "connected-path-length": 0 if connected == -1 else connected}            # :69-77
+
+
+def holey_border_idxs(h, w):
+    """holey_prob.py:20-30 get_border_idxs: non-corner border cells of the (h+2, w+2) map, row-major."""
+    m = np.zeros((h + 2, w + 2), dtype=np.uint8)
+    m[1:-1, 0] = m[1:-1, -1] = 1
+    m[0, 1:-1] = m[-1, 1:-1] = 1
+    return np.argwhere(m == 1)
+
+
+def valid_holes(entrance, exit_, h, w):
+    """holey_prob.py:74-90 _valid_holes, restated literally (its x/y naming and the `_width - 1` tests are
+    the reference's own): each hole is pulled one cell inwards on at most one axis, then the two must differ
+    by more than one cell on some axis."""
+    pts = []
+    for (x, y) in (entrance, exit_):
+        x, y = int(x), int(y)
+        if x == 0:
+            x = 1
+        elif x == w - 1:
+            x = w - 2
+        elif y == 0:
+            y = 1
+        elif y == h - 1:
+            y = h - 2
+        pts.append((x, y))
+    return max(abs(pts[0][0] - pts[1][0]), abs(pts[0][1] - pts[1][1])) > 1
+
+
+def get_stats(problem, grid, holes=None):
+    if problem == "binary_holey":
+        return binary_holey_stats(grid, holes)
     if problem == "binary":
         return binary_stats(grid)
     if problem == "zelda":
@@ -259,6 +316,14 @@ def problem_constants(problem, map_shape):
         return dict(static_trgs={"regions": 1, "path-length": mp},
                     cond_bounds={"regions": (0, w * np.ceil(h / 2)), "path-length": (0, mp)},
                     default_weights={"regions": 100, "path-length": 100})
+    if problem == "binary_holey":
+        # binary_holey_prob.py:19-42 on top of BinaryProblem's constructor
+        h, w = map_shape
+        mp = np.ceil(w / 2) * h + np.floor(h / 2)
+        return dict(static_trgs={"regions": 1, "path-length": mp + 2, "connected-path-length": mp + 2},
+                    cond_bounds={"regions": (0, w * np.ceil(h / 2)), "path-length": (0, mp + 2),
+                                 "connected-path-length": (0, mp + 2)},
+                    default_weights={"regions": 100, "path-length": 0, "connected-path-length": 100})
     if problem == "zelda":
         h, w = map_shape
         mne = np.ceil(w / 2 + 1) * h
@@ -511,7 +576,8 @@ class OracleEnv:
         self.coords = narrow_coords(self.map_shape) if self.act_window is None else \
             multiaction_coords(self.map_shape, self.act_window)
 
-    def reset(self, grid, pos=None, targets=None, static=None):
+    def reset(self, grid, pos=None, targets=None, static=None, holes=None):
+        self.holes = None if holes is None else [int(v) for v in holes]   # pcgrl_holey_env.py:44-45
         if targets:
             self.targets.update(targets)                                        # control_wrappers.py:170-178
         self.grid = np.array(grid, dtype=np.int64).reshape(self.map_shape)
@@ -522,7 +588,8 @@ class OracleEnv:
                       "pos": [0] * len(self.map_shape) if pos is None else [int(v) for v in pos]}
         if self.rep == "narrow":
             self.state["pos"] = [int(v) for v in self.coords[0]]               # narrow_rep.py:43-50
-        self.stats = get_stats(self.problem, self.grid)                         # pcgrl_env.py:174-175
+        self.stats = get_stats(self.problem, self.grid, self.holes) if self.holes is not None else \
+            get_stats(self.problem, self.grid)                                  # pcgrl_env.py:174-175
         self.last_loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)
         return self.stats
 
@@ -537,7 +604,8 @@ class OracleEnv:
             done = done or self.changes > self.max_changes                      # :308-309
         old_stats = self.stats
         if changed:
-            self.stats = get_stats(self.problem, self.grid)                     # :314-323
+            self.stats = get_stats(self.problem, self.grid, self.holes) if self.holes is not None else \
+                get_stats(self.problem, self.grid)                              # :314-323
         if self.reward_mode == "range":                                         # legacy Problem.get_reward
             return legacy_reward(self.problem, self.stats, old_stats), bool(done), changed
         loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)
