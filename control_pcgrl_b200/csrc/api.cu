@@ -16,6 +16,7 @@ cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported);
 int64_t sokoban_scratch_bytes();
 int64_t smb_scratch_bytes();
+int64_t maze3d_scratch_bytes();
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
 
 static thread_local std::string g_err;
@@ -151,7 +152,9 @@ static int run(const KParams& p, int problem, void* stream) {
         e = launch_smb(p, (cudaStream_t)stream, supported);
     else
         e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
-    if (!supported) return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet");
+    if (!supported)
+        return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet (or scratch is NULL although "
+                                         "pcgrl_scratch_bytes() > 0)");
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
@@ -200,7 +203,8 @@ int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
     // node pools / heaps / hash tables of the solver problems: one slice per resident search warp
     if (cfg->problem == PCGRL_PROB_SOKOBAN) return sokoban_scratch_bytes();
     if (cfg->problem == PCGRL_PROB_SMB) return smb_scratch_bytes();
-    return 0;  // binary / zelda / minecraft keep all search state in registers / shared memory
+    if (cfg->problem == PCGRL_PROB_MINECRAFT_3D_MAZE) return maze3d_scratch_bytes();   // per-cell jump counts
+    return 0;  // binary / zelda keep all search state in registers / shared memory
 }
 
 int64_t pcgrl_step_bytes(const pcgrl_config* c) {

@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, con
 
 // host side: persistent launch sized from the occupancy the dynamic shared memory allows
 template <class Prob, int WARPS = SEARCH_WARPS>
-static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int max_ctas_per_sm = 1 << 20) {
+static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int max_ctas_per_sm = 1 << 20,
+                                 int max_ctas = SEARCH_MAX_CTAS) {
     static int n_sm = 0;
     static std::atomic<unsigned> next_slot{0};
     constexpr int SEARCH_THREADS = WARPS * 32;
@@ -181,7 +182,7 @@ static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_
     if (tiles == 0) return cudaSuccess;
     if (per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
     int64_t cap = (int64_t)n_sm * per_sm;
-    if (max_ctas_per_sm < (1 << 20) && cap > SEARCH_MAX_CTAS) cap = SEARCH_MAX_CTAS;   // scratch is sized for this
+    if (max_ctas_per_sm < (1 << 20) && cap > max_ctas) cap = max_ctas;   // the global scratch is sized for this
     const int ctas = (int)(tiles < cap ? tiles : cap);
     const int slot = (int)(next_slot.fetch_add(1) % SEARCH_SLOTS);
     kern<<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp, slot);
