@@ -24,7 +24,11 @@ namespace pcgrl {
 
 constexpr int SMB_POWER = 10000;                 // smb_prob.py:21 _solver_power
 constexpr int SMB_NODES = 4 * SMB_POWER + 8;
-constexpr int SMB_MAX_CTAS_PER_SM = 2;
+#ifndef PCGRL_SMB_CTAS_PER_SM
+#define PCGRL_SMB_CTAS_PER_SM 4   // A/B on B200 (116x16, 65 536 envs): 2 / 3 / 4 CTAs per SM -> 7.0 / 8.5 / 9.7e6 env-steps/s
+#endif
+constexpr int SMB_MAX_CTAS_PER_SM = PCGRL_SMB_CTAS_PER_SM;
+constexpr int SMB_MAX_CTAS = 160 * SMB_MAX_CTAS_PER_SM;   // sizes the global scratch (>= 148 SMs x CTAs per SM)
 constexpr int SMB_YOFF = 8;                      // y >= -5 (four rows per jump, re-jump possible from y = -1)
 
 struct SmbScratch {
@@ -33,7 +37,7 @@ struct SmbScratch {
     static constexpr size_t total = (heap + 4 * (size_t)SMB_NODES + 255) / 256 * 256;
 };
 
-int64_t smb_scratch_bytes() { return (int64_t)SmbScratch::total * SEARCH_MAX_CTAS * SEARCH_WARPS; }
+int64_t smb_scratch_bytes() { return (int64_t)SmbScratch::total * SMB_MAX_CTAS * SEARCH_WARPS; }
 
 struct SmbLayout {
     int stage, solid, visited, total, visited_bytes;
@@ -322,7 +326,7 @@ cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported) {
         supported = false;
         return cudaSuccess;
     }
-    return launch_search<SmbProb>(p, s, L.total, SMB_MAX_CTAS_PER_SM);
+    return launch_search<SmbProb>(p, s, L.total, SMB_MAX_CTAS_PER_SM, SMB_MAX_CTAS);
 }
 
 }  // namespace pcgrl

@@ -29,7 +29,11 @@ constexpr int SOK_POWER = 10000;                 // sokoban_prob.py:40 _solver_p
 constexpr int SOK_NODES = 4 * SOK_POWER + 8;     // root + <= 4 children per iteration
 constexpr int SOK_TABLE = 32768;                 // visited hash slots (<= 10 000 insertions per search)
 constexpr int SOK_MAX_CRATES = 15;
-constexpr int SOK_MAX_CTAS_PER_SM = 2;
+#ifndef PCGRL_SOK_CTAS_PER_SM
+#define PCGRL_SOK_CTAS_PER_SM 2   // A/B on B200: 2 / 3 / 4 CTAs per SM change nothing (bounded by the longest solve)
+#endif
+constexpr int SOK_MAX_CTAS_PER_SM = PCGRL_SOK_CTAS_PER_SM;
+constexpr int SOK_MAX_CTAS = 160 * SOK_MAX_CTAS_PER_SM;   // sizes the global scratch (>= 148 SMs x CTAs per SM)
 
 struct SokScratch {
     // byte offsets inside one warp's slice
@@ -41,7 +45,7 @@ struct SokScratch {
     static constexpr size_t total = (table + 4 * (size_t)SOK_TABLE + 255) / 256 * 256;
 };
 
-int64_t sokoban_scratch_bytes() { return (int64_t)SokScratch::total * SEARCH_MAX_CTAS * SEARCH_WARPS; }
+int64_t sokoban_scratch_bytes() { return (int64_t)SokScratch::total * SOK_MAX_CTAS * SEARCH_WARPS; }
 
 struct SokobanProb {
     static constexpr int K = 7;   // player crate target regions dist-win sol-length ratio
@@ -449,7 +453,7 @@ struct SokobanProb {
 cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported) {
     supported = p.ndim == 2 && p.d0 <= 14 && p.d1 <= 14 && p.scratch != nullptr;
     if (!supported) return cudaSuccess;
-    return launch_search<SokobanProb>(p, s, SokobanProb::smem_bytes(p.row_stride), SOK_MAX_CTAS_PER_SM);
+    return launch_search<SokobanProb>(p, s, SokobanProb::smem_bytes(p.row_stride), SOK_MAX_CTAS_PER_SM, SOK_MAX_CTAS);
 }
 
 }  // namespace pcgrl
