@@ -217,6 +217,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     lib = _lib.load()
+    # one process per GPU: stay on the host cores / NUMA node local to this GPU (pinned buffers follow)
+    from control_pcgrl_b200.dist import bind_to_gpu_cpus
+    bound = bind_to_gpu_cpus(local) if world > 1 else []
 
     cfg = P.make_config(problem, rep, map_shape=shape, obs_window=obs_window, controls=controls)
     env = P.BatchedPcgrlEnv(cfg, n_envs, device=dev, env_offset=rank * n_envs, seed=a.seed, auto_reset=True,
@@ -374,7 +377,8 @@ def main():
                        "episode_steps": int(env.max_iterations) + 1, "auto_reset": True,
                        "l2": ("inputs larger than L2 (%.0f MB grids)" % (grid_bytes / 1e6)) if flush is None
                              else "256 MB L2 flush between steps (excluded from the timing)",
-                       "parallelism": f"env-sharded x{world}, no collective on the step path"},
+                       "parallelism": f"env-sharded x{world}, no collective on the step path",
+                       "host_cores_bound_rank0": len(bound)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "mean_stats": {n: float(v) for n, v in zip(env.stat_names, red["mean"].tolist())}}
     print(json.dumps(line), flush=True)

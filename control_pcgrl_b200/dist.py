@@ -41,6 +41,39 @@ def init_from_env(backend: str | None = None):
     return rank, local, world
 
 
+def bind_to_gpu_cpus(device_index: int) -> list:
+    """One process per GPU: pin this process to the host cores NVML reports as local to the GPU (same NUMA node /
+    PCIe root), intersected with the cores the container allows.  Pinned staging buffers allocated afterwards
+    land on that node, so the host<->device copies of the e2e path do not cross sockets when 8 ranks run at
+    once.  Returns the cores bound to ([] = left unchanged: NVML missing, or nothing in common)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        # torch's device index -> NVML handle through the PCI bus id (CUDA_VISIBLE_DEVICES may reorder)
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(
+            torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        h = None
+        if bus is not None:
+            for i in range(pynvml.nvmlDeviceGetCount()):
+                hi = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(hi).bus == bus:
+                    h = hi
+                    break
+        if h is None:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cores = sorted(local & allowed)
+        if cores and len(cores) < len(allowed):
+            os.sched_setaffinity(0, cores)
+            return cores
+    except Exception:  # noqa: BLE001 -- affinity is an optimisation, never a requirement
+        pass
+    return []
+
+
 def reduce_episode_stats(values: torch.Tensor, names=None, group=None):
     """values: [n_local_episodes, K] (any numeric dtype, any device) -> dict of global
     count / mean / std / min / max per column, identical on every rank."""
