@@ -9,6 +9,7 @@
 // One thread per output pixel writes all of its channels (channels-last => contiguous per thread, and
 // consecutive threads write consecutive pixels => coalesced stores).  The int8 grid rows are re-read
 // through L1/L2; nothing else is loaded.
+#include <cstdlib>
 #include "pcgrl_device.cuh"
 
 namespace pcgrl {
@@ -82,6 +83,214 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Staged writer (the one that normally runs).  The output is HBM-write bound (3 KB .. 17 KB per env against a
+// 256-byte grid), so the stores must be full 128-bit coalesced vectors -- but a pixel's record (its channels) is
+// 3 .. 9+ elements, never a vector.  Per trip a CTA therefore takes GB groups of G envs whose output is a whole
+// number of 16-byte vectors, stages their grids / positions / ControlWrapper planes in shared memory, builds the
+// records there (zero fill + one store per pixel, 32-bit index math with multiply-high divisions), and then
+// streams the staged bytes to HBM with one 128-bit store per thread.  The one-thread-per-pixel kernel above,
+// which stores element by element, stays as the fallback for unaligned output pointers / oversized groups.
+// ------------------------------------------------------------------------------------------------
+struct ObsVec {
+    int32_t G, GB, E, pix, n_ch, n_map_ch, stage_bytes, planes_bytes;
+    uint32_t m_pix, m_o2, m_o12;   // floor(2^32 / d) of the divisors
+};
+__host__ __device__ inline uint32_t floor_magic(uint32_t d) { return d <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / d); }
+// n / d for any 32-bit n: the multiply-high by floor(2^32/d) is at most one too small
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t d, uint32_t magic, uint32_t& rem) {
+    uint32_t q = __umulhi(n, magic);
+    rem = n - q * d;
+    if (rem >= d) {
+        ++q;
+        rem -= d;
+    }
+    return q;
+}
+constexpr int OBS_MAX_CTA_ENVS = 64;   // GB * G
+constexpr int OBS_THREADS = 256;
+
+template <typename T, bool CROP, bool STATIC, bool D3>
+__global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams p, const ObsVec v) {
+    extern __shared__ __align__(16) uint8_t obs_smem[];
+    T* stage = (T*)obs_smem;                                         // [envs of the trip][pix][n_ch]
+    T* s_planes = (T*)(obs_smem + v.stage_bytes);                    // [envs of the trip][2 * n_ctrl]
+    // the trip's level grids (+ frozen-tile masks) and positions, staged with coalesced 128-bit loads so that the
+    // per-pixel phase never waits on HBM
+    const int8_t* s_grid = (const int8_t*)(obs_smem + v.stage_bytes + v.planes_bytes);
+    const uint8_t* s_mask = (const uint8_t*)s_grid + (size_t)v.GB * v.G * p.row_stride;
+    const int32_t* s_pos = (const int32_t*)(s_mask + (p.static_mask ? (size_t)v.GB * v.G * p.row_stride : 0));
+    const int tid = threadIdx.x;
+    const int envs_per_trip = v.GB * v.G;
+    const int64_t trips = (p.n_envs + envs_per_trip - 1) / envs_per_trip;
+    const int o12 = p.o1 * p.o2;
+    const int n_pl = 2 * p.n_ctrl;
+    for (int64_t trip = blockIdx.x; trip < trips; trip += gridDim.x) {
+        const int64_t env0 = trip * envs_per_trip;
+        const int n_here = (int)min((int64_t)envs_per_trip, p.n_envs - env0);
+        __syncthreads();                                             // the previous trip's copy-out is done
+        {
+            const int nz = (int)(((int64_t)n_here * v.E * (int64_t)sizeof(T) + 15) / 16);
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            for (int i = tid; i < nz; i += OBS_THREADS) ((uint4*)stage)[i] = z;
+            const int nv = n_here * (p.row_stride / 16);
+            const uint4* g = (const uint4*)(p.grids + env0 * p.row_stride);
+            for (int i = tid; i < nv; i += OBS_THREADS) ((uint4*)s_grid)[i] = g[i];
+            if (p.static_mask) {
+                const uint4* m = (const uint4*)(p.static_mask + env0 * p.row_stride);
+                for (int i = tid; i < nv; i += OBS_THREADS) ((uint4*)s_mask)[i] = m[i];
+            }
+            if (p.crop)
+                for (int i = tid; i < n_here * 3; i += OBS_THREADS) ((int32_t*)s_pos)[i] = p.pos[env0 * 3 + i];
+        }
+        if (p.n_ctrl > 0) {
+            for (int i = tid; i < n_here * p.n_ctrl; i += OBS_THREADS) {
+                const int el = i / p.n_ctrl, c = i - el * p.n_ctrl;
+                const int64_t env = env0 + el;
+                const int k = p.ctrl_idx[c];
+                const double* trg = p.targets + ((p.targets_per_env ? env * p.n_stats : 0) + k) * 2;
+                double t = trg[0];
+                if (!isnan(trg[1])) t = (trg[0] + trg[1]) / 2;
+                s_planes[el * n_pl + 2 * c] = (T)(t / p.ctrl_range[c]);
+                s_planes[el * n_pl + 2 * c + 1] = (T)((double)p.stats[env * p.n_stats + k] / p.ctrl_range[c]);
+            }
+        }
+        __syncthreads();
+        // ---- records: the stage is zero-filled with 128-bit stores, then every pixel sets its ONE hot element ----
+        // (a one-hot record is all zeros but one element, so building it is a single store at offset `hot`; the
+        // ControlWrapper planes and the static_builds plane are the only other elements written.)  A thread takes
+        // four consecutive pixels: the index math is paid once and the coordinates advance with carries.
+        const int n_pix = n_here * v.pix;
+        for (int first = tid * 4; first < n_pix; first += OBS_THREADS * 4) {
+            // coordinates of the first pixel: (env of the trip, q0, q1[, q2]); in 2D the image is (o0, o1)
+            uint32_t r, q0, q1, q2 = 0;
+            uint32_t el = fdiv((uint32_t)first, (uint32_t)v.pix, v.m_pix, r);
+            if (D3) {
+                uint32_t pr;
+                q0 = fdiv(r, (uint32_t)o12, v.m_o12, pr);
+                q1 = fdiv(pr, (uint32_t)p.o2, v.m_o2, q2);
+            } else {
+                q0 = fdiv(r, (uint32_t)p.o1, v.m_o12, q1);
+            }
+            const int8_t* grid = s_grid + el * p.row_stride;
+            int c0 = 0, c1 = 0, c2 = 0;
+            if (CROP) {
+                c0 = s_pos[el * 3 + 0] - p.o0 / 2;
+                c1 = s_pos[el * 3 + 1] - p.o1 / 2;
+                if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
+            }
+            T* o = stage + (size_t)first * v.n_ch + n_pl;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (first + k < n_pix) {
+                    const int s0 = c0 + (int)q0, s1 = c1 + (int)q1, s2 = D3 ? c2 + (int)q2 : 0;
+                    bool inside = true;
+                    if (CROP)
+                        inside = (unsigned)s0 < (unsigned)p.d0 && (unsigned)s1 < (unsigned)p.d1 &&
+                                 (!D3 || (unsigned)s2 < (unsigned)p.d2);
+                    const int cell = D3 ? (s0 * p.d1 + s1) * p.d2 + s2 : s0 * p.d1 + s1;
+                    // crop: channel 0 = out of bounds, tile t -> channel t + 1 (wrappers.py:420-437); else channel = tile
+                    const int hot = inside ? grid[cell] + (CROP ? 1 : 0) : 0;
+                    for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
+                    o[k * v.n_ch + hot] = (T)1;
+                    if (STATIC) {   // see k_observe: the bordered frozen-tile mask through the same crop
+                        const int b0 = s0 - 1, b1 = s1 - 1, b2 = D3 ? s2 - 1 : 0;
+                        const bool in_bordered = b0 >= -1 && b0 <= p.d0 && b1 >= -1 && b1 <= p.d1 &&
+                                                 (!D3 || (b2 >= -1 && b2 <= p.d2));
+                        if (in_bordered) {
+                            const bool inner = (unsigned)b0 < (unsigned)p.d0 && (unsigned)b1 < (unsigned)p.d1 &&
+                                               (unsigned)b2 < (unsigned)p.d2;
+                            if (!inner || s_mask[el * p.row_stride + (b0 * p.d1 + b1) * p.d2 + b2] != 0)
+                                o[k * v.n_ch + v.n_map_ch] = (T)1;
+                        }
+                    }
+                    // next pixel: the last image axis is fastest
+                    bool wrap_env = false;
+                    if (D3) {
+                        if (++q2 == (uint32_t)p.o2) {
+                            q2 = 0;
+                            if (++q1 == (uint32_t)p.o1) {
+                                q1 = 0;
+                                wrap_env = ++q0 == (uint32_t)p.o0;
+                            }
+                        }
+                    } else if (++q1 == (uint32_t)p.o1) {
+                        q1 = 0;
+                        wrap_env = ++q0 == (uint32_t)p.o0;
+                    }
+                    if (wrap_env) {   // the quad continues in the next env of the trip
+                        q0 = 0;
+                        ++el;
+                        grid += p.row_stride;
+                        if (CROP && first + k + 1 < n_pix) {
+                            c0 = s_pos[el * 3 + 0] - p.o0 / 2;
+                            c1 = s_pos[el * 3 + 1] - p.o1 / 2;
+                            if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- copy-out: 128-bit coalesced stores ---------------------------------------------------------------
+        const int64_t elems = (int64_t)n_here * v.E;
+        const int n_vec = (int)(elems * (int64_t)sizeof(T) / 16);
+        uint4* dst = (uint4*)((T*)p.out + env0 * v.E);
+        const uint4* src = (const uint4*)stage;
+        for (int i = tid; i < n_vec; i += OBS_THREADS) dst[i] = src[i];
+        // a partly filled last group may end inside a vector: element-wise tail
+        const int done = n_vec * (16 / (int)sizeof(T));
+        for (int i = done + tid; i < (int)elems; i += OBS_THREADS) ((T*)p.out + env0 * v.E)[i] = stage[i];
+    }
+}
+
+template <typename T>
+static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
+    done = false;
+    if ((uintptr_t)p.out % 16) return cudaSuccess;
+    const int64_t pix = (int64_t)p.o0 * p.o1 * p.o2;
+    const int n_map_ch = p.crop ? p.n_tiles + 1 : p.n_tiles;
+    const int n_ch = 2 * p.n_ctrl + n_map_ch + (p.static_mask ? 1 : 0);
+    const int64_t E = pix * n_ch;
+    ObsVec v;
+    v.G = 1;
+    while ((v.G * E * (int64_t)sizeof(T)) % 16) v.G *= 2;          // <= 16
+    const int64_t group_bytes = v.G * E * (int64_t)sizeof(T);
+    if (group_bytes > 160 * 1024) return cudaSuccess;               // oversized: the scalar kernel handles it
+    v.GB = 1;
+    while (v.GB * v.G * 2 <= OBS_MAX_CTA_ENVS && (v.GB * 2) * group_bytes <= 24 * 1024) v.GB *= 2;
+    v.E = (int)E;
+    v.pix = (int)pix;
+    v.n_ch = n_ch;
+    v.n_map_ch = n_map_ch;
+    v.stage_bytes = (int)(v.GB * group_bytes);
+    v.m_pix = floor_magic((uint32_t)pix);
+    v.m_o2 = floor_magic((uint32_t)p.o2);
+    v.m_o12 = floor_magic((uint32_t)(p.o1 * p.o2));   // 2D: o2 == 1, i.e. the magic of o1
+    v.planes_bytes = (v.GB * v.G * 2 * p.n_ctrl * (int)sizeof(T) + 15) / 16 * 16;
+    const int dyn = v.stage_bytes + v.planes_bytes + v.GB * v.G * (p.row_stride * (p.static_mask ? 2 : 1) + 12);
+    const bool d3 = p.ndim == 3, st = p.static_mask != nullptr, cr = p.crop != 0;
+    void (*kern)(const ObsParams, const ObsVec) =
+        cr ? (st ? (d3 ? k_observe_staged<T, true, true, true> : k_observe_staged<T, true, true, false>)
+                 : (d3 ? k_observe_staged<T, true, false, true> : k_observe_staged<T, true, false, false>))
+           : (d3 ? k_observe_staged<T, false, false, true> : k_observe_staged<T, false, false, false>);
+    cudaError_t e;
+    if (dyn > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)
+        return e;
+    int per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, OBS_THREADS, dyn)) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaSuccess;
+    int dev = 0, n_sm = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t trips = (p.n_envs + v.GB * v.G - 1) / (v.GB * v.G);
+    const int64_t cap = (int64_t)n_sm * per_sm;
+    const unsigned blocks = (unsigned)(trips < cap ? trips : cap);
+    kern<<<blocks, OBS_THREADS, dyn, s>>>(p, v);
+    done = true;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& a, cudaStream_t s) {
     ObsParams p;
     p.ndim = cfg.ndim;
@@ -116,6 +325,13 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     if (a.out_kind == 0 && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
     const int64_t total = st.n_envs * (int64_t)p.o0 * p.o1 * p.o2;
     if (total == 0) return cudaSuccess;
+    if (!getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
+        bool done = false;
+        cudaError_t e = a.out_kind == 0 ? launch_vec<uint8_t>(p, s, done)
+                      : a.out_kind == 1 ? launch_vec<float>(p, s, done)
+                      : a.out_kind == 2 ? launch_vec<double>(p, s, done) : cudaErrorInvalidValue;
+        if (e != cudaSuccess || done) return e;
+    }
     const int64_t want = (total + 255) / 256;
     const unsigned blocks = (unsigned)(want < 148 * 32 ? want : 148 * 32);
     if (a.out_kind == 0)
