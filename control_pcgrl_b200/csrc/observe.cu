@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t d, uint32_t magic,
 constexpr int OBS_MAX_CTA_ENVS = 64;   // GB * G
 constexpr int OBS_THREADS = 256;
 
-template <typename T, bool CROP, bool STATIC, bool D3>
+template <typename T, bool CROP, bool STATIC, bool D3, bool ROW4>
 __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams p, const ObsVec v) {
     extern __shared__ __align__(16) uint8_t obs_smem[];
     T* stage = (T*)obs_smem;                                         // [envs of the trip][pix][n_ch]
@@ -180,6 +180,35 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
             }
             T* o = stage + (size_t)first * v.n_ch + n_pl;
+            if constexpr (ROW4) {
+                // the last image axis is a multiple of 4 long: the four pixels share a row, so the row test and the
+                // row pointer are computed once and nothing carries
+                bool row_ok = true;
+                if (CROP) row_ok = D3 ? ((unsigned)(c0 + (int)q0) < (unsigned)p.d0 && (unsigned)(c1 + (int)q1) < (unsigned)p.d1)
+                                      : (unsigned)(c0 + (int)q0) < (unsigned)p.d0;
+                const int dl = D3 ? p.d2 : p.d1;
+                const int sl = D3 ? c2 + (int)q2 : c1 + (int)q1;
+                const int8_t* rowp = D3 ? grid + ((c0 + (int)q0) * p.d1 + (c1 + (int)q1)) * p.d2 : grid + (c0 + (int)q0) * p.d1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
+                    const int hot = inside ? rowp[sl + k] + (CROP ? 1 : 0) : 0;
+                    for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
+                    o[k * v.n_ch + hot] = (T)1;
+                    if (STATIC) {   // see k_observe: the bordered frozen-tile mask through the same crop
+                        const int s0 = c0 + (int)q0, s1 = D3 ? c1 + (int)q1 : sl + k, s2 = D3 ? sl + k : 0;
+                        const int b0 = s0 - 1, b1 = s1 - 1, b2 = D3 ? s2 - 1 : 0;
+                        const bool in_bordered = b0 >= -1 && b0 <= p.d0 && b1 >= -1 && b1 <= p.d1 &&
+                                                 (!D3 || (b2 >= -1 && b2 <= p.d2));
+                        if (in_bordered) {
+                            const bool inner = (unsigned)b0 < (unsigned)p.d0 && (unsigned)b1 < (unsigned)p.d1 &&
+                                               (unsigned)b2 < (unsigned)p.d2;
+                            if (!inner || s_mask[el * p.row_stride + (b0 * p.d1 + b1) * p.d2 + b2] != 0)
+                                o[k * v.n_ch + v.n_map_ch] = (T)1;
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 if (first + k < n_pix) {
@@ -230,6 +259,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                     }
                 }
             }
+            }
         }
         __syncthreads();
         // ---- copy-out: 128-bit coalesced stores ---------------------------------------------------------------
@@ -270,10 +300,13 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
     v.planes_bytes = (v.GB * v.G * 2 * p.n_ctrl * (int)sizeof(T) + 15) / 16 * 16;
     const int dyn = v.stage_bytes + v.planes_bytes + v.GB * v.G * (p.row_stride * (p.static_mask ? 2 : 1) + 12);
     const bool d3 = p.ndim == 3, st = p.static_mask != nullptr, cr = p.crop != 0;
-    void (*kern)(const ObsParams, const ObsVec) =
-        cr ? (st ? (d3 ? k_observe_staged<T, true, true, true> : k_observe_staged<T, true, true, false>)
-                 : (d3 ? k_observe_staged<T, true, false, true> : k_observe_staged<T, true, false, false>))
-           : (d3 ? k_observe_staged<T, false, false, true> : k_observe_staged<T, false, false, false>);
+    const bool row4 = (d3 ? p.o2 : p.o1) % 4 == 0;
+#define OBS_PICK(R4)                                                                                                     \
+    (cr ? (st ? (d3 ? k_observe_staged<T, true, true, true, R4> : k_observe_staged<T, true, true, false, R4>)            \
+              : (d3 ? k_observe_staged<T, true, false, true, R4> : k_observe_staged<T, true, false, false, R4>))         \
+        : (d3 ? k_observe_staged<T, false, false, true, R4> : k_observe_staged<T, false, false, false, R4>))
+    void (*kern)(const ObsParams, const ObsVec) = row4 ? OBS_PICK(true) : OBS_PICK(false);
+#undef OBS_PICK
     cudaError_t e;
     if (dyn > 48 * 1024 &&
         (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)

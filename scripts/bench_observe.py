@@ -29,6 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=1 << 18)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--out", default="", help="also append the JSON lines to this file")
     a = ap.parse_args()
     peak = 6544.0
     try:
@@ -57,10 +58,14 @@ def main():
         ms = e0.elapsed_time(e1) / a.reps
         nbytes = out.numel() * out.element_size() + a.envs * (env.row_stride + 12)
         gbs = nbytes / ms / 1e6
-        print(json.dumps({"case": f"{problem}-{rep}-{'x'.join(map(str, shape))}", "dtype": str(dt).split('.')[-1],
+        line = json.dumps({"case": f"{problem}-{rep}-{'x'.join(map(str, shape))}", "dtype": str(dt).split('.')[-1],
                           "controls": bool(controls), "envs": a.envs, "obs_shape": list(env.obs_shape()),
                           "ms": round(ms, 4), "bytes": nbytes, "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 3),
-                          "env_obs_per_s": round(a.envs / ms * 1e3)}), flush=True)
+                          "env_obs_per_s": round(a.envs / ms * 1e3)})
+        print(line, flush=True)
+        if a.out:
+            with open(a.out, "a") as f:
+                f.write(line + "\n")
         del env, out
         torch.cuda.empty_cache()
 

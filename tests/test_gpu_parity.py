@@ -335,3 +335,43 @@ def test_action_patch_rollout_vs_oracle(problem, shape, aw):
             assert reward[e] == pytest.approx(r, rel=1e-6, abs=1e-7)
     assert env.changes.cpu().numpy().tolist() == [o.changes for o in oracles]
     env.check_status()
+
+
+@pytest.mark.parametrize("problem,rep,shape,obs,kw", [
+    ("binary", "narrow", (16, 16), (32, 32), {}),
+    ("binary", "turtle", (9, 13), (18, 26), {}),
+    ("binary", "wide", (16, 16), (16, 16), {"controls": ["regions", "path-length"]}),
+    ("binary", "narrow", (16, 16), (32, 32), {"controls": ["path-length"]}),
+    ("zelda", "turtle", (7, 11), (22, 22), {}),
+    ("zelda", "narrow", (7, 11), (22, 22), {"static_tile_wrapper": True, "static_prob": 0.5, "n_static_walls": 2}),
+    ("sokoban", "cellular", (5, 5), (5, 5), {}),
+    ("minecraft_3D_maze", "narrow", (14, 14, 14), (14, 14, 14), {}),
+    ("minecraft_3D_maze", "turtle", (6, 7, 8), (12, 14, 16), {}),
+])
+def test_staged_observation_writer_equals_pixel_writer(problem, rep, shape, obs, kw, monkeypatch):
+    """The shared-memory staged writer (128-bit stores) against the one-thread-per-pixel writer it replaced (which
+    the trace replays pinned on the reference's wrapped observations): every dtype, odd env counts (partly filled
+    groups / vector tails), controls, frozen-tile plane, 2D and 3D crops."""
+    for n in (1, 3, 67, 130):
+        env = _mk(problem, rep, shape, n, obs_window=obs, seed=n, **kw)
+        if kw.get("controls"):
+            env.sample_uniform_targets()
+        env.reset()
+        if rep in ("narrow", "turtle"):
+            for i, d in enumerate(shape):
+                env.pos[:, i] = torch.randint(0, d, (n,), device=env.device, dtype=torch.int32)
+        for dt in (torch.uint8, torch.float32, torch.float64):
+            if dt == torch.uint8 and kw.get("controls"):
+                continue
+            monkeypatch.delenv("PCGRL_OBSERVE_SCALAR", raising=False)
+            a = env.observe(dtype=dt).clone()
+            monkeypatch.setenv("PCGRL_OBSERVE_SCALAR", "1")
+            b = env.observe(dtype=dt)
+            monkeypatch.delenv("PCGRL_OBSERVE_SCALAR", raising=False)
+            assert torch.equal(a, b), (problem, rep, n, dt)
+            assert float(a.sum()) > 0
+            # an unaligned output pointer falls back to the pixel writer and still agrees
+            if dt == torch.uint8:
+                buf = torch.empty(a.numel() + 16, dtype=dt, device=env.device)
+                view = buf[1:1 + a.numel()].view(a.shape)
+                assert torch.equal(env.observe(out=view), a)
