@@ -13,6 +13,9 @@
 
 namespace pcgrl {
 
+#ifndef PCGRL_UF_HALVING
+#define PCGRL_UF_HALVING 1
+#endif
 constexpr int SEARCH_WARPS = 8;   // default warps per CTA (a problem may ask for more)
 constexpr int SEARCH_TILE = 64;   // envs per CTA iteration
 constexpr int SEARCH_SLOTS = 64;  // concurrent launches that can share the tile counters below
@@ -42,8 +45,23 @@ __device__ __forceinline__ int run_start(uint32_t a, int b) {
 __device__ inline void uf_union(volatile uint16_t* parent, int a, int b) {
     for (;;) {
         int pa, pb;
+#if PCGRL_UF_HALVING
+        // find with path halving: every visited node is re-pointed at its grandparent.  Racing lanes only ever
+        // replace a pointer by another ancestor of the same node, so the forest stays valid without locks.
+        while ((pa = parent[a]) != a) {
+            const int ga = parent[pa];
+            if (ga != pa) parent[a] = (uint16_t)ga;
+            a = ga;
+        }
+        while ((pb = parent[b]) != b) {
+            const int gb = parent[pb];
+            if (gb != pb) parent[b] = (uint16_t)gb;
+            b = gb;
+        }
+#else
         while ((pa = parent[a]) != a) a = pa;
         while ((pb = parent[b]) != b) b = pb;
+#endif
         if (a == b) return;
         if (a < b) {
             const int t = a;
