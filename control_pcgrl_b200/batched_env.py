@@ -416,21 +416,28 @@ class BatchedPcgrlEnv:
                                         self._stream()), "pcgrl_stats")
         return out
 
-    def obs_shape(self):
+    def obs_shape(self, onehot: bool = True):
         crop = self.representation in ("narrow", "turtle")
         dims = self.obs_window if crop else self.map_shape
-        ch = (self.n_tiles + 1 if crop else self.n_tiles) + 2 * len(self.ctrl_metrics)
+        ch = ((self.n_tiles + 1 if crop else self.n_tiles) if onehot else 1) + 2 * len(self.ctrl_metrics)
         ch += 1 if self.static_mask is not None else 0      # 'static_builds' plane (wrappers.py:451-453)
         return (*dims, ch)
 
-    def observe(self, out: torch.Tensor | None = None, dtype=torch.float32):
+    def observe(self, out: torch.Tensor | None = None, dtype=torch.float32, onehot: bool = True):
         """The wrapped observation of every env: [N, *obs_dims, channels] (channels last), exactly what
-        CroppedImagePCGRLWrapper / ActionMapImagePCGRLWrapper + ControlWrapper return per env."""
+        CroppedImagePCGRLWrapper / ActionMapImagePCGRLWrapper + ControlWrapper return per env.
+        onehot=False (uint8 only, no controls): the tile codes of the crop instead of their one-hot records --
+        Cropped's own output (wrappers.py:407-437: 0 = out of bounds, tile t -> t + 1), one channel, for policies
+        that embed the tile themselves."""
+        if not onehot:
+            if self.ctrl_metrics or (out is not None and out.dtype != torch.uint8):
+                raise ValueError("onehot=False is a uint8 observation without control planes")
+            dtype = torch.uint8
         if self.holey:
             # HoleyRepresentation.get_observation (envs/reps/wrappers.py:153-160) shows the bordered map with
             # pos + 1; not on the GPU yet -- fail loudly rather than return the un-bordered crop
             raise NotImplementedError("observations of holey problems are not implemented; use .maps / .holes")
-        shape = (self.n_envs, *self.obs_shape())
+        shape = (self.n_envs, *self.obs_shape(onehot))
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         if tuple(out.shape) != shape or not out.is_contiguous():
@@ -445,7 +452,7 @@ class BatchedPcgrlEnv:
         for i, k in enumerate(self.ctrl_metrics):
             oa.ctrl_idx[i] = self.stat_names.index(k)
             oa.ctrl_range[i] = float(self.param_ranges[k])
-        oa.out_kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}[out.dtype]
+        oa.out_kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}[out.dtype] if onehot else 3
         oa.out = out.data_ptr()
         oa.static_channel = 1 if self.static_mask is not None else 0
         _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")

@@ -17,6 +17,7 @@ namespace pcgrl {
 struct ObsParams {
     int32_t ndim, d0, d1, d2, row_stride, n_tiles, n_stats;
     int32_t crop, o0, o1, o2;
+    int32_t raw;                  // 1: write the tile code of each pixel (Cropped's output) instead of its one-hot record
     int32_t n_ctrl;
     int32_t ctrl_idx[PCGRL_MAX_STATS];
     double ctrl_range[PCGRL_MAX_STATS];
@@ -34,7 +35,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
     const int64_t pix_per_env = (int64_t)p.o0 * p.o1 * p.o2;
     const int64_t total = p.n_envs * pix_per_env;
-    const int n_map_ch = p.crop ? p.n_tiles + 1 : p.n_tiles;
+    const int n_map_ch = p.raw ? 1 : (p.crop ? p.n_tiles + 1 : p.n_tiles);
     const int n_ch = 2 * p.n_ctrl + n_map_ch + (p.static_mask ? 1 : 0);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t env = i / pix_per_env;
@@ -78,7 +79,11 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
             o[2 * c + 1] = (T)((double)p.stats[env * p.n_stats + k] / p.ctrl_range[c]);
         }
         o += 2 * p.n_ctrl;
-        for (int c = 0; c < n_map_ch; ++c) o[c] = (T)(c == hot ? 1 : 0);
+        if (p.raw) {
+            o[0] = (T)hot;
+        } else {
+            for (int c = 0; c < n_map_ch; ++c) o[c] = (T)(c == hot ? 1 : 0);
+        }
         if (p.static_mask) o[n_map_ch] = (T)frozen;
     }
 }
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                     const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
                     const int hot = inside ? rowp[sl + k] + (CROP ? 1 : 0) : 0;
                     for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
-                    o[k * v.n_ch + hot] = (T)1;
+                    o[k * v.n_ch + (p.raw ? 0 : hot)] = p.raw ? (T)hot : (T)1;
                     if (STATIC) {   // see k_observe: the bordered frozen-tile mask through the same crop
                         const int s0 = c0 + (int)q0, s1 = D3 ? c1 + (int)q1 : sl + k, s2 = D3 ? sl + k : 0;
                         const int b0 = s0 - 1, b1 = s1 - 1, b2 = D3 ? s2 - 1 : 0;
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                     // crop: channel 0 = out of bounds, tile t -> channel t + 1 (wrappers.py:420-437); else channel = tile
                     const int hot = inside ? grid[cell] + (CROP ? 1 : 0) : 0;
                     for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
-                    o[k * v.n_ch + hot] = (T)1;
+                    o[k * v.n_ch + (p.raw ? 0 : hot)] = p.raw ? (T)hot : (T)1;
                     if (STATIC) {   // see k_observe: the bordered frozen-tile mask through the same crop
                         const int b0 = s0 - 1, b1 = s1 - 1, b2 = D3 ? s2 - 1 : 0;
                         const bool in_bordered = b0 >= -1 && b0 <= p.d0 && b1 >= -1 && b1 <= p.d1 &&
@@ -279,7 +284,7 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
     done = false;
     if ((uintptr_t)p.out % 16) return cudaSuccess;
     const int64_t pix = (int64_t)p.o0 * p.o1 * p.o2;
-    const int n_map_ch = p.crop ? p.n_tiles + 1 : p.n_tiles;
+    const int n_map_ch = p.raw ? 1 : (p.crop ? p.n_tiles + 1 : p.n_tiles);
     const int n_ch = 2 * p.n_ctrl + n_map_ch + (p.static_mask ? 1 : 0);
     const int64_t E = pix * n_ch;
     ObsVec v;
@@ -334,6 +339,7 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     p.n_tiles = cfg.n_tiles;
     p.n_stats = cfg.n_stats;
     p.crop = a.crop;
+    p.raw = a.out_kind == 3;
     p.o0 = a.obs_dims[0];
     p.o1 = a.obs_dims[1];
     p.o2 = cfg.ndim == 3 ? a.obs_dims[2] : 1;
@@ -355,19 +361,19 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     }
     p.out = a.out;
     if (!a.crop && (p.o0 != p.d0 || p.o1 != p.d1 || p.o2 != p.d2)) return cudaErrorInvalidValue;
-    if (a.out_kind == 0 && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
+    if ((a.out_kind == 0 || a.out_kind == 3) && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
     const int64_t total = st.n_envs * (int64_t)p.o0 * p.o1 * p.o2;
     if (total == 0) return cudaSuccess;
     if (!getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
         bool done = false;
-        cudaError_t e = a.out_kind == 0 ? launch_vec<uint8_t>(p, s, done)
+        cudaError_t e = (a.out_kind == 0 || a.out_kind == 3) ? launch_vec<uint8_t>(p, s, done)
                       : a.out_kind == 1 ? launch_vec<float>(p, s, done)
                       : a.out_kind == 2 ? launch_vec<double>(p, s, done) : cudaErrorInvalidValue;
         if (e != cudaSuccess || done) return e;
     }
     const int64_t want = (total + 255) / 256;
     const unsigned blocks = (unsigned)(want < 148 * 32 ? want : 148 * 32);
-    if (a.out_kind == 0)
+    if (a.out_kind == 0 || a.out_kind == 3)
         k_observe<uint8_t><<<blocks, 256, 0, s>>>(p);
     else if (a.out_kind == 1)
         k_observe<float><<<blocks, 256, 0, s>>>(p);

@@ -179,7 +179,10 @@ int32_t pcgrl_stats_holey(const pcgrl_config* cfg, const int8_t* grids, const in
  *   crop == 0 : the whole map, C one-hot channels (wide / cellular stacks)
  *   n_ctrl controlled metrics prepend 2*n_ctrl constant planes (trg/range, value/range); ctrl_idx[i] is the
  *   stat index, ctrl_range[i] = |hi - lo| of cond_bounds.
- *   out_kind: 0 = uint8, 1 = float32, 2 = float64 (the reference's np.eye dtype).  Output layout [N, *obs_dims, channels] (channels last):
+ *   out_kind: 0 = uint8, 1 = float32, 2 = float64 (the reference's np.eye dtype), 3 = uint8 TILE CODES instead of
+ *   one-hot records (Cropped's own output, the input of OneHotEncoding: 0 = out of bounds, tile t -> t + 1 behind a
+ *   crop; for policies that embed the tile themselves -- a third of the bytes; no target planes).
+ *   Output layout [N, *obs_dims, channels] (channels last):
  *   [2*n_ctrl target planes | C+1 or C one-hot | static_builds]. */
 typedef struct pcgrl_obs_args {
     int32_t crop;

@@ -15,8 +15,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import control_pcgrl_b200 as P  # noqa: E402
 
-CASES = [  # (problem, rep, map_shape, obs_window, controls, out dtype)
+CASES = [  # (problem, rep, map_shape, obs_window, controls, out dtype; "codes" = uint8 tile codes, not one-hot)
     ("binary", "narrow", (16, 16), (32, 32), None, torch.uint8),
+    ("binary", "narrow", (16, 16), (32, 32), None, "codes"),
     ("binary", "narrow", (16, 16), (32, 32), None, torch.float32),
     ("binary", "wide", (16, 16), (16, 16), ["regions", "path-length"], torch.float32),
     ("zelda", "turtle", (7, 11), (22, 22), None, torch.uint8),
@@ -45,7 +46,12 @@ def main():
         if rep in ("narrow", "turtle"):   # spread the crop centres
             for i, d in enumerate(shape):
                 env.pos[:, i] = torch.randint(0, d, (a.envs,), device=env.device, dtype=torch.int32)
-        out = torch.empty((a.envs, *env.obs_shape()), dtype=dt, device=env.device)
+        onehot = dt != "codes"
+        dt = dt if onehot else torch.uint8
+        out = torch.empty((a.envs, *env.obs_shape(onehot)), dtype=dt, device=env.device)
+        obs_shape = list(env.obs_shape(onehot))
+        _observe = env.observe
+        env.observe = lambda out: _observe(out=out, onehot=onehot)
         for _ in range(3):
             env.observe(out=out)
         torch.cuda.synchronize()
@@ -58,8 +64,8 @@ def main():
         ms = e0.elapsed_time(e1) / a.reps
         nbytes = out.numel() * out.element_size() + a.envs * (env.row_stride + 12)
         gbs = nbytes / ms / 1e6
-        line = json.dumps({"case": f"{problem}-{rep}-{'x'.join(map(str, shape))}", "dtype": str(dt).split('.')[-1],
-                          "controls": bool(controls), "envs": a.envs, "obs_shape": list(env.obs_shape()),
+        line = json.dumps({"case": f"{problem}-{rep}-{'x'.join(map(str, shape))}", "dtype": str(dt).split('.')[-1] + ("" if onehot else " tile codes"),
+                          "controls": bool(controls), "envs": a.envs, "obs_shape": obs_shape,
                           "ms": round(ms, 4), "bytes": nbytes, "GB/s": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 3),
                           "env_obs_per_s": round(a.envs / ms * 1e3)})
         print(line, flush=True)

@@ -375,3 +375,25 @@ def test_staged_observation_writer_equals_pixel_writer(problem, rep, shape, obs,
                 buf = torch.empty(a.numel() + 16, dtype=dt, device=env.device)
                 view = buf[1:1 + a.numel()].view(a.shape)
                 assert torch.equal(env.observe(out=view), a)
+
+
+@pytest.mark.parametrize("problem,rep,shape,obs", [("binary", "narrow", (16, 16), (32, 32)),
+                                                   ("zelda", "turtle", (7, 11), (22, 22)),
+                                                   ("minecraft_3D_maze", "narrow", (6, 7, 8), (12, 14, 16)),
+                                                   ("binary", "wide", (16, 16), (16, 16))])
+def test_tile_code_observation_is_the_argmax_of_the_onehot(problem, rep, shape, obs, monkeypatch):
+    """observe(onehot=False) = Cropped's own output: the channel index of the one-hot record of every pixel."""
+    for n in (5, 64):
+        env = _mk(problem, rep, shape, n, obs_window=obs, seed=n, action_kind="wide_flat" if rep == "wide" else None)
+        env.reset()
+        if rep in ("narrow", "turtle"):
+            for i, d in enumerate(shape):
+                env.pos[:, i] = torch.randint(0, d, (n,), device=env.device, dtype=torch.int32)
+        onehot = env.observe(dtype=torch.uint8)
+        raw = env.observe(onehot=False)
+        assert raw.shape == (*onehot.shape[:-1], 1) and raw.dtype == torch.uint8
+        assert torch.equal(raw[..., 0].long(), onehot.argmax(dim=-1))
+        assert int(onehot.sum()) == raw[..., 0].numel()
+        monkeypatch.setenv("PCGRL_OBSERVE_SCALAR", "1")
+        assert torch.equal(env.observe(onehot=False), raw)
+        monkeypatch.delenv("PCGRL_OBSERVE_SCALAR", raising=False)
