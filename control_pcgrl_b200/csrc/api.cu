@@ -178,8 +178,12 @@ static int host_chunks(const pcgrl_config* cfg, int64_t n) {
         const int v = atoi(e);
         if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(1, n / 256));
     }
-    if (n < (1 << 16)) return 1;
-    return 4;   // measured on B200, 1 Mi envs binary-narrow: 1/2/4/8/16 chunks -> 1.16/1.45/1.64/1.54/1.22e9 env-steps/s
+    // measured on B200 (binary 16x16, e2e env-steps/s): 64 Ki envs 1 chunk best (2 / 4 chunks: 3.3 / 2.4e8); 256 Ki
+    // 1 / 2 / 4 chunks -> 8.5 / 9.1 / 7.1e8; 512 Ki -> 1.07 / 1.26 / 1.09e9; 1 Mi 2 / 4 / 8 -> 1.77 / 2.0 / 1.77e9.
+    // Every chunk costs ~18 us of queue operations, so small shards take fewer.
+    if (n < (1 << 17)) return 1;
+    if (n < (1 << 20)) return 2;
+    return 4;
 }
 }  // namespace pcgrl
 
