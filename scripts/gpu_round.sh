@@ -18,7 +18,7 @@ for f in sorted(glob.glob("gpurun_out/bench_*.json")):
     try:
         d = json.loads(open(f).read().strip().splitlines()[-1])
         print(f.split("bench_")[1][:-5], "value %.4g" % d["value"], "e2e %.4g" % d.get("e2e", {}).get("value", float("nan")),
-              "frac %.3f" % d.get("roofline", {}).get("frac", float("nan")), "cpu", d.get("cpu_baseline", {}).get("value"))
+              "frac %.3f" % d.get("roofline", {}).get("frac", float("nan")), "cpu", (d.get("cpu_baseline") or {}).get("value"))
     except Exception as e:
         print(f, "FAILED", e)
 PY
