@@ -115,7 +115,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t d, uint32_t magic,
 constexpr int OBS_MAX_CTA_ENVS = 64;   // GB * G
 constexpr int OBS_THREADS = 256;
 
-template <typename T, bool CROP, bool STATIC, bool D3, bool ROW4>
+template <typename T, bool CROP, bool STATIC, bool D3, int ROWN /* 0, or 4 / 8: pixels per thread, all in one image row */>
 __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams p, const ObsVec v) {
     extern __shared__ __align__(16) uint8_t obs_smem[];
     T* stage = (T*)obs_smem;                                         // [envs of the trip][pix][n_ch]
@@ -166,7 +166,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
         // ControlWrapper planes and the static_builds plane are the only other elements written.)  A thread takes
         // four consecutive pixels: the index math is paid once and the coordinates advance with carries.
         const int n_pix = n_here * v.pix;
-        for (int first = tid * 4; first < n_pix; first += OBS_THREADS * 4) {
+        constexpr int PPT = ROWN ? ROWN : 4;   // pixels per thread
+        for (int first = tid * PPT; first < n_pix; first += OBS_THREADS * PPT) {
             // coordinates of the first pixel: (env of the trip, q0, q1[, q2]); in 2D the image is (o0, o1)
             uint32_t r, q0, q1, q2 = 0;
             uint32_t el = fdiv((uint32_t)first, (uint32_t)v.pix, v.m_pix, r);
@@ -185,8 +186,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
             }
             T* o = stage + (size_t)first * v.n_ch + n_pl;
-            if constexpr (ROW4) {
-                // the last image axis is a multiple of 4 long: the four pixels share a row, so the row test and the
+            if constexpr (ROWN != 0) {
+                // the last image axis is a multiple of ROWN long: the pixels share a row, so the row test and the
                 // row pointer are computed once and nothing carries
                 bool row_ok = true;
                 if (CROP) row_ok = D3 ? ((unsigned)(c0 + (int)q0) < (unsigned)p.d0 && (unsigned)(c1 + (int)q1) < (unsigned)p.d1)
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 const int sl = D3 ? c2 + (int)q2 : c1 + (int)q1;
                 const int8_t* rowp = D3 ? grid + ((c0 + (int)q0) * p.d1 + (c1 + (int)q1)) * p.d2 : grid + (c0 + (int)q0) * p.d1;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < ROWN; ++k) {
                     const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
                     const int hot = inside ? rowp[sl + k] + (CROP ? 1 : 0) : 0;
                     for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
@@ -305,12 +306,15 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
     v.planes_bytes = (v.GB * v.G * 2 * p.n_ctrl * (int)sizeof(T) + 15) / 16 * 16;
     const int dyn = v.stage_bytes + v.planes_bytes + v.GB * v.G * (p.row_stride * (p.static_mask ? 2 : 1) + 12);
     const bool d3 = p.ndim == 3, st = p.static_mask != nullptr, cr = p.crop != 0;
-    const bool row4 = (d3 ? p.o2 : p.o1) % 4 == 0;
-#define OBS_PICK(R4)                                                                                                     \
-    (cr ? (st ? (d3 ? k_observe_staged<T, true, true, true, R4> : k_observe_staged<T, true, true, false, R4>)            \
-              : (d3 ? k_observe_staged<T, true, false, true, R4> : k_observe_staged<T, true, false, false, R4>))         \
-        : (d3 ? k_observe_staged<T, false, false, true, R4> : k_observe_staged<T, false, false, false, R4>))
-    void (*kern)(const ObsParams, const ObsVec) = row4 ? OBS_PICK(true) : OBS_PICK(false);
+    const int last_axis = d3 ? p.o2 : p.o1;
+    // 8 pixels per thread only for 1-byte elements: with 4-byte elements a thread's 8 records are 8 * n_ch words
+    // apart and the shared-memory stores conflict (f32 binary-narrow 4.05e8 -> 3.68e8 obs/s with 8, u8 8.8e8 -> 9.7e8)
+    const int rown = (sizeof(T) == 1 && last_axis % 8 == 0) ? 8 : (last_axis % 4 == 0 ? 4 : 0);
+#define OBS_PICK(RN)                                                                                                     \
+    (cr ? (st ? (d3 ? k_observe_staged<T, true, true, true, RN> : k_observe_staged<T, true, true, false, RN>)            \
+              : (d3 ? k_observe_staged<T, true, false, true, RN> : k_observe_staged<T, true, false, false, RN>))         \
+        : (d3 ? k_observe_staged<T, false, false, true, RN> : k_observe_staged<T, false, false, false, RN>))
+    void (*kern)(const ObsParams, const ObsVec) = rown == 8 ? OBS_PICK(8) : (rown == 4 ? OBS_PICK(4) : OBS_PICK(0));
 #undef OBS_PICK
     cudaError_t e;
     if (dyn > 48 * 1024 &&
