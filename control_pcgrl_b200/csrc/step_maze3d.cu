@@ -31,8 +31,11 @@
 namespace pcgrl {
 
 constexpr int MAZE_QCAP = 256;    // FIFO ring capacity (entries); measured maximum with push filtering: 50
-constexpr int MAZE_WARPS = 4;     // small CTAs, several per SM: finer-grained tile barriers
-constexpr int MAZE_CTAS_PER_SM = 8;
+#ifndef PCGRL_MAZE_WARPS
+#define PCGRL_MAZE_WARPS 6   // A/B on B200 (14^3, 65 536 envs): 4 / 6 / 8 / 16 warps per CTA -> 1.81 / 2.13 / 2.05 / 1.41e7 env-steps/s
+#endif
+constexpr int MAZE_WARPS = PCGRL_MAZE_WARPS;     // small CTAs, several per SM: finer-grained tile barriers
+constexpr int MAZE_CTAS_PER_SM = 32 / MAZE_WARPS;
 constexpr int MAZE_MAX_CTAS = 160 * MAZE_CTAS_PER_SM;   // sizes the global scratch (>= 148 SMs x 8 CTAs)
 constexpr int MAZE_NJ_SLICE = 16 * 16 * 16 * 2;         // bytes of nj per warp (maps up to 16^3)
 constexpr int MAZE_ORDER_SLICE = (16 / 2 + 1) * 16 * 16 * 2;   // bytes of the first-recording order list per warp
