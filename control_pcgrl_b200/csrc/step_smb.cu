@@ -24,6 +24,10 @@ namespace pcgrl {
 
 constexpr int SMB_POWER = 10000;                 // smb_prob.py:21 _solver_power
 constexpr int SMB_NODES = 4 * SMB_POWER + 8;
+#ifndef PCGRL_SMB_WARPS
+#define PCGRL_SMB_WARPS 8
+#endif
+constexpr int SMB_WARPS = PCGRL_SMB_WARPS;   // warps per CTA
 #ifndef PCGRL_SMB_CTAS_PER_SM
 #define PCGRL_SMB_CTAS_PER_SM 4   // A/B on B200 (116x16, 65 536 envs): 2 / 3 / 4 CTAs per SM -> 7.0 / 8.5 / 9.7e6 env-steps/s
 #endif
@@ -37,7 +41,7 @@ struct SmbScratch {
     static constexpr size_t total = (heap + 4 * (size_t)SMB_NODES + 255) / 256 * 256;
 };
 
-int64_t smb_scratch_bytes() { return (int64_t)SmbScratch::total * SMB_MAX_CTAS * SEARCH_WARPS; }
+int64_t smb_scratch_bytes() { return (int64_t)SmbScratch::total * SMB_MAX_CTAS * SMB_WARPS; }
 
 struct SmbLayout {
     int stage, solid, visited, total, visited_bytes;
@@ -322,11 +326,11 @@ cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported) {
     supported = p.ndim == 2 && p.d1 <= 122 && p.d0 >= 4 && p.d0 <= 240 && p.scratch != nullptr;
     if (!supported) return cudaSuccess;
     const SmbLayout L = smb_layout(p.d0, p.d1, p.row_stride);
-    if (L.total * SEARCH_WARPS > 200 * 1024) {
+    if (L.total * SMB_WARPS > 200 * 1024) {
         supported = false;
         return cudaSuccess;
     }
-    return launch_search<SmbProb>(p, s, L.total, SMB_MAX_CTAS_PER_SM, SMB_MAX_CTAS);
+    return launch_search<SmbProb, SMB_WARPS>(p, s, L.total, SMB_MAX_CTAS_PER_SM, SMB_MAX_CTAS);
 }
 
 }  // namespace pcgrl
