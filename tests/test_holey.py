@@ -180,3 +180,27 @@ def test_single_env_facade():
     grid[0, 0] = 1 - grid[0, 0]
     assert info["regions"] == O.binary_holey_stats(grid, [0, 3, 17, 9])["regions"]
     assert obs["pos"].tolist() == [1, 1]      # narrow: cell 0 is edited twice (narrow_rep.py:98-100)
+
+
+@pytest.mark.gpu
+def test_full_size_incremental_stats_equal_recomputed():
+    """65 536 envs, random holes: after a rollout the incrementally maintained stats equal get_stats recomputed from
+    scratch on the final maps (size-independent property), unchanged envs got exactly 0 reward, and a sample agrees
+    with the oracle."""
+    import torch
+    from oracle import pcgrl_oracle as O
+    n = 65536
+    env = _mk((16, 16), n, seed=8)
+    env.reset()
+    g = torch.Generator(device=env.device).manual_seed(1)
+    for _ in range(30):
+        a = torch.randint(0, 2, (n,), generator=g, device=env.device, dtype=torch.int32)
+        reward, _ = env.step(a)
+        unchanged = env.changed == 0
+        assert bool((reward[unchanged] == 0).all())
+    again = env.compute_stats(env.maps, holes=env.holes)
+    assert torch.equal(again, env.stats)
+    maps, holes, stats = env.maps.cpu().numpy(), env.holes.cpu().numpy(), env.stats.cpu().numpy()
+    for e in range(0, n, 4099):
+        assert stats[e].tolist() == O.stats_vector("binary_holey", O.binary_holey_stats(maps[e], holes[e]))
+    env.check_status()
