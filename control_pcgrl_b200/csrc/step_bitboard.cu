@@ -24,6 +24,12 @@ namespace pcgrl {
 #ifndef PCGRL_THREADS
 #define PCGRL_THREADS 128
 #endif
+#ifndef PCGRL_MIN_CTAS
+#define PCGRL_MIN_CTAS 1
+#endif
+#ifndef PCGRL_SKIP_CLAIM
+#define PCGRL_SKIP_CLAIM 0
+#endif
 #ifndef PCGRL_STATIC_ITEMS
 #define PCGRL_STATIC_ITEMS 0
 #endif
@@ -410,7 +416,7 @@ __device__ __forceinline__ void pack16(const uint4 v, uint32_t (&out)[Prob::P]) 
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <class Machine, int NW, bool TWO>
-__global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
+__global__ void __launch_bounds__(THREADS, PCGRL_MIN_CTAS) k_step_bitboard(const KParams p) {
     using Prob = typename Machine::Prob;
     constexpr int P = Prob::P;
     constexpr int K = Prob::K;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(THREADS) k_step_bitboard(const KParams p) {
 #define PCGRL_NEXT_ITEM(cur) ((cur) + THREADS)
         int item = tid;
 #else
-#define PCGRL_NEXT_ITEM(cur) atomicAdd(&s_next, 1)
+#define PCGRL_NEXT_ITEM(cur) ((PCGRL_SKIP_CLAIM && M <= THREADS) ? M : atomicAdd(&s_next, 1))
         int item = atomicAdd(&s_next, 1);
 #endif
         bool active = item < M;

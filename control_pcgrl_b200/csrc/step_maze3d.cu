@@ -31,6 +31,9 @@
 namespace pcgrl {
 
 constexpr int MAZE_QCAP = 256;    // FIFO ring capacity (entries); measured maximum with push filtering: 50
+#ifndef PCGRL_UF_RUNS32
+#define PCGRL_UF_RUNS32 0
+#endif
 #ifndef PCGRL_MAZE_WARPS
 #define PCGRL_MAZE_WARPS 6   // A/B on B200 (14^3, 65 536 envs): 4 / 6 / 8 / 16 warps per CTA -> 1.81 / 2.13 / 2.05 / 1.41e7 env-steps/s
 #endif
@@ -50,6 +53,9 @@ __host__ __device__ inline MazeLayout maze_layout(int Z, int Y, int X, int row_s
     const int cells = Z * Y * X;
     int bb = 2 * cells;
     if (bb < row_stride) bb = row_stride;      // the raw grid is staged here first
+#if PCGRL_UF_RUNS32
+    if (bb < Z * Y * 32) bb = Z * Y * 32;      // ... and the region count's 32-bit run parents live here last
+#endif
     bb = (bb + 15) / 16 * 16;
     L.best_bytes = bb;
     L.order_cap = (Z / 2 + 1) * Y * X;
@@ -286,7 +292,11 @@ struct Maze3DProb {
         }
 
         // ---- calc_num_regions (helper_3D.py:396-406): 6-neighbour AIR components by union-find over runs ---
+#if PCGRL_UF_RUNS32
+        const int regions = count_regions_runs32(c.row, Z, Y, X, (uint32_t*)c.best, lane);
+#else
         const int regions = count_regions_rows(c.row, Z, Y, X, c.best, lane);
+#endif
 
         if (lane == 0) {
             // jumps[far] of the last processed component: nj[] still holds that search's recordings (lane 0

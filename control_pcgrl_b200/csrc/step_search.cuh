@@ -111,6 +111,71 @@ __device__ inline int count_regions_rows(const uint16_t* row, int Z, int Y, int 
     return __reduce_add_sync(0xffffffffu, roots);
 }
 
+// The same labelling with 32-bit parents indexed by (row, k-th run of the row): rows are at most 16 cells wide, so a
+// row has at most 8 runs and `parent` needs Z*Y*8 words -- about the size of the per-cell u16 table for 14-wide
+// rows, but the hook is a native 32-bit atomicCAS instead of the 16-bit one CUDA emulates with a CAS loop on the
+// containing word.
+__device__ __forceinline__ int run_id(uint32_t a, int r, int bpos) {
+    const uint32_t starts = a & ~(a << 1);
+    return r * 8 + __popc(starts & ((2u << bpos) - 1u)) - 1;   // bpos lies in its run, at or above the run's start
+}
+__device__ inline void uf_union32(volatile uint32_t* parent, int a, int b) {
+    for (;;) {
+        int pa, pb;
+        while ((pa = (int)parent[a]) != a) {
+            const int ga = (int)parent[pa];
+            if (ga != pa) parent[a] = (uint32_t)ga;
+            a = ga;
+        }
+        while ((pb = (int)parent[b]) != b) {
+            const int gb = (int)parent[pb];
+            if (gb != pb) parent[b] = (uint32_t)gb;
+            b = gb;
+        }
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        if (atomicCAS((unsigned int*)parent + a, (unsigned int)a, (unsigned int)b) == (unsigned int)a) return;
+    }
+}
+__device__ inline int count_regions_runs32(const uint16_t* row, int Z, int Y, int X, uint32_t* parent, int lane) {
+    const int R = Z * Y;
+    const uint32_t magic_y = div_magic(Y);
+    for (int r = lane; r < R; r += 32) {
+        const uint32_t a = row[r];
+        const int n = __popc(a & ~(a << 1));
+        for (int k = 0; k < n; ++k) parent[r * 8 + k] = (uint32_t)(r * 8 + k);
+    }
+    __syncwarp();
+    for (int r = lane; r < R; r += 32) {
+        const int z = div_by(r, magic_y), y = r - z * Y;
+        const uint32_t a = row[r];
+        if (!a) continue;
+#pragma unroll
+        for (int dir = 0; dir < 2; ++dir) {
+            if (dir == 0 ? y == 0 : z == 0) continue;
+            const int rp = dir == 0 ? r - 1 : r - Y;
+            const uint32_t ap = row[rp];
+            const uint32_t t = a & ap;                          // vertically adjacent passable pairs
+            for (uint32_t s = t & ~(t << 1); s; s &= s - 1) {   // one union per stretch of such pairs
+                const int bpos = __ffs(s) - 1;
+                uf_union32(parent, run_id(a, r, bpos), run_id(ap, rp, bpos));
+            }
+        }
+    }
+    __syncwarp();
+    int roots = 0;
+    for (int r = lane; r < R; r += 32) {
+        const uint32_t a = row[r];
+        const int n = __popc(a & ~(a << 1));
+        for (int k = 0; k < n; ++k) roots += parent[r * 8 + k] == (uint32_t)(r * 8 + k);
+    }
+    return __reduce_add_sync(0xffffffffu, roots);
+}
+
 // Prob must provide:
 //   static constexpr int K;
 //   struct Ctx;                                         per-warp context (pointers into its workspaces)
