@@ -25,7 +25,10 @@ namespace pcgrl {
 #define PCGRL_THREADS 128
 #endif
 #ifndef PCGRL_MIN_CTAS
-#define PCGRL_MIN_CTAS 1
+#define PCGRL_MIN_CTAS 10  // boards of <= 8 words: 48 registers, 10 CTAs (40 warps) per SM; A/B 1 / 10 -> 2.88 / 2.95e9
+#endif
+#ifndef PCGRL_CARVEOUT
+#define PCGRL_CARVEOUT 0
 #endif
 #ifndef PCGRL_SKIP_CLAIM
 #define PCGRL_SKIP_CLAIM 0
@@ -416,7 +419,7 @@ __device__ __forceinline__ void pack16(const uint4 v, uint32_t (&out)[Prob::P]) 
 // the kernel
 // ------------------------------------------------------------------------------------------------
 template <class Machine, int NW, bool TWO>
-__global__ void __launch_bounds__(THREADS, PCGRL_MIN_CTAS) k_step_bitboard(const KParams p) {
+__global__ void __launch_bounds__(THREADS, NW <= 8 ? PCGRL_MIN_CTAS : 1) k_step_bitboard(const KParams p) {
     using Prob = typename Machine::Prob;
     constexpr int P = Prob::P;
     constexpr int K = Prob::K;
@@ -609,6 +612,13 @@ static cudaError_t launch(const KParams& p, cudaStream_t s) {
     constexpr int TILE = tile_for(Machine::Prob::P * NW);
     const int64_t ctas = (p.n_envs + TILE - 1) / TILE;
     if (ctas == 0) return cudaSuccess;
+#if PCGRL_CARVEOUT > 0
+    static bool carved = false;   // ask for enough shared memory per SM that PCGRL_MIN_CTAS CTAs fit
+    if (!carved) {
+        cudaFuncSetAttribute(k_step_bitboard<Machine, NW, TWO>, cudaFuncAttributePreferredSharedMemoryCarveout, PCGRL_CARVEOUT);
+        carved = true;
+    }
+#endif
     k_step_bitboard<Machine, NW, TWO><<<(unsigned)ctas, THREADS, 0, s>>>(p);
     return cudaGetLastError();
 }
