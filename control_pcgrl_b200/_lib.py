@@ -50,6 +50,7 @@ class ObsArgs(C.Structure):
         ("crop", C.c_int32), ("obs_dims", C.c_int32 * 3), ("n_ctrl", C.c_int32),
         ("ctrl_idx", C.c_int32 * MAX_STATS), ("ctrl_range", C.c_double * MAX_STATS),
         ("out_kind", C.c_int32), ("out", C.c_void_p), ("static_channel", C.c_int32),
+        ("holey_border_tile", C.c_int32),
     ]
 
 

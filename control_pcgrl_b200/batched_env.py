@@ -419,6 +419,8 @@ class BatchedPcgrlEnv:
     def obs_shape(self, onehot: bool = True):
         crop = self.representation in ("narrow", "turtle")
         dims = self.obs_window if crop else self.map_shape
+        if self.holey:      # HoleyRepresentation.get_observation_space (envs/reps/wrappers.py:162-174): map + 2
+            dims = tuple(d + 2 for d in dims)
         ch = ((self.n_tiles + 1 if crop else self.n_tiles) if onehot else 1) + 2 * len(self.ctrl_metrics)
         ch += 1 if self.static_mask is not None else 0      # 'static_builds' plane (wrappers.py:451-453)
         return (*dims, ch)
@@ -433,10 +435,6 @@ class BatchedPcgrlEnv:
             if self.ctrl_metrics or (out is not None and out.dtype != torch.uint8):
                 raise ValueError("onehot=False is a uint8 observation without control planes")
             dtype = torch.uint8
-        if self.holey:
-            # HoleyRepresentation.get_observation (envs/reps/wrappers.py:153-160) shows the bordered map with
-            # pos + 1; not on the GPU yet -- fail loudly rather than return the un-bordered crop
-            raise NotImplementedError("observations of holey problems are not implemented; use .maps / .holes")
         shape = (self.n_envs, *self.obs_shape(onehot))
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
@@ -446,6 +444,10 @@ class BatchedPcgrlEnv:
         oa = _lib.ObsArgs()
         oa.crop = 1 if crop else 0
         dims = self.obs_window if crop else self.map_shape
+        if self.holey:
+            # the bordered map with the holes, positions + 1 (HoleyRepresentation.get_observation, wrappers.py:153-160)
+            dims = tuple(d + 2 for d in dims)
+            oa.holey_border_tile = self.spec.tiles.index(self.spec.border_tile)
         for i in range(3):
             oa.obs_dims[i] = dims[i] if i < self.ndim else 1
         oa.n_ctrl = len(self.ctrl_metrics)

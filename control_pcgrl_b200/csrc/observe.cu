@@ -28,6 +28,8 @@ struct ObsParams {
     const int32_t* stats;
     const double* targets;
     const uint8_t* static_mask;   // NULL: no static_builds plane
+    const int32_t* holes;         // holey problems: [N,4] entrance / exit in bordered coordinates, else NULL
+    int32_t border_tile;
     void* out;
 };
 
@@ -45,7 +47,25 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
         const int q1 = r % p.o1;
         const int q0 = r / p.o1;
         int hot, frozen = 0;
-        if (p.crop) {
+        if (p.holes) {
+            // holey problems (2D): the observed map is the bordered map with the two holes dug as empty tiles, and
+            // the position is shifted by the border (HoleyRepresentation.get_observation, envs/reps/wrappers.py:153-160)
+            const int32_t* h = p.holes + env * 4;
+            int s0 = q0, s1 = q1;
+            if (p.crop) {
+                const int32_t* pos = p.pos + env * 3;
+                s0 = pos[0] + 1 + q0 - p.o0 / 2;
+                s1 = pos[1] + 1 + q1 - p.o1 / 2;
+            }
+            int v = -1;                                       // outside the bordered map: the crop's padding
+            if ((unsigned)s0 < (unsigned)(p.d0 + 2) && (unsigned)s1 < (unsigned)(p.d1 + 2)) {
+                if (s0 >= 1 && s0 <= p.d0 && s1 >= 1 && s1 <= p.d1)
+                    v = p.grids[env * p.row_stride + (s0 - 1) * p.d1 + (s1 - 1)];
+                else
+                    v = ((s0 == h[0] && s1 == h[1]) || (s0 == h[2] && s1 == h[3])) ? 0 : p.border_tile;
+            }
+            hot = p.crop ? v + 1 : v;
+        } else if (p.crop) {
             const int32_t* pos = p.pos + env * 3;
             const int s0 = pos[0] + q0 - p.o0 / 2, s1 = pos[1] + q1 - p.o1 / 2;
             const int s2 = (p.ndim == 3) ? pos[2] + q2 - p.o2 / 2 : 0;
@@ -358,17 +378,28 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     p.pos = st.pos;
     p.stats = st.stats;
     p.targets = st.targets;
+    p.holes = nullptr;
+    p.border_tile = 0;
+    const bool holey = cfg.problem == PCGRL_PROB_BINARY_HOLEY;
+    if (holey) {
+        if (!st.holes || cfg.ndim != 2 || a.static_channel) return cudaErrorInvalidValue;
+        if (a.holey_border_tile < 0 || a.holey_border_tile >= cfg.n_tiles) return cudaErrorInvalidValue;
+        p.holes = st.holes;
+        p.border_tile = a.holey_border_tile;
+    }
     p.static_mask = nullptr;
     if (a.static_channel) {
         if (!a.crop || !st.static_mask) return cudaErrorInvalidValue;
         p.static_mask = st.static_mask;
     }
     p.out = a.out;
-    if (!a.crop && (p.o0 != p.d0 || p.o1 != p.d1 || p.o2 != p.d2)) return cudaErrorInvalidValue;
+    const int grow = holey ? 2 : 0;   // without a crop the whole (bordered) map is observed
+    if (!a.crop && (p.o0 != p.d0 + grow || p.o1 != p.d1 + grow || p.o2 != p.d2)) return cudaErrorInvalidValue;
     if ((a.out_kind == 0 || a.out_kind == 3) && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
     const int64_t total = st.n_envs * (int64_t)p.o0 * p.o1 * p.o2;
     if (total == 0) return cudaSuccess;
-    if (!getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
+    // (holey observations take the pixel-per-thread writer: the staged kernel does not know the border frame yet)
+    if (!getenv("PCGRL_OBSERVE_SCALAR") && !holey) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
         bool done = false;
         cudaError_t e = (a.out_kind == 0 || a.out_kind == 3) ? launch_vec<uint8_t>(p, s, done)
                       : a.out_kind == 1 ? launch_vec<float>(p, s, done)

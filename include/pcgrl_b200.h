@@ -195,6 +195,11 @@ typedef struct pcgrl_obs_args {
     int32_t static_channel;   /* ABI 3, crop only: append the 'static_builds' plane after the one-hot channels
                                  (wrappers.py:451-453): the BORDERED frozen-tile mask cropped with the map's
                                  padding, i.e. sampled one cell up-left of the map channels (border = 1) */
+    int32_t holey_border_tile;/* ABI 4, holey problems only (else ignored): the observed map is the BORDERED map
+                                 (dims + 2: border cells show this tile, the two holes of pcgrl_state.holes the empty
+                                 tile 0) and positions are shifted by one, as HoleyRepresentation.get_observation
+                                 returns it (envs/reps/wrappers.py:153-160); obs_dims are then the window + 2 (crop) or
+                                 the map dims + 2 (no crop), :162-174 */
 } pcgrl_obs_args;
 int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgrl_obs_args* obs, void* stream);
 

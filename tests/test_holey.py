@@ -149,11 +149,39 @@ def test_random_and_fixed_holes_on_reset():
 
 
 @pytest.mark.gpu
-def test_holey_observation_fails_loudly():
-    env = _mk((16, 16), 4)
-    env.reset()
-    with pytest.raises(NotImplementedError):
-        env.observe()
+@pytest.mark.parametrize("rep,shape,window", [("narrow", (16, 16), (32, 32)), ("turtle", (9, 12), (18, 24)),
+                                              ("wide", (10, 10), (10, 10))])
+def test_holey_observation_matches_oracle(rep, shape, window):
+    """HoleyRepresentation.get_observation (envs/reps/wrappers.py:153-174): the bordered map with the two holes,
+    positions + 1, through the usual Cropped / OneHot stack whose window is then two cells larger."""
+    import torch
+    from oracle import pcgrl_oracle as O
+    import control_pcgrl_b200 as P
+    rng = np.random.default_rng(3)
+    n = 37
+    h, w = shape
+    border = O.holey_border_idxs(h, w)
+    grids = (rng.random((n, h, w)) < 0.5).astype(np.int8)
+    holes = np.array([np.concatenate([border[k] for k in rng.choice(len(border), 2, replace=False)]) for _ in range(n)],
+                     dtype=np.int32)
+    cfg = P.make_config("binary_holey", rep, map_shape=shape, obs_window=window)
+    env = P.BatchedPcgrlEnv(cfg, n, action_kind="wide_coords" if rep == "wide" else None)
+    pos = np.stack([rng.integers(0, h, n), rng.integers(0, w, n)], axis=1)
+    env.reset(grids=grids, holes=holes, pos=pos if rep == "turtle" else None)
+    if rep == "narrow":
+        env.pos[:, :2] = torch.from_numpy(pos).to(env.device, torch.int32)
+    obs = env.observe(dtype=torch.float64).cpu().numpy()
+    codes = env.observe(onehot=False).cpu().numpy()[..., 0]
+    ow = tuple(d + 2 for d in (window if rep != "wide" else shape))
+    assert obs.shape == (n, *ow, 3 if rep != "wide" else 2)
+    for e in range(n):
+        b = O.bordered_with_holes(grids[e], holes[e])
+        if rep == "wide":
+            want = O.full_onehot(b, 2)
+        else:
+            want = O.cropped_onehot(b, [int(pos[e, 0]) + 1, int(pos[e, 1]) + 1], ow, 2)
+        assert np.array_equal(obs[e], want), (rep, e)
+        assert np.array_equal(codes[e], want.argmax(-1)), (rep, e)
 
 
 @pytest.mark.gpu
