@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Device-time the RL-side loop: PcgrlVectorEnv.step (fused env step + auto-reset) + the observation of every env,
+every step, all on the GPU (what a policy that lives on the same device consumes).
+    python scripts/bench_rl_loop.py [--envs N] [--steps K] [--obs uint8|float32|codes]"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import control_pcgrl_b200 as P  # noqa: E402
+from control_pcgrl_b200.vector_env import PcgrlVectorEnv  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--envs", type=int, default=1 << 20)
+ap.add_argument("--steps", type=int, default=100)
+a = ap.parse_args()
+for obs in ("uint8", "float32"):
+    env = PcgrlVectorEnv(P.make_config("binary", "narrow"), a.envs, obs_dtype=getattr(torch, obs))
+    env.reset()
+    acts = torch.randint(0, 2, (a.steps + 5, a.envs), device=env.env.device, dtype=torch.int32)
+    for t in range(5):
+        env.step(acts[t])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(a.steps):
+        env.step(acts[5 + t])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    print(json.dumps({"loop": "PcgrlVectorEnv.step + observe, binary-narrow 16x16", "obs": obs, "envs": a.envs,
+                      "ms_per_step": round(ms, 4), "env_steps_per_s": round(a.envs / ms * 1e3)}), flush=True)
+    del env
+    torch.cuda.empty_cache()
