@@ -200,9 +200,10 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
             }
             const int8_t* grid = s_grid + el * p.row_stride;
             int c0 = 0, c1 = 0, c2 = 0;
+            const int hb = p.holes ? 1 : 0;   // holey: positions are shifted by the border (wrappers.py:158-159)
             if (CROP) {
-                c0 = s_pos[el * 3 + 0] - p.o0 / 2;
-                c1 = s_pos[el * 3 + 1] - p.o1 / 2;
+                c0 = s_pos[el * 3 + 0] + hb - p.o0 / 2;
+                c1 = s_pos[el * 3 + 1] + hb - p.o1 / 2;
                 if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
             }
             T* o = stage + (size_t)first * v.n_ch + n_pl;
@@ -245,7 +246,22 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                                  (!D3 || (unsigned)s2 < (unsigned)p.d2);
                     const int cell = D3 ? (s0 * p.d1 + s1) * p.d2 + s2 : s0 * p.d1 + s1;
                     // crop: channel 0 = out of bounds, tile t -> channel t + 1 (wrappers.py:420-437); else channel = tile
-                    const int hot = inside ? grid[cell] + (CROP ? 1 : 0) : 0;
+                    int hot;
+                    if (p.holes) {
+                        // holey (2D): (s0, s1) address the BORDERED map -- level inside, border tile around it, the
+                        // two holes empty (see k_observe)
+                        const int32_t* h = p.holes + (env0 + el) * 4;
+                        int val = -1;
+                        if ((unsigned)s0 < (unsigned)(p.d0 + 2) && (unsigned)s1 < (unsigned)(p.d1 + 2)) {
+                            if (s0 >= 1 && s0 <= p.d0 && s1 >= 1 && s1 <= p.d1)
+                                val = grid[(s0 - 1) * p.d1 + (s1 - 1)];
+                            else
+                                val = ((s0 == h[0] && s1 == h[1]) || (s0 == h[2] && s1 == h[3])) ? 0 : p.border_tile;
+                        }
+                        hot = CROP ? val + 1 : val;
+                    } else {
+                        hot = inside ? grid[cell] + (CROP ? 1 : 0) : 0;
+                    }
                     for (int c = 0; c < n_pl; ++c) o[k * v.n_ch - n_pl + c] = s_planes[el * n_pl + c];
                     o[k * v.n_ch + (p.raw ? 0 : hot)] = p.raw ? (T)hot : (T)1;
                     if (STATIC) {   // see k_observe: the bordered frozen-tile mask through the same crop
@@ -278,8 +294,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                         ++el;
                         grid += p.row_stride;
                         if (CROP && first + k + 1 < n_pix) {
-                            c0 = s_pos[el * 3 + 0] - p.o0 / 2;
-                            c1 = s_pos[el * 3 + 1] - p.o1 / 2;
+                            c0 = s_pos[el * 3 + 0] + hb - p.o0 / 2;
+                            c1 = s_pos[el * 3 + 1] + hb - p.o1 / 2;
                             if (D3) c2 = s_pos[el * 3 + 2] - p.o2 / 2;
                         }
                     }
@@ -329,7 +345,8 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
     const int last_axis = d3 ? p.o2 : p.o1;
     // 8 pixels per thread only for 1-byte elements: with 4-byte elements a thread's 8 records are 8 * n_ch words
     // apart and the shared-memory stores conflict (f32 binary-narrow 4.05e8 -> 3.68e8 obs/s with 8, u8 8.8e8 -> 9.7e8)
-    const int rown = (sizeof(T) == 1 && last_axis % 8 == 0) ? 8 : (last_axis % 4 == 0 ? 4 : 0);
+    const int rown = p.holes ? 0   // the border frame is only handled by the general path
+                   : (sizeof(T) == 1 && last_axis % 8 == 0) ? 8 : (last_axis % 4 == 0 ? 4 : 0);
 #define OBS_PICK(RN)                                                                                                     \
     (cr ? (st ? (d3 ? k_observe_staged<T, true, true, true, RN> : k_observe_staged<T, true, true, false, RN>)            \
               : (d3 ? k_observe_staged<T, true, false, true, RN> : k_observe_staged<T, true, false, false, RN>))         \
@@ -398,8 +415,7 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     if ((a.out_kind == 0 || a.out_kind == 3) && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
     const int64_t total = st.n_envs * (int64_t)p.o0 * p.o1 * p.o2;
     if (total == 0) return cudaSuccess;
-    // (holey observations take the pixel-per-thread writer: the staged kernel does not know the border frame yet)
-    if (!getenv("PCGRL_OBSERVE_SCALAR") && !holey) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
+    if (!getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
         bool done = false;
         cudaError_t e = (a.out_kind == 0 || a.out_kind == 3) ? launch_vec<uint8_t>(p, s, done)
                       : a.out_kind == 1 ? launch_vec<float>(p, s, done)
