@@ -323,6 +323,66 @@ def binary_holey_fixture():
     print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
 
 
+def maze3d_holey_fixture():
+    """minecraft_3D_holey_maze (oracle-only so far): sequences of get_stats calls on the reference's problem object
+    (built without its broken constructor, like binary_holey), because `path-length` reports the de-stacked path
+    of the PREVIOUS call.  Holes come from the reference's own gen_holes, cast to int64: its uint8 arrays make
+    `x + dir` raise under numpy 2 (numpy 1 promoted to a wider int)."""
+    R.install()
+    import sys as _sys
+    import types as _types
+    _sys.modules["ray"].get = lambda x: x
+    mr = _sys.modules["control_pcgrl.envs.probs.minecraft.mc_render"]
+    setattr(mr, "spawn_3D_doors", lambda *a, **k: None)
+    _sys.modules.setdefault("control_pcgrl.envs.probs.minecraft.minecraft_pb2",
+                            _types.SimpleNamespace(BEDROCK=0, WOODEN_SLAB=0, LEAVES=0, TORCH=0, PURPUR_SLAB=0, WOOL=0))
+    H = R.load_helpers()
+    from control_pcgrl.envs.probs.minecraft.minecraft_3D_holey_maze_prob import Minecraft3DholeymazeProblem
+    rng = np.random.default_rng(123)
+    arrays = {}
+    for gi, (size, trials, steps) in enumerate([(7, 60, 4), (10, 12, 3), (14, 5, 3)]):
+        p = object.__new__(Minecraft3DholeymazeProblem)
+        p._height = p._width = p._length = size
+        p._tile_types = ["AIR", "DIRT"]
+        p._hole_queue, p.fixed_holes = [], False
+        p._border_idxs = p.get_border_idxs()
+        maps, holes, stats = [], [], []
+        for trial in range(trials):
+            p.path_coords = []
+            np.random.seed(1000 * gi + trial)
+            if trial % 4 == 3:
+                p.fixed_holes = True
+            ent, ext = p.gen_holes()
+            p.fixed_holes = False
+            ent, ext = np.asarray(ent).astype(np.int64), np.asarray(ext).astype(np.int64)
+            p.entrance_coords, p.exit_coords = ent, ext
+            for step in range(steps):
+                g = (rng.random((size,) * 3) < [0.2, 0.35, 0.5][trial % 3]).astype(np.int8)
+                if trial % 5 == 0:
+                    g[:] = 1
+                    g[0:3] = 0            # an open hall on the floor
+                if trial % 5 == 1:
+                    g[:] = 1
+                    g[0:2] = 0
+                    g[2:5, :, ::3] = 0    # storeys reached by jumps / stairs
+                b = np.ones((size + 2,) * 3, dtype=np.int8)
+                b[1:-1, 1:-1, 1:-1] = g
+                for hh in (ent, ext):
+                    for c in hh:
+                        b[c[0], c[1], c[2]] = 0
+                st = p.get_stats(H.h3.get_string_map(b, ["AIR", "DIRT"]))
+                maps.append(b)
+                holes.append(np.stack([ent, ext]))
+                stats.append([int(st[k]) for k in ("regions", "path-length", "connected-path-length", "n_jump")])
+        arrays[f"maps_{gi}"] = np.stack(maps)
+        arrays[f"holes_{gi}"] = np.stack(holes).astype(np.int32)
+        arrays[f"stats_{gi}"] = np.array(stats, dtype=np.int64)
+        arrays[f"steps_{gi}"] = np.array(steps)
+    path = os.path.join(OUT, "stats_maze3d_holey.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
+
+
 # ------------------------------------------------------------------------------------------ traces
 def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None, n_envs=4, seed=0,
               max_board_scans=3, change_percentage=None, raw_only=False, n_steps=None, init_p=None,
@@ -518,6 +578,7 @@ def main(which=None):
                                                          n_envs=3, obs_every=17),
     })
     jobs["stats_binary_holey"] = binary_holey_fixture
+    jobs["stats_maze3d_holey"] = maze3d_holey_fixture
     for k, fn in jobs.items():
         if which and k not in which:
             continue

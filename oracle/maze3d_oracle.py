@@ -165,3 +165,95 @@ def maze3d_stats(grid, counters=None):
     air = np.asarray(grid) == 0
     length, nj = longest_path_3d(air, counters)
     return {"regions": count_regions_3d(air), "path-length": int(length), "n_jump": int(nj)}
+
+
+# --------------------------------------------------------------------------------------------
+# minecraft_3D_holey_maze -- oracle only so far; the CUDA path is round-2 work
+# --------------------------------------------------------------------------------------------
+def moves_with_traversed(a, x, y, z, Z, Y, X):
+    """helper_3D.py:214-319 _passable with the tiles each move passes through (they are appended to the path
+    before the foothold, helper_3D.py:484): walk [], step down [(nx,ny,z)], step up [(x,y,z+1)], jump level
+    [(nx,ny,z)], jump up [(nx,ny,z),(nx,ny,z+1)], jump down [(nx,ny,z),(nx,ny,z-1)]."""
+    out = []
+    for (nx, ny, nz, cost, j), (dx, dy) in _moves_dirs(a, x, y, z, Z, Y, X):
+        mx, my = x + dx, y + dy
+        if j == 0:
+            if cost == 1:
+                trav = []
+            elif nz == z - 1:
+                trav = [(mx, my, z)]
+            else:
+                trav = [(x, y, z + 1)]
+        elif nz == z:
+            trav = [(mx, my, z)]
+        elif nz == z + 1:
+            trav = [(mx, my, z), (mx, my, z + 1)]
+        else:
+            trav = [(mx, my, z), (mx, my, z - 1)]
+        out.append((nx, ny, nz, trav, j))
+    return out
+
+
+def _moves_dirs(a, x, y, z, Z, Y, X):
+    """moves() paired with the direction that produced each foothold (same branch order)."""
+    out = []
+    for d in DIRS:
+        saved = globals()["DIRS"]
+        try:
+            globals()["DIRS"] = (d,)
+            for m in moves(a, x, y, z, Z, Y, X):
+                out.append((m, d))
+        finally:
+            globals()["DIRS"] = saved
+    return out
+
+
+def search_paths(a, sx, sy, sz, Z, Y, X):
+    """helper_3D.py:422-490 run_dijkstra keeping the path lists: -> (order, paths, njump)."""
+    paths, njump, order = {}, {}, []
+    q = deque([(sx, sy, sz, [(sx, sy, sz)], 0)])
+    while q:
+        cx, cy, cz, path, nj = q.popleft()
+        c = (cx, cy, cz)
+        old = paths.get(c, [])
+        if 0 < len(old) <= len(path):                                  # :437-440
+            continue
+        if cz + 1 == Z or not a[cz + 1][cy][cx]:                       # :443-445
+            continue
+        if c not in paths:
+            order.append(c)
+        paths[c] = path
+        njump[c] = nj
+        for nx, ny, nz, trav, j in moves_with_traversed(a, cx, cy, cz, Z, Y, X):
+            q.append((nx, ny, nz, path + trav + [(nx, ny, nz)], nj + j))
+    return order, paths, njump
+
+
+def remove_stacked(path):
+    """helper_3D.py:657-675 remove_stacked_path_tiles: drop every tile that sits directly on top of another tile
+    of the path (the iteration runs over a snapshot, so a tile goes iff the one below it was in the ORIGINAL set)."""
+    s = set(tuple(e) for e in path)
+    return [c for c in s if (c[0], c[1], c[2] - 1) not in s]
+
+
+def maze3d_holey_stats(bordered, entrance, exit_, prev_path_len):
+    """probs/minecraft/minecraft_3D_holey_maze_prob.py:71-124 on the bordered map (holes already dug).
+    entrance / exit_: ((z, y, x) foot, (z, y, x) head).  Returns (stats, len(path_coords)) -- `path-length` is
+    len(self.path_coords) of the PREVIOUS call (:92-93 assign in the wrong order), so the caller carries the
+    second value to the next call (0 before the first)."""
+    air = np.asarray(bordered) == 0
+    Z, Y, X = air.shape
+    a = air.tolist()
+    ez, ey, ex = (int(v) for v in entrance[0])
+    order, paths, jumps = search_paths(a, ex, ey, ez, Z, Y, X)        # :81
+    xz, xy, xx = (int(v) for v in exit_[0])
+    xc = (xx, xy, xz)                                                 # :83
+    connected = len(paths[xc]) if xc in paths else -1                 # :84
+    n_jump = jumps[xc] if xc in jumps else 0                          # :89
+    best, bl = None, -1
+    for c in order:                                                   # :90-92 np.argmax over insertion order
+        if len(paths[c]) > bl:
+            best, bl = c, len(paths[c])
+    new_len = len(remove_stacked(paths[best]))                        # :94
+    return ({"regions": count_regions_3d(air), "path-length": int(prev_path_len),
+             "connected-path-length": int(connected), "n_jump": int(n_jump)}, new_len)

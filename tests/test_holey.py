@@ -239,3 +239,28 @@ def test_full_size_incremental_stats_equal_recomputed():
     for e in range(0, n, 4099):
         assert stats[e].tolist() == O.stats_vector("binary_holey", O.binary_holey_stats(maps[e], holes[e]))
     env.check_status()
+
+
+def test_maze3d_holey_oracle_matches_reference_get_stats():
+    """minecraft_3D_holey_maze (oracle only so far; the CUDA path is round-2 work): the restatement -- one search
+    from the entrance keeping the path lists, connected length / jumps at the exit, and `path-length` = the
+    de-stacked longest path of the PREVIOUS call -- against sequences of calls on the reference's problem object
+    (tests/golden/stats_maze3d_holey.npz, oracle/gen_golden.py)."""
+    from oracle import maze3d_oracle as M
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "stats_maze3d_holey.npz"))
+    total, connected, stale = 0, 0, 0
+    gi = 0
+    while f"maps_{gi}" in z:
+        maps, holes, stats, steps = z[f"maps_{gi}"], z[f"holes_{gi}"], z[f"stats_{gi}"], int(z[f"steps_{gi}"])
+        prev = 0
+        for i in range(len(maps)):
+            if i % steps == 0:
+                prev = 0                                   # a fresh problem object: path_coords = []
+            st, prev = M.maze3d_holey_stats(maps[i], holes[i][0], holes[i][1], prev)
+            got = [st[k] for k in ("regions", "path-length", "connected-path-length", "n_jump")]
+            assert got == stats[i].tolist(), (gi, i, got, stats[i])
+            total += 1
+            connected += stats[i][2] > 0
+            stale += stats[i][1] > 0
+        gi += 1
+    assert total >= 290 and connected >= 20 and stale >= 100
