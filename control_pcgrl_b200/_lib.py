@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-PCGRL_ABI_VERSION = 4
+PCGRL_ABI_VERSION = 5
 MAX_STATS = 16
 MAX_TILES = 16
 
@@ -33,6 +33,7 @@ class Config(C.Structure):
         ("init_probs", C.c_float * MAX_TILES), ("weights", C.c_double * MAX_STATS),
         ("act_window", C.c_int32 * 3), ("static_prob", C.c_float), ("n_static_walls", C.c_int32),
         ("wall_tile", C.c_int32), ("static_eval_mode", C.c_int32), ("hole_mode", C.c_int32),
+        ("action_elem_bytes", C.c_int32), ("record_stat_bytes", C.c_int32),
     ]
 
 
@@ -42,6 +43,7 @@ class State(C.Structure):
         ("n_step", C.c_void_p), ("iteration", C.c_void_p), ("changes", C.c_void_p), ("stats", C.c_void_p),
         ("targets", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("changed", C.c_void_p),
         ("status", C.c_void_p), ("scratch", C.c_void_p), ("static_mask", C.c_void_p), ("holes", C.c_void_p),
+        ("records", C.c_void_p),
     ]
 
 
@@ -70,6 +72,9 @@ SYMBOLS = {
     "pcgrl_observe": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.POINTER(ObsArgs), C.c_void_p]),
     "pcgrl_step_host": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.c_void_p, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pcgrl_step_host_packed": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_void_p]),
+    "pcgrl_record_stride": (C.c_int32, [C.POINTER(Config)]),
     "pcgrl_launch_count": (C.c_int64, []),
 }
 

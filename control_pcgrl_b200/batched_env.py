@@ -31,7 +31,7 @@ def _ptr(t):
 class BatchedPcgrlEnv:
     def __init__(self, cfg, n_envs: int, device="cuda:0", env_offset: int = 0, seed: int = 0,
                  action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True,
-                 reward_mode: str = "control"):
+                 reward_mode: str = "control", compact_host_io: bool = False):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.PcgrlError("control_pcgrl_b200 needs a CUDA device (there is no CPU fallback)")
@@ -127,6 +127,20 @@ class BatchedPcgrlEnv:
             raise ValueError(f"the reference defines no legacy get_reward for {self.problem}")
         self.reward_mode = reward_mode
         cc.reward_mode = _lib.REWARD_RANGE if reward_mode == "range" else _lib.REWARD_CONTROL
+        # compact host I/O (ABI 5): scalar actions in the narrowest unsigned type that holds the action space, and
+        # one packed result record per env (reward f32 | stats u8 / i16 / i32 | done | changed) so a host step is
+        # ONE device-to-host copy per pipeline chunk
+        self.compact_host_io = bool(compact_host_io)
+        self._act_elem = 4
+        self._rec_sb = 0
+        if self.compact_host_io:
+            if action_kind in ("int32", "wide_flat"):
+                n_act = {"narrow": self.n_tiles, "turtle": 4 + self.n_tiles}.get(
+                    rep, self.obs_window[0] * self.obs_window[1] * self.n_tiles)
+                self._act_elem = 1 if n_act <= 256 else 2 if n_act <= 65536 else 4
+            self._rec_sb = self._stat_bytes()
+        cc.action_elem_bytes = self._act_elem
+        cc.record_stat_bytes = self._rec_sb
         for i, pr in enumerate(self.spec.init_probs):
             cc.init_probs[i] = pr
         for k, name in enumerate(self.stat_names):
@@ -154,6 +168,8 @@ class BatchedPcgrlEnv:
             if self.static_tile_wrapper else None
         # (entrance_y, entrance_x, exit_y, exit_x) in bordered coordinates (holey_prob.py:41-42)
         self.holes = torch.zeros((N, 4), dtype=torch.int32, device=dev) if self.holey else None
+        self.record_stride = int(self.lib.pcgrl_record_stride(cc)) if self._rec_sb else 0
+        self.records = torch.zeros((N, self.record_stride), dtype=torch.uint8, device=dev) if self._rec_sb else None
         nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
         # zero-initialised once: the solver kernels keep generation counters for their hash tables in it
         self.scratch = torch.zeros(int(nscratch), dtype=torch.uint8, device=dev) if nscratch > 0 else None
@@ -172,7 +188,26 @@ class BatchedPcgrlEnv:
         st.changed, st.status, st.scratch = _ptr(self.changed), _ptr(self.status), _ptr(self.scratch)
         st.static_mask = _ptr(self.static_mask)
         st.holes = _ptr(self.holes)
+        st.records = _ptr(self.records)
         self._st = st
+
+    def _stat_bytes(self):
+        """Narrowest record type that holds every stat of this problem: the largest |bound| over cond_bounds, the
+        cell count (tile counts) and the solver defaults (sokoban dist-win = W*H*(W+H), sokoban_prob.py:170)."""
+        hi = self.cells * (sum(self.map_shape) if self.problem in ("sokoban", "smb") else 1)
+        for lo_, hi_ in self.cond_bounds.values():
+            hi = max(hi, abs(float(lo_)), abs(float(hi_)))
+        if self.problem in ("binary", "binary_holey", "minecraft_2D_maze") and hi <= 255:
+            return 1          # counts / lengths, never negative
+        return 2 if hi <= 32767 else 4
+
+    def record_dtype(self):
+        """numpy structured dtype of one packed result record (pcgrl_state.records)."""
+        st = {1: np.uint8, 2: np.int16, 4: np.int32}[self._rec_sb]
+        return np.dtype({"names": ["reward", "stats", "done", "changed"],
+                         "formats": [np.float32, (st, (self.K,)), np.uint8, np.uint8],
+                         "offsets": [0, 4, self.record_stride - 2, self.record_stride - 1],
+                         "itemsize": self.record_stride})
 
     # ------------------------------------------------------------------ targets
     def _target_rows(self, trgs):
@@ -192,29 +227,31 @@ class BatchedPcgrlEnv:
         self.targets[:] = rows.unsqueeze(0)
 
     def set_trgs(self, trgs: dict, env_ids=None):
-        """ControlWrapper.set_trgs/do_set_trgs (control_wrappers.py:167-172) for all envs or a subset.
-        Values may be scalars / (lo, hi) tuples, or per-env arrays of scalars.  Like the reference, new
-        targets take effect for the reward from the next reset (last_loss is re-based there)."""
-        scalar = {k: v for k, v in trgs.items() if np.ndim(v) == 0 or isinstance(v, tuple)}
-        if env_ids is None:
-            self.metric_trgs.update(scalar)
-        rows = torch.from_numpy(self._target_rows({**self.metric_trgs, **scalar})).to(self.device)
-        if env_ids is None:
-            self.targets[:] = rows.unsqueeze(0)
-        else:
-            if not self.ctrl_metrics:
-                raise ValueError("per-env targets need controls (cfg.controls) so targets are stored per env")
-            self.targets[env_ids] = rows.unsqueeze(0)
+        """ControlWrapper.do_set_trgs (control_wrappers.py:170-172) for all envs or a subset: the targets named in
+        `trgs` change IMMEDIATELY, i.e. the next step's reward is loss(new stats) - loss(old stats) under the new
+        targets; every other metric's target (static, sampled or set earlier, per env) is left alone.  The
+        reference's queueing set_trgs (applied at the next reset, :167-168, 174-178) lives in the single-env
+        ControlWrapper facade (envs.py), which calls this at reset time.
+        Values: scalars, (lo, hi) tuples (np.arange(lo, hi), hi excluded), or per-env arrays of scalars."""
+        idx = slice(None) if env_ids is None else env_ids
         for k, v in trgs.items():
-            if k in scalar:
-                continue
-            if not self.ctrl_metrics:
-                raise ValueError("per-env targets need controls (cfg.controls)")
+            if k not in self.stat_names:
+                raise KeyError(f"unknown metric {k!r} (stats: {self.stat_names})")
             col = self.stat_names.index(k)
-            vals = torch.as_tensor(np.asarray(v, dtype=np.float64), device=self.device)
-            idx = slice(None) if env_ids is None else env_ids
-            self.targets[idx, col, 0] = vals
-            self.targets[idx, col, 1] = float("nan")
+            scalar = isinstance(v, tuple) or np.ndim(v) == 0
+            if (not scalar or env_ids is not None) and not self.ctrl_metrics:
+                raise ValueError("per-env targets need controls (cfg.controls) so targets are stored per env")
+            if scalar and env_ids is None:
+                self.metric_trgs[k] = v
+            if isinstance(v, tuple):
+                self.targets[idx, col, 0] = float(v[0])
+                self.targets[idx, col, 1] = float(v[1])
+            else:
+                vals = float(v) if scalar else torch.as_tensor(np.asarray(v, dtype=np.float64), device=self.device)
+                self.targets[idx, col, 0] = vals
+                self.targets[idx, col, 1] = float("nan")
+
+    do_set_trgs = set_trgs
 
     def sample_uniform_targets(self, generator=None):
         """The intended UniformNoiseyTargets behaviour (control_wrappers.py:452-458, SURVEY A-25):
@@ -234,6 +271,10 @@ class BatchedPcgrlEnv:
 
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _on_device(self):
+        """The C ABI launches on the calling thread's CURRENT CUDA device: make that the env's device for the call."""
+        return torch.cuda.device(self.device)
 
     def _pack_grids(self, grids):
         g = torch.as_tensor(np.asarray(grids) if not torch.is_tensor(grids) else grids)
@@ -305,8 +346,9 @@ class BatchedPcgrlEnv:
         if mask is not None:
             m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         self._epoch += 1
-        _lib.check(self.lib.pcgrl_reset(cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
-                                        self._stream()), "pcgrl_reset")
+        with self._on_device():
+            _lib.check(self.lib.pcgrl_reset(cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
+                                            self._stream()), "pcgrl_reset")
         self._synced_steps = 0 if mask is None else None
         return self.stats
 
@@ -314,7 +356,8 @@ class BatchedPcgrlEnv:
         """One env-step for all N envs.  `actions` is a device tensor laid out per `action_kind`.
         Returns (reward[N] f32, done[N] u8) device tensors (overwritten by the next step)."""
         a = self._check_actions(actions)
-        _lib.check(self.lib.pcgrl_step(self._cc, self._st, a.data_ptr(), self._stream()), "pcgrl_step")
+        with self._on_device():
+            _lib.check(self.lib.pcgrl_step(self._cc, self._st, a.data_ptr(), self._stream()), "pcgrl_step")
         self._after_step()
         return self.reward, self.done
 
@@ -330,27 +373,29 @@ class BatchedPcgrlEnv:
         else:
             self.reset(mask=self.done)
 
+    def _action_layout(self):
+        """(shape, numpy dtype, torch dtype) of one action batch for this env's action_kind."""
+        N = self.n_envs
+        scalar = {4: (np.int32, torch.int32), 1: (np.uint8, torch.uint8), 2: (np.uint16, torch.uint16)}[self._act_elem]
+        return {"int32": ((N,), *scalar), "wide_flat": ((N,), *scalar),
+                "wide_coords": ((N, self.ndim + 1), np.int32, torch.int32),
+                "ca_tiles": ((N, self.row_stride), np.int8, torch.int8),
+                "ca_logits": ((N, self.n_tiles * self.cells), np.float32, torch.float32),
+                "patch": ((N, int(np.prod(self.act_window or (1,)))), np.int32, torch.int32)}[self.action_kind]
+
     def _check_actions(self, actions):
         if not torch.is_tensor(actions) or actions.device != self.device:
             raise TypeError("actions must be a tensor on the env's device (use step_host for host arrays)")
-        want = {"int32": ((self.n_envs,), torch.int32), "wide_flat": ((self.n_envs,), torch.int32),
-                "wide_coords": ((self.n_envs, self.ndim + 1), torch.int32),
-                "ca_tiles": ((self.n_envs, self.row_stride), torch.int8),
-                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), torch.float32),
-                "patch": ((self.n_envs, int(np.prod(self.act_window or (1,)))), torch.int32)}[self.action_kind]
-        if actions.dtype != want[1]:
-            raise TypeError(f"actions dtype {actions.dtype} != {want[1]} for action_kind {self.action_kind}")
-        a = actions.reshape(want[0]) if actions.numel() == int(np.prod(want[0])) else None
-        if a is None:
-            raise ValueError(f"actions shape {tuple(actions.shape)} does not match {want[0]}")
-        return a.contiguous()
+        shape, _, tdt = self._action_layout()
+        if actions.dtype != tdt:
+            raise TypeError(f"actions dtype {actions.dtype} != {tdt} for action_kind {self.action_kind}")
+        if actions.numel() != int(np.prod(shape)):
+            raise ValueError(f"actions shape {tuple(actions.shape)} does not match {shape}")
+        return actions.reshape(shape).contiguous()
 
     def action_shape_dtype(self):
-        return {"int32": ((self.n_envs,), np.int32), "wide_flat": ((self.n_envs,), np.int32),
-                "wide_coords": ((self.n_envs, self.ndim + 1), np.int32),
-                "ca_tiles": ((self.n_envs, self.row_stride), np.int8),
-                "ca_logits": ((self.n_envs, self.n_tiles * self.cells), np.float32),
-                "patch": ((self.n_envs, int(np.prod(self.act_window or (1,)))), np.int32)}[self.action_kind]
+        shape, dt, _ = self._action_layout()
+        return shape, dt
 
     def _pinned_buf(self, name, shape, dtype):
         b = self._pinned.get(name)
@@ -361,8 +406,7 @@ class BatchedPcgrlEnv:
 
     def host_action_buffer(self, name="actions"):
         """A pinned host tensor of the action layout; fill it and pass it to step_host to skip the staging copy."""
-        shape, dt = self.action_shape_dtype()
-        tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float32: torch.float32}[dt]
+        shape, _, tdt = self._action_layout()
         return torch.empty(shape, dtype=tdt, pin_memory=True) if name is None else self._pinned_buf(name, shape, tdt)
 
     def step_host(self, actions, want_stats=True):
@@ -371,25 +415,46 @@ class BatchedPcgrlEnv:
         Large binary / zelda shards are cut into chunks whose upload, kernel and download overlap on helper
         streams (pcgrl_step_host).  `actions`: numpy array (staged through a pinned buffer) or an already
         pinned torch tensor of the action layout (used in place).
-        Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats i32[N,K] or None)."""
-        shape, dt = self.action_shape_dtype()
-        tdt = {np.int32: torch.int32, np.int8: torch.int8, np.float32: torch.float32}[dt]
+        Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats [N,K] or None).  By default these
+        are three dense arrays (stats int32); with compact_host_io they are strided views of ONE packed record
+        array (stats uint8 / int16 as the problem's bounds allow, see record_dtype()), downloaded with a single
+        copy per pipeline chunk (pcgrl_step_host_packed)."""
+        shape, dt, tdt = self._action_layout()
         if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() and \
                 actions.dtype == tdt and actions.is_contiguous() and actions.numel() == int(np.prod(shape)):
             a_pin = actions
         else:
             a_pin = self._pinned_buf("actions", shape, tdt)
-            a_pin.numpy()[...] = np.asarray(actions, dtype=dt).reshape(shape)
+            a_pin.view(torch.uint8).numpy().view(dt).reshape(shape)[...] = np.asarray(actions).astype(dt, copy=False).reshape(shape)
         if self._actions_dev is None:
             self._actions_dev = torch.empty(shape, dtype=tdt, device=self.device)
+        if self.compact_host_io:
+            rec = self._pinned_buf("records", (self.n_envs, self.record_stride), torch.uint8)
+            with self._on_device():
+                _lib.check(self.lib.pcgrl_step_host_packed(self._cc, self._st, a_pin.data_ptr(),
+                                                           self._actions_dev.data_ptr(),
+                                                           a_pin.numel() * a_pin.element_size(), rec.data_ptr(),
+                                                           self._stream()), "pcgrl_step_host_packed")
+            self._after_step()
+            v = rec.numpy().view(self.record_dtype()).reshape(self.n_envs)
+            return v["reward"], v["done"], (v["stats"] if want_stats else None)
         r = self._pinned_buf("reward", (self.n_envs,), torch.float32)
         d = self._pinned_buf("done", (self.n_envs,), torch.uint8)
         s = self._pinned_buf("stats", (self.n_envs, self.K), torch.int32) if want_stats else None
-        _lib.check(self.lib.pcgrl_step_host(self._cc, self._st, a_pin.data_ptr(), self._actions_dev.data_ptr(),
-                                            a_pin.numel() * a_pin.element_size(), r.data_ptr(), d.data_ptr(),
-                                            _ptr(s), self._stream()), "pcgrl_step_host")
+        with self._on_device():
+            _lib.check(self.lib.pcgrl_step_host(self._cc, self._st, a_pin.data_ptr(), self._actions_dev.data_ptr(),
+                                                a_pin.numel() * a_pin.element_size(), r.data_ptr(), d.data_ptr(),
+                                                _ptr(s), self._stream()), "pcgrl_step_host")
         self._after_step()
         return r.numpy(), d.numpy(), (s.numpy() if s is not None else None)
+
+    def host_io_bytes(self, want_stats=True):
+        """(h2d, d2h) bytes one step_host call moves over PCIe, counted from the buffers it copies."""
+        shape, dt, _ = self._action_layout()
+        h2d = int(np.prod(shape)) * np.dtype(dt).itemsize
+        if self.compact_host_io:
+            return h2d, self.n_envs * self.record_stride
+        return h2d, self.n_envs * (4 + 1 + (4 * self.K if want_stats else 0))
 
     # ------------------------------------------------------------------ stats / observations
     def compute_stats(self, grids, holes=None) -> torch.Tensor:
@@ -409,11 +474,13 @@ class BatchedPcgrlEnv:
                 raise ValueError("a holey problem needs holes [n, 4] for compute_stats")
             hv = torch.as_tensor(np.asarray(holes) if not torch.is_tensor(holes) else holes)
             hv = hv.to(self.device, torch.int32).reshape(n, 4).contiguous()
-            _lib.check(self.lib.pcgrl_stats_holey(self._cc, g.data_ptr(), hv.data_ptr(), out.data_ptr(), n,
-                                                  _ptr(self.scratch), self._stream()), "pcgrl_stats_holey")
+            with self._on_device():
+                _lib.check(self.lib.pcgrl_stats_holey(self._cc, g.data_ptr(), hv.data_ptr(), out.data_ptr(), n,
+                                                      _ptr(self.scratch), self._stream()), "pcgrl_stats_holey")
             return out
-        _lib.check(self.lib.pcgrl_stats(self._cc, g.data_ptr(), out.data_ptr(), n, _ptr(self.scratch),
-                                        self._stream()), "pcgrl_stats")
+        with self._on_device():
+            _lib.check(self.lib.pcgrl_stats(self._cc, g.data_ptr(), out.data_ptr(), n, _ptr(self.scratch),
+                                            self._stream()), "pcgrl_stats")
         return out
 
     def obs_shape(self, onehot: bool = True):
@@ -457,15 +524,32 @@ class BatchedPcgrlEnv:
         oa.out_kind = {torch.uint8: 0, torch.float32: 1, torch.float64: 2}[out.dtype] if onehot else 3
         oa.out = out.data_ptr()
         oa.static_channel = 1 if self.static_mask is not None else 0
-        _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")
+        with self._on_device():
+            _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")
         return out
 
+    STATUS_BITS = (
+        (1, ValueError, "an action outside the action space reached pcgrl_step (ignored on device)"),
+        (2, IndexError, "minecraft_3D_maze: the reference raises IndexError on this map (helper_3D.py:531: a recorded "
+                        "x or y >= depth); the stats of that env are not meaningful"),
+        (4, RuntimeError, "a search workspace overflowed: the stats of at least one env are NOT the reference's "
+                          "(parity lost) -- report the map"),
+        (8, RuntimeError, "sokoban: a level with more than 15 crates met the solver preconditions; a packed solver "
+                          "state holds 15, so its dist-win / sol-length were not computed"),
+        (16, OverflowError, "a stat did not fit the packed result record (record_stat_bytes too small)"),
+    )
+
     def check_status(self):
-        """Raise if any action so far was out of range (device-side flag; one D2H sync)."""
+        """Raise the error that matches the device status word (include/pcgrl_b200.h, pcgrl_state.status); one D2H
+        sync.  Parity-relevant conditions (workspace overflow, crate limit) outrank a bad action."""
         s = int(self.status.item())
-        if s:
-            self.status.zero_()
-            raise ValueError("an action outside the action space reached pcgrl_step (ignored on device)")
+        if not s:
+            return
+        self.status.zero_()
+        for bit, exc, msg in sorted(self.STATUS_BITS, key=lambda b: b[0] not in (4, 8)):
+            if s & bit:
+                raise exc(f"{msg} [status word {s}]")
+        raise RuntimeError(f"unknown device status word {s}")
 
     def step_bytes(self) -> int:
         return int(self.lib.pcgrl_step_bytes(self._cc))
@@ -474,13 +558,28 @@ class BatchedPcgrlEnv:
         row = self.stats[i].tolist()
         return OrderedDict(zip(self.stat_names, row))
 
+    _STATE_TENSORS = ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes",
+                      "records")
+
     def state_dict(self):
-        """Everything needed to reconstruct the env state (checkpoint row)."""
-        return {k: getattr(self, k).clone() for k in
-                ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes")
-                if getattr(self, k) is not None}
+        """Everything needed to reconstruct the env state (checkpoint row), including the
+        position of the counter-based reset RNG stream (seed, epoch)."""
+        sd = {k: getattr(self, k).clone() for k in self._STATE_TENSORS if getattr(self, k) is not None}
+        sd["_epoch"] = int(self._epoch)
+        sd["seed"] = int(self.seed)
+        return sd
 
     def load_state_dict(self, sd):
-        for k, v in sd.items():
-            getattr(self, k).copy_(v)
+        want = {k for k in self._STATE_TENSORS if getattr(self, k) is not None}
+        have = {k for k in sd if k not in ("_epoch", "seed")}
+        if want != have:
+            raise KeyError(f"state_dict keys differ: missing {sorted(want - have)}, unexpected {sorted(have - want)}")
+        for k in want:
+            if tuple(sd[k].shape) != tuple(getattr(self, k).shape) or sd[k].dtype != getattr(self, k).dtype:
+                raise ValueError(f"state_dict[{k!r}]: shape / dtype {tuple(sd[k].shape)} {sd[k].dtype} != "
+                                 f"{tuple(getattr(self, k).shape)} {getattr(self, k).dtype}")
+        for k in want:
+            getattr(self, k).copy_(sd[k])
+        self._epoch = int(sd.get("_epoch", self._epoch))
+        self.seed = int(sd.get("seed", self.seed))
         self._synced_steps = None

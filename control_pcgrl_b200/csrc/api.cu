@@ -71,7 +71,22 @@ static int check(const pcgrl_config* c) {
         return fail(PCGRL_E_ARG, "wall_tile out of range");
     if (c->reward_mode != PCGRL_REWARD_CONTROL && c->reward_mode != PCGRL_REWARD_RANGE)
         return fail(PCGRL_E_ARG, "unknown reward_mode");
+    const int ab = c->action_elem_bytes;
+    if (ab != 0 && ab != 1 && ab != 2 && ab != 4) return fail(PCGRL_E_ARG, "action_elem_bytes must be 0, 1, 2 or 4");
+    if ((ab == 1 || ab == 2) && a != PCGRL_ACT_INT32 && a != PCGRL_ACT_WIDE_FLAT)
+        return fail(PCGRL_E_ARG, "narrow action elements only apply to scalar actions (PCGRL_ACT_INT32 / PCGRL_ACT_WIDE_FLAT)");
+    if (ab == 1 || ab == 2) {   // every legal action must be representable
+        const int64_t n_act = a == PCGRL_ACT_WIDE_FLAT ? (int64_t)c->act_h * c->act_w * c->n_tiles
+                            : r == PCGRL_REP_TURTLE ? 4 + c->n_tiles : c->n_tiles;
+        if (n_act > (ab == 1 ? 256 : 65536)) return fail(PCGRL_E_ARG, "action_elem_bytes too small for the action space");
+    }
+    const int sb = c->record_stat_bytes;
+    if (sb != 0 && sb != 1 && sb != 2 && sb != 4) return fail(PCGRL_E_ARG, "record_stat_bytes must be 0, 1, 2 or 4");
     return 0;
+}
+static int action_elem(const pcgrl_config* c) { return c->action_elem_bytes ? c->action_elem_bytes : 4; }
+static int record_stride(const pcgrl_config* c) {
+    return c->record_stat_bytes ? (4 + c->n_stats * c->record_stat_bytes + 2 + 3) / 4 * 4 : 0;
 }
 
 static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
@@ -102,6 +117,9 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
     p.wall_tile = c->wall_tile;
     p.static_eval_mode = c->static_eval_mode;
     p.hole_mode = c->hole_mode;
+    p.act_bytes = action_elem(c);
+    p.rec_sb = c->record_stat_bytes;
+    p.rec_stride = record_stride(c);
     double tot = 0;
     for (int t = 0; t < c->n_tiles; ++t) tot += c->init_probs[t] > 0 ? c->init_probs[t] : 0;
     double run = 0;
@@ -127,6 +145,7 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
         p.scratch = st->scratch;
         p.static_mask = st->static_mask;
         p.holes = st->holes;
+        p.records = p.rec_sb ? st->records : nullptr;
     }
 }
 
@@ -171,7 +190,8 @@ struct HostPipe {
 };
 static thread_local HostPipe g_pipe[16];
 
-static int host_chunks(const pcgrl_config* cfg, int64_t n) {
+static int host_chunks(const pcgrl_config* cfg, int64_t n, bool packed) {
+    (void)packed;
     if (cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA && cfg->problem != PCGRL_PROB_BINARY_HOLEY)
         return 1;
     if (const char* e = getenv("PCGRL_HOST_CHUNKS")) {
@@ -214,13 +234,18 @@ int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
 int64_t pcgrl_step_bytes(const pcgrl_config* c) {
     if (check(c)) return -1;
     const int64_t G = cells_of(c), K = c->n_stats;
-    int64_t A = 4;
+    int64_t A = action_elem(c);
     if (c->action_kind == PCGRL_ACT_WIDE_COORDS) A = 4 * (c->ndim + 1);
     if (c->action_kind == PCGRL_ACT_CA_TILES) A = G;
     if (c->action_kind == PCGRL_ACT_PATCH)
         A = 4 * (int64_t)c->act_window[0] * c->act_window[1] * (c->ndim == 3 ? c->act_window[2] : 1);
     if (c->action_kind == PCGRL_ACT_CA_LOGITS) A = 4 * (int64_t)c->n_tiles * G;
     return 2 * G + A + 8 * K + 5 + (c->targets_per_env ? 16 * K : 0);
+}
+
+int32_t pcgrl_record_stride(const pcgrl_config* cfg) {
+    if (check(cfg)) return -1;
+    return record_stride(cfg);
 }
 
 int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream) {
@@ -299,9 +324,11 @@ int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgr
     return 0;
 }
 
-int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host, void* actions_dev,
-                        int64_t action_bytes, float* reward_host, uint8_t* done_host, int32_t* stats_host,
-                        void* stream) {
+// Shared body of pcgrl_step_host / pcgrl_step_host_packed: with records_host the only download is the packed
+// record range of each chunk (one copy); otherwise reward / done / stats are copied separately.
+static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host, void* actions_dev,
+                              int64_t action_bytes, float* reward_host, uint8_t* done_host, int32_t* stats_host,
+                              uint8_t* records_host, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e;
     int r = check(cfg);
@@ -309,14 +336,19 @@ int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const vo
     if ((r = check_state(st))) return r;
     if (actions_host && (!actions_dev || action_bytes < 0)) return fail(PCGRL_E_ARG, "actions_dev / action_bytes");
     if (!actions_dev) return fail(PCGRL_E_ARG, "actions_dev is NULL");
+    const int64_t rs = record_stride(cfg);
+    if (records_host && (!st->records || rs == 0))
+        return fail(PCGRL_E_ARG, "packed host step needs cfg.record_stat_bytes and pcgrl_state.records");
     const int64_t n = st->n_envs;
     const int K = cfg->n_stats;
-    const int chunks = (n > 0 && (!actions_host || action_bytes % n == 0)) ? host_chunks(cfg, n) : 1;
+    const int chunks = (n > 0 && (!actions_host || action_bytes % n == 0)) ? host_chunks(cfg, n, records_host != nullptr) : 1;
     if (chunks <= 1) {
         if (actions_host &&
             (e = cudaMemcpyAsync(actions_dev, actions_host, (size_t)action_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess)
             return cuda_fail(e, "H2D actions");
         if ((r = pcgrl_step(cfg, st, actions_dev, stream))) return r;
+        if (records_host && (e = cudaMemcpyAsync(records_host, st->records, (size_t)(n * rs), cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+            return cuda_fail(e, "D2H records");
         if (reward_host && (e = cudaMemcpyAsync(reward_host, st->reward, n * sizeof(float), cudaMemcpyDeviceToHost, s)) != cudaSuccess)
             return cuda_fail(e, "D2H reward");
         if (done_host && (e = cudaMemcpyAsync(done_host, st->done, n, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
@@ -365,19 +397,22 @@ int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const vo
         sub.changed = st->changed ? st->changed + off : nullptr;
         sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
         sub.holes = st->holes ? st->holes + off * 4 : nullptr;
+        sub.records = st->records ? st->records + off * rs : nullptr;
         int64_t a_stride = a_env;
         if (!actions_host) {   // actions already on the device: per-env stride from the action layout
             a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)
                      : cfg->action_kind == PCGRL_ACT_PATCH
                          ? 4 * (int64_t)cfg->act_window[0] * cfg->act_window[1] * (cfg->ndim == 3 ? cfg->act_window[2] : 1)
                      : cfg->action_kind == PCGRL_ACT_CA_TILES ? cfg->row_stride
-                     : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : 4;
+                     : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : action_elem(cfg);
         }
         char* a_dev = (char*)actions_dev + off * a_stride;
         if (actions_host &&
             (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
             return cuda_fail(e, "H2D actions");
         if ((r = pcgrl_step(cfg, &sub, a_dev, cs))) return r;
+        if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+            return cuda_fail(e, "D2H records");
         if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
             return cuda_fail(e, "D2H reward");
         if (done_host && (e = cudaMemcpyAsync(done_host + off, sub.done, m, cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
@@ -392,6 +427,20 @@ int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const vo
     }
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(e, "stream sync");
     return 0;
+}
+
+int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host, void* actions_dev,
+                        int64_t action_bytes, float* reward_host, uint8_t* done_host, int32_t* stats_host,
+                        void* stream) {
+    return step_host_impl(cfg, st, actions_host, actions_dev, action_bytes, reward_host, done_host, stats_host, nullptr,
+                          stream);
+}
+
+int32_t pcgrl_step_host_packed(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host,
+                               void* actions_dev, int64_t action_bytes, void* records_host, void* stream) {
+    if (!records_host) return fail(PCGRL_E_ARG, "records_host is NULL");
+    return step_host_impl(cfg, st, actions_host, actions_dev, action_bytes, nullptr, nullptr, nullptr,
+                          (uint8_t*)records_host, stream);
 }
 
 }  // extern "C"

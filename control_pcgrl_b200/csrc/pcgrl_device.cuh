@@ -66,7 +66,58 @@ struct KParams {
     // holey problems: [N,4] (entrance_y, entrance_x, exit_y, exit_x) in bordered coordinates
     int32_t* holes;
     int32_t hole_mode;
+    // compact host I/O (ABI 5): narrow action elements, packed per-env result records
+    int32_t act_bytes;            // 4, 1 or 2: element size of PCGRL_ACT_INT32 / PCGRL_ACT_WIDE_FLAT actions
+    int32_t rec_stride, rec_sb;   // bytes per record / per stat in it (rec_sb == 0: no records)
+    uint8_t* records;             // [N, rec_stride] or NULL
 };
+
+// one scalar action (narrow / turtle / flat wide) in the width the caller chose (cfg.action_elem_bytes)
+__device__ __forceinline__ int load_action(const KParams& p, int64_t gid) {
+    if (p.act_bytes == 1) return ((const uint8_t*)p.actions)[gid];
+    if (p.act_bytes == 2) return ((const uint16_t*)p.actions)[gid];
+    return ((const int32_t*)p.actions)[gid];
+}
+
+// Packed result record of env gid (include/pcgrl_b200.h, pcgrl_state.records):
+//   [f32 reward][n_stats x rec_sb bytes][pad][u8 done][u8 changed]
+__device__ __forceinline__ void record_flags(const KParams& p, int64_t gid, int done, int changed) {
+    if (!p.records) return;
+    uint8_t* r = p.records + gid * p.rec_stride;
+    *(uint16_t*)(r + p.rec_stride - 2) = (uint16_t)((done ? 1 : 0) | (changed ? 0x100 : 0));
+}
+__device__ __forceinline__ void record_reward(const KParams& p, int64_t gid, float reward) {
+    if (!p.records) return;
+    *(float*)(p.records + gid * p.rec_stride) = reward;
+}
+template <int K>
+__device__ __forceinline__ void record_stats(const KParams& p, int64_t gid, const int32_t (&v)[K]) {
+    if (!p.records) return;
+    uint8_t* r = p.records + gid * p.rec_stride + 4;
+    bool fits = true;
+    if (p.rec_sb == 1) {
+        if (K == 2) {   // binary: both stats in one 16-bit store
+            *(uint16_t*)r = (uint16_t)((v[0] & 0xFF) | ((v[1] & 0xFF) << 8));
+            fits = ((unsigned)v[0] | (unsigned)v[1]) < 256u;
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                r[k] = (uint8_t)v[k];
+                fits = fits && (unsigned)v[k] < 256u;
+            }
+        }
+    } else if (p.rec_sb == 2) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            ((int16_t*)r)[k] = (int16_t)v[k];
+            fits = fits && v[k] == (int)(int16_t)v[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) ((int32_t*)r)[k] = v[k];
+    }
+    if (!fits && p.status) atomicOr(p.status, 16);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter-based: no RNG state lives in HBM.

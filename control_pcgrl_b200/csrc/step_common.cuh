@@ -63,7 +63,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
         p.n_step[gid] = ns + 1;
     } else if (p.rep == PCGRL_REP_NARROW) {
         // reps/narrow_rep.py:89-102: write at _pos, then _pos = coords[n_step % N], then n_step += 1
-        const int a = ((const int32_t*)p.actions)[gid];
+        const int a = load_action(p, gid);
         const int c = cell_index(p, pos[0], pos[1], pos[2]);
         if ((unsigned)a >= (unsigned)p.n_tiles) {
             if (p.status) atomicOr(p.status, 1);
@@ -81,7 +81,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
         p.n_step[gid] = ns + 1;
     } else if (p.rep == PCGRL_REP_TURTLE) {
         // reps/turtle_rep.py:87-107: 0..3 move along axis 0 / axis 1 (clamped), >= 4 writes tile a-4
-        const int a = ((const int32_t*)p.actions)[gid];
+        const int a = load_action(p, gid);
         if (a >= 0 && a < 4) {
             const int axis = a >> 1;
             const int lim = (axis == 0 ? p.d0 : p.d1) - 1;
@@ -101,7 +101,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
         int q0, q1, q2 = 0, v;
         if (p.action_kind == PCGRL_ACT_WIDE_FLAT) {
             // wrappers.py:304-323: (y, x, v) = unravel(a, (h, w, C)); env.step([x, y, v]) -> _map[x, y] = v
-            const int a = ((const int32_t*)p.actions)[gid];
+            const int a = load_action(p, gid);
             v = a % p.n_tiles;
             const int x = (a / p.n_tiles) % p.act_w;
             const int y = a / (p.n_tiles * p.act_w);
@@ -392,9 +392,13 @@ __device__ __forceinline__ void phase_a(const KParams& p, int64_t base, int tile
                 if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
                 p.done[gid] = done;
                 if (p.changed) p.changed[gid] = change != 0;
+                record_flags(p, gid, done, change);
                 need = (cw & 2) != 0;                  // :314 stats only when the map changed (an undone edit of a
                                                        // frozen tile leaves map, stats and loss as they were)
-                if (!need) p.reward[gid] = 0.f;
+                if (!need) {
+                    p.reward[gid] = 0.f;
+                    record_reward(p, gid, 0.f);
+                }
             } else if (p.mode == MODE_RESET) {
                 need = p.mask == nullptr || p.mask[gid] != 0;
                 if (need) reset_env(p, gid);
@@ -449,7 +453,9 @@ __device__ __forceinline__ void phase_d(const KParams& p, int64_t base, int tile
                                  ? range_reward_sum(nw, od, trg, p.weights, K)
                                  : control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
             p.reward[gid] = (float)r;
+            record_reward(p, gid, (float)r);
         }
+        record_stats<K>(p, gid, nw);
 #pragma unroll
         for (int k = 0; k < K; ++k) st[k] = nw[k];
     }

@@ -49,30 +49,34 @@ class PcgrlVectorEnv:
     def step(self, actions: torch.Tensor):
         """-> obs, reward, terminated(False), truncated(done), info; finished envs are reset in place and
         their `obs` row is the first observation of the new episode (gymnasium autoreset semantics);
-        info carries the final stats of finished episodes."""
+        info carries the final stats of finished episodes.  reward / done are the env's own output tensors: a
+        reset leaves them alone (include/pcgrl_b200.h, pcgrl_reset), so they need no copies."""
         b = self.env
         reward, done = b.step(actions)
         self.episode_return += reward.double()
         self.episode_length += 1
-        d = done.bool()
         info = {}
-        if self._any_done(d):
+        # lock-step episodes (no change budget, every env reset together): the episode end is known on the host
+        # without a device-to-host sync, and STAYS known afterwards because the reset below is a full one
+        lock_step = b.max_changes is None and b._synced_steps is not None
+        any_done = (b._synced_steps > b.max_iterations) if lock_step else bool(done.any())
+        if any_done:
+            d = done.bool()
             info = {"final_stats": b.stats.clone(), "final_return": self.episode_return.clone(),
-                    "final_length": self.episode_length.clone(), "_final": d.clone()}
-            rew, dn = reward.clone(), done.clone()
-            if self.uniform_targets:
-                keep = b.targets.clone()
-                b.sample_uniform_targets()
-                b.targets[~d] = keep[~d]
-            b.reset(mask=done)
-            self.episode_return[d] = 0
-            self.episode_length[d] = 0
-            reward, done = rew, dn
+                    "final_length": self.episode_length.clone(), "_final": d}
+            if lock_step:
+                if self.uniform_targets:
+                    b.sample_uniform_targets()
+                b.reset()
+                self.episode_return.zero_()
+                self.episode_length.zero_()
+            else:
+                if self.uniform_targets:
+                    keep = b.targets.clone()
+                    b.sample_uniform_targets()
+                    b.targets[~d] = keep[~d]
+                b.reset(mask=done)
+                self.episode_return[d] = 0
+                self.episode_length[d] = 0
         obs = b.observe(out=self._obs)
         return obs, reward, torch.zeros_like(done), done, info
-
-    def _any_done(self, d):
-        b = self.env
-        if b.max_changes is None and b._synced_steps is not None:
-            return b._synced_steps > b.max_iterations      # lock-step episodes: known without a sync
-        return bool(d.any())

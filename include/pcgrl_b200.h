@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PCGRL_ABI_VERSION 4
+#define PCGRL_ABI_VERSION 5
 
 /* problems: envs/probs/__init__.py:31-58 (the five BASELINE.json names) */
 enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGRL_PROB_SMB = 3,
@@ -101,6 +101,13 @@ typedef struct pcgrl_config {
     int32_t static_eval_mode; /* 1: use static_prob itself instead of U(0,1)*static_prob (set_eval_mode, :268) */
     /* -- holey problems, ABI 4 --------------------------------------------------------------------------- */
     int32_t hole_mode;        /* PCGRL_HOLES_*; only read by resets of a holey problem */
+    /* -- compact host I/O, ABI 5 ------------------------------------------------------------------------- */
+    int32_t action_elem_bytes;/* PCGRL_ACT_INT32 / PCGRL_ACT_WIDE_FLAT only: bytes per action element, 0 or 4 = int32
+                                 (the default), 1 = uint8, 2 = uint16 -- a Discrete(2) action is one byte over PCIe
+                                 instead of four */
+    int32_t record_stat_bytes;/* 0 = no packed result records; 1 = uint8, 2 = int16, 4 = int32 per stat in
+                                 pcgrl_state.records (the host picks the narrowest type the problem's stat bounds
+                                 fit; a value that does not fit sets status bit 4) */
 } pcgrl_config;
 
 /* Device-resident state of N envs + the per-step inputs/outputs.
@@ -125,7 +132,8 @@ typedef struct pcgrl_state {
     int32_t* status;       /* [1] device error word, may be NULL.  bit0 (1) an action was out of range;
                               bit1 (2) minecraft_3D_maze: the reference would raise IndexError on this map
                               (helper_3D.py:531, a recorded x or y >= depth); bit2 (4) a search workspace
-                              overflowed; bit3 (8) sokoban: more crates than a packed solver state holds (15) */
+                              overflowed; bit3 (8) sokoban: more crates than a packed solver state holds (15);
+                              bit4 (16) a stat did not fit cfg.record_stat_bytes in the packed record */
     void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0.  Must be zero-filled
                               once before its first use (it holds hash-table generation counters) and must not
                               be shared by launches that can run concurrently */
@@ -137,6 +145,14 @@ typedef struct pcgrl_state {
     int32_t* holes;        /* [N, 4] (ABI 4), holey problems only, else NULL: (entrance_y, entrance_x, exit_y, exit_x)
                               in BORDERED coordinates, i.e. the reference's entrance_coords / exit_coords
                               (holey_prob.py:41-42).  Read by step; written by reset per cfg.hole_mode */
+    uint8_t* records;      /* [N, pcgrl_record_stride(cfg)] (ABI 5) or NULL: one packed result record per env, what
+                              step() returns besides the observation (pcgrl_env.py:329-342: reward, done, info stats):
+                                offset 0            float32 reward
+                                offset 4            n_stats values of cfg.record_stat_bytes each (the env's CURRENT stats)
+                                offset stride - 2   uint8 done, uint8 changed
+                              written by step next to reward / done / stats (which stay the int32 view of the same
+                              values); resets refresh the stats part only.  One contiguous device range per env range,
+                              so a host step needs ONE device-to-host copy (pcgrl_step_host_packed) */
 } pcgrl_state;
 
 /* -- queries (host only, no CUDA calls) ------------------------------------------------------- */
@@ -147,6 +163,10 @@ int32_t     pcgrl_config_check(pcgrl_config* cfg);
 int64_t     pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs);
 /* Algorithmic HBM bytes one env-step moves (2G + A + 8K + 5 [+ 16K per-env targets]). */
 int64_t     pcgrl_step_bytes(const pcgrl_config* cfg);
+
+/* Bytes per env of pcgrl_state.records: 4 + n_stats * record_stat_bytes + 2 rounded up to a multiple of 4
+ * (0 when cfg.record_stat_bytes == 0). */
+int32_t     pcgrl_record_stride(const pcgrl_config* cfg);
 
 /* -- launches ---------------------------------------------------------------------------------- */
 /* One env-step for every env of the shard.  `actions` layout depends on cfg->action_kind. */
@@ -209,6 +229,12 @@ int32_t pcgrl_observe(const pcgrl_config* cfg, const pcgrl_state* st, const pcgr
 int32_t pcgrl_step_host(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host,
                         void* actions_dev, int64_t action_bytes, float* reward_host, uint8_t* done_host,
                         int32_t* stats_host, void* stream);
+
+/* Same with compact host I/O (ABI 5): the ONLY device-to-host traffic is pcgrl_state.records -> records_host
+ * ([N, pcgrl_record_stride] bytes, one copy per pipeline chunk instead of three); actions may use
+ * cfg.action_elem_bytes = 1 / 2.  st->records must be set. */
+int32_t pcgrl_step_host_packed(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions_host,
+                               void* actions_dev, int64_t action_bytes, void* records_host, void* stream);
 
 /* Counter of kernels this library has launched in this process (for bench.py's gpu_launches). */
 int64_t pcgrl_launch_count(void);

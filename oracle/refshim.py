@@ -1,6 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- loader that runs the *real* reference from /root/reference.
 
-This module is only usable in the build container (the GPU box has no /root/reference).
+The reference tree is /root/reference in the build container; on the GPU box (no /root/reference) it is the
+unmodified pip install under baseline/_ref that oracle/install_reference.sh makes, when present.
 It is used by oracle/gen_golden.py to produce the committed fixtures under tests/golden/
 and by the `needs_reference` tests that pin oracle/pcgrl_oracle.py against the reference.
 Nothing under control_pcgrl_b200/ may import it.
@@ -22,7 +23,21 @@ from types import SimpleNamespace
 
 import numpy as np
 
-REF_ROOT = os.environ.get("PCGRL_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    """First tree that holds the reference's env package: $PCGRL_REFERENCE_ROOT, the read-only mount of the build
+    container, or the unmodified copy oracle/install_reference.sh pip-installs into baseline/_ref (git-ignored, but
+    it travels to the GPU box with the repo snapshot, so the CPU arm there runs the reference's own code)."""
+    cands = [os.environ.get("PCGRL_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "control_pcgrl", "envs")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def available() -> bool:

@@ -15,7 +15,9 @@ from control_pcgrl_b200.vector_env import PcgrlVectorEnv  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=1 << 20)
-ap.add_argument("--steps", type=int, default=100)
+# default: two whole 770-step episodes, so the number includes the auto-resets (and would expose a per-step
+# device-to-host sync after the first episode boundary)
+ap.add_argument("--steps", type=int, default=1600)
 a = ap.parse_args()
 for obs in ("uint8", "float32"):
     env = PcgrlVectorEnv(P.make_config("binary", "narrow"), a.envs, obs_dtype=getattr(torch, obs))
@@ -31,7 +33,9 @@ for obs in ("uint8", "float32"):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    assert env.env._synced_steps is not None, "lost the sync-free episode-end detection"
     print(json.dumps({"loop": "PcgrlVectorEnv.step + observe, binary-narrow 16x16", "obs": obs, "envs": a.envs,
+                      "steps": a.steps, "episode_steps": int(env.env.max_iterations) + 1,
                       "ms_per_step": round(ms, 4), "env_steps_per_s": round(a.envs / ms * 1e3)}), flush=True)
     del env
     torch.cuda.empty_cache()

@@ -70,6 +70,24 @@ def test_host_queries_and_argument_errors():
     z = _cfg("zelda", "turtle", (7, 11), 8, 7)
     assert lib.pcgrl_config_check(z) == 0 and z.row_stride == 80
     assert lib.pcgrl_step_bytes(z) == 2 * 77 + 4 + 56 + 5              # 219 B
+    # ABI 5: narrow action elements and packed result records
+    assert lib.pcgrl_record_stride(c) == 0
+    c8 = _cfg()
+    c8.action_elem_bytes, c8.record_stat_bytes = 1, 1
+    assert lib.pcgrl_config_check(c8) == 0
+    assert lib.pcgrl_record_stride(c8) == 8                            # f32 reward | 2 x u8 stats | done | changed
+    assert lib.pcgrl_step_bytes(c8) == 2 * 256 + 1 + 8 * 2 + 5
+    z.record_stat_bytes = 2
+    assert lib.pcgrl_record_stride(z) == 20                            # 4 + 7 * 2 + 2
+    bad = _cfg("zelda", "turtle", (7, 11), 8, 7)
+    bad.action_kind, bad.representation, bad.act_h, bad.act_w = _lib.ACT_WIDE_FLAT, _lib.REP_IDS["wide"], 7, 11
+    bad.action_elem_bytes = 1                                          # 7 * 11 * 8 = 616 actions do not fit a byte
+    assert lib.pcgrl_config_check(bad) == _lib_err("PCGRL_E_ARG")
+    bad.action_elem_bytes = 2
+    assert lib.pcgrl_config_check(bad) == 0
+    bad = _cfg()
+    bad.record_stat_bytes = 3
+    assert lib.pcgrl_config_check(bad) == _lib_err("PCGRL_E_ARG")
     bad = _cfg()
     bad.n_stats = 5
     assert lib.pcgrl_config_check(bad) == _lib_err("PCGRL_E_ARG")

@@ -257,6 +257,104 @@ def test_pipelined_host_step_equals_device_step(problem, rep, shape, controls, m
     a.check_status()
 
 
+@pytest.mark.parametrize("problem,rep,shape,controls", [("binary", "narrow", (16, 16), None),
+                                                        ("binary", "wide", (16, 16), ["regions", "path-length"]),
+                                                        ("zelda", "turtle", (7, 11), None),
+                                                        ("sokoban", "narrow", (5, 5), None)])
+def test_compact_host_io_equals_int32_outputs(problem, rep, shape, controls, monkeypatch):
+    """ABI 5 compact host I/O: uint8 / uint16 actions in, ONE packed record array out (reward f32 | stats u8 or i16
+    | done | changed).  Every field must equal the int32 ABI's outputs on the same env, for every chunking."""
+    n = 33_333 if problem != "sokoban" else 4_099
+    kw = dict(obs_window=shape) if rep == "wide" else {}
+    import control_pcgrl_b200 as P
+    cfg = P.make_config(problem, rep, map_shape=shape, controls=controls, max_board_scans=0.1, **kw)
+    a = P.BatchedPcgrlEnv(cfg, n, seed=7, auto_reset=True, compact_host_io=True)
+    b = P.BatchedPcgrlEnv(cfg, n, seed=7, auto_reset=True)
+    want_act = {"narrow": np.uint8, "turtle": np.uint8, "wide": np.uint16}[rep]
+    assert a.action_shape_dtype()[1] == want_act and b.action_shape_dtype()[1] == np.int32
+    want_sb = {"binary": 1, "zelda": 2, "sokoban": 2}[problem]
+    assert a.record_dtype()["stats"].base.itemsize == want_sb
+    assert a.record_stride == (4 + a.K * want_sb + 2 + 3) // 4 * 4
+    if controls:
+        g = torch.Generator(device=a.device).manual_seed(1)
+        a.sample_uniform_targets(generator=g)
+        b.targets.copy_(a.targets)
+    a.reset()
+    b.reset()
+    # resets refresh the stats part of the records
+    rec0 = a.records.cpu().numpy().view(a.record_dtype()).reshape(n)
+    np.testing.assert_array_equal(rec0["stats"].astype(np.int32), b.stats.cpu().numpy())
+    n_act = {"narrow": a.n_tiles, "turtle": 4 + a.n_tiles, "wide": shape[0] * shape[1] * a.n_tiles}[rep]
+    rng = np.random.default_rng(0)
+    h2d, d2h = a.host_io_bytes()
+    assert h2d == n * np.dtype(want_act).itemsize and d2h == n * a.record_stride
+    for t, chunks in enumerate(["1", "3", "", "8"] * 4):
+        if chunks:
+            monkeypatch.setenv("PCGRL_HOST_CHUNKS", chunks)
+        else:
+            monkeypatch.delenv("PCGRL_HOST_CHUNKS", raising=False)
+        act = rng.integers(0, n_act, size=n)
+        r, d, s = a.step_host(act.astype(want_act))
+        changed_a = a._pinned["records"].numpy().view(a.record_dtype()).reshape(n)["changed"].copy()
+        r, d, s = r.copy(), d.copy(), s.copy()
+        rb, db, sb = b.step_host(act.astype(np.int32))
+        np.testing.assert_array_equal(r, rb)
+        np.testing.assert_array_equal(d, db)
+        # b's int32 stats are copied after its auto-reset ran inside step_host? no: step_host downloads before the
+        # auto-reset launches, like the packed path
+        np.testing.assert_array_equal(s.astype(np.int32), sb)
+        np.testing.assert_array_equal(changed_a, b.changed.cpu().numpy()) if not d.any() else None
+        assert torch.equal(a.grids, b.grids) and torch.equal(a.stats, b.stats)
+        # the device-side int32 views stay valid next to the records
+        assert torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
+    a.check_status()
+    b.check_status()
+    # a device-resident step also keeps the records current (pcgrl_step writes them)
+    act = torch.from_numpy(rng.integers(0, n_act, size=n).astype(np.int32))
+    shape_a, _, tdt = a._action_layout()
+    ra, da = a.step(act.to(tdt).to(a.device))
+    rb, db = b.step(act.to(b.device))
+    rec = a.records.cpu().numpy().view(a.record_dtype()).reshape(n)
+    live = ~db.cpu().numpy().astype(bool)          # finished envs were auto-reset: their stats moved on
+    np.testing.assert_array_equal(rec["reward"], rb.cpu().numpy())
+    np.testing.assert_array_equal(rec["done"], db.cpu().numpy())
+    np.testing.assert_array_equal(rec["stats"].astype(np.int32)[live], b.stats.cpu().numpy()[live])
+
+
+def test_env_on_non_current_device_and_status_bits():
+    """The C ABI launches on the thread's current device: BatchedPcgrlEnv must switch to its own device for every
+    call, and check_status must name the condition behind each status bit."""
+    import control_pcgrl_b200 as P
+    env = P.BatchedPcgrlEnv(P.make_config("binary", "narrow"), 256, device="cuda:0")
+    env.reset()
+    for bit, exc in ((1, ValueError), (2, IndexError), (4, RuntimeError), (8, RuntimeError), (16, OverflowError)):
+        env.status.fill_(bit)
+        with pytest.raises(exc):
+            env.check_status()
+        assert int(env.status.item()) == 0
+    env.status.fill_(1 | 4)
+    with pytest.raises(RuntimeError, match="workspace"):
+        env.check_status()
+    bad = torch.full((256,), 7, dtype=torch.int32, device=env.device)
+    env.step(bad)
+    with pytest.raises(ValueError, match="action"):
+        env.check_status()
+    if torch.cuda.device_count() < 2:
+        return
+    torch.cuda.set_device(0)
+    e1 = P.BatchedPcgrlEnv(P.make_config("binary", "narrow"), 4096, device="cuda:1", seed=3)
+    e0 = P.BatchedPcgrlEnv(P.make_config("binary", "narrow"), 4096, device="cuda:0", seed=3)
+    e1.reset()
+    e0.reset()
+    act = torch.randint(0, 2, (4096,), dtype=torch.int32)
+    for _ in range(5):
+        r1, _ = e1.step(act.to("cuda:1"))
+        r0, _ = e0.step(act.to("cuda:0"))
+    assert torch.equal(e1.grids.cpu(), e0.grids.cpu()) and torch.equal(e1.stats.cpu(), e0.stats.cpu())
+    assert torch.equal(r1.cpu(), r0.cpu())
+    assert torch.equal(e1.observe(dtype=torch.uint8).cpu(), e0.observe(dtype=torch.uint8).cpu())
+
+
 def test_static_tiles_random_reset_and_frozen_cells():
     """StaticTileRepresentation (envs/reps/wrappers.py:234-376) at scale: the random-reset generator
     (static_prob / n_static_walls) and the invariant that a frozen cell never changes while its attempted
