@@ -43,7 +43,7 @@ class State(C.Structure):
         ("n_step", C.c_void_p), ("iteration", C.c_void_p), ("changes", C.c_void_p), ("stats", C.c_void_p),
         ("targets", C.c_void_p), ("reward", C.c_void_p), ("done", C.c_void_p), ("changed", C.c_void_p),
         ("status", C.c_void_p), ("scratch", C.c_void_p), ("static_mask", C.c_void_p), ("holes", C.c_void_p),
-        ("records", C.c_void_p),
+        ("records", C.c_void_p), ("worklist", C.c_void_p), ("cache", C.c_void_p),
     ]
 
 
@@ -75,6 +75,8 @@ SYMBOLS = {
     "pcgrl_step_host_packed": (C.c_int32, [C.POINTER(Config), C.POINTER(State), C.c_void_p, C.c_void_p, C.c_int64,
                                            C.c_void_p, C.c_void_p]),
     "pcgrl_record_stride": (C.c_int32, [C.POINTER(Config)]),
+    "pcgrl_worklist_ints": (C.c_int64, [C.POINTER(Config), C.c_int64]),
+    "pcgrl_cache_stride": (C.c_int32, [C.POINTER(Config)]),
     "pcgrl_launch_count": (C.c_int64, []),
 }
 

@@ -13,8 +13,10 @@ provider.  No CPU path exists: constructing this class without CUDA raises.
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from collections import OrderedDict
+from types import SimpleNamespace
 
 import numpy as np
 import torch
@@ -28,10 +30,13 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+_NULL_CTX = contextlib.nullcontext()
+
+
 class BatchedPcgrlEnv:
     def __init__(self, cfg, n_envs: int, device="cuda:0", env_offset: int = 0, seed: int = 0,
                  action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True,
-                 reward_mode: str = "control", compact_host_io: bool = False):
+                 reward_mode: str = "control", compact_host_io: bool = False, split_step: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.PcgrlError("control_pcgrl_b200 needs a CUDA device (there is no CPU fallback)")
@@ -44,6 +49,7 @@ class BatchedPcgrlEnv:
         self.spec = get_spec(self.problem, self.map_shape)
         self.n_envs = int(n_envs)
         self.device = torch.device(device)
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.env_offset = int(env_offset)
         self.seed = int(seed)
         self.auto_reset = auto_reset
@@ -170,10 +176,17 @@ class BatchedPcgrlEnv:
         self.holes = torch.zeros((N, 4), dtype=torch.int32, device=dev) if self.holey else None
         self.record_stride = int(self.lib.pcgrl_record_stride(cc)) if self._rec_sb else 0
         self.records = torch.zeros((N, self.record_stride), dtype=torch.uint8, device=dev) if self._rec_sb else None
+        # split step path of the bit-board problems (csrc/step_split.cu): a global work list of changed envs, and
+        # for binary maps up to 16x16 the per-env search cache of the incremental stats.  split_step=False keeps the
+        # fused single-kernel path; the results are identical (tests/test_gpu_split.py)
+        n_wl = int(self.lib.pcgrl_worklist_ints(cc, N)) if split_step else 0
+        self.worklist = torch.zeros(n_wl, dtype=torch.int32, device=dev) if n_wl > 0 else None
+        self.cache_stride = int(self.lib.pcgrl_cache_stride(cc)) if n_wl > 0 else 0
+        self.cache = torch.zeros((N, self.cache_stride), dtype=torch.uint8, device=dev) if self.cache_stride > 0 else None
         nscratch = self.lib.pcgrl_scratch_bytes(cc, N)
         # zero-initialised once: the solver kernels keep generation counters for their hash tables in it
         self.scratch = torch.zeros(int(nscratch), dtype=torch.uint8, device=dev) if nscratch > 0 else None
-        self._actions_dev = None
+        self._hio = None
         self._pinned = {}
         self._epoch = 0
         self._synced_steps = None     # steps since the last full reset while all envs are in lock-step
@@ -189,16 +202,21 @@ class BatchedPcgrlEnv:
         st.static_mask = _ptr(self.static_mask)
         st.holes = _ptr(self.holes)
         st.records = _ptr(self.records)
+        st.worklist = _ptr(self.worklist)
+        st.cache = _ptr(self.cache)
         self._st = st
 
     def _stat_bytes(self):
-        """Narrowest record type that holds every stat of this problem: the largest |bound| over cond_bounds, the
-        cell count (tile counts) and the solver defaults (sokoban dist-win = W*H*(W+H), sokoban_prob.py:170)."""
-        hi = self.cells * (sum(self.map_shape) if self.problem in ("sokoban", "smb") else 1)
-        for lo_, hi_ in self.cond_bounds.values():
-            hi = max(hi, abs(float(lo_)), abs(float(hi_)))
-        if self.problem in ("binary", "binary_holey", "minecraft_2D_maze") and hi <= 255:
-            return 1          # counts / lengths, never negative
+        """Narrowest record type that holds every stat of this problem.  binary family: region counts and path
+        lengths, bounded by cond_bounds (binary_prob.py:66-84: 128 / 136 for 16x16), never negative -> uint8 when
+        those fit; everything else: the largest of |cond_bounds|, the cell count (tile counts) and the solver
+        defaults (sokoban dist-win = W*H*(W+H), sokoban_prob.py:170) -> int16, else int32.  A value that still does
+        not fit raises through status bit 4."""
+        bound = max([abs(float(v)) for b in self.cond_bounds.values() for v in b] or [0.0])
+        if self.problem in ("binary", "binary_holey", "minecraft_2D_maze"):
+            if max(bound, math.ceil(self.cells / 2)) <= 255:
+                return 1
+        hi = max(bound, self.cells * (sum(self.map_shape) if self.problem in ("sokoban", "smb") else 1))
         return 2 if hi <= 32767 else 4
 
     def record_dtype(self):
@@ -273,7 +291,10 @@ class BatchedPcgrlEnv:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def _on_device(self):
-        """The C ABI launches on the calling thread's CURRENT CUDA device: make that the env's device for the call."""
+        """The C ABI launches on the calling thread's CURRENT CUDA device: make that the env's device for the call
+        (a no-op context when it already is -- the common case, and this sits on the per-step path)."""
+        if torch.cuda.current_device() == self._dev_index:
+            return _NULL_CTX
         return torch.cuda.device(self.device)
 
     def _pack_grids(self, grids):
@@ -409,44 +430,64 @@ class BatchedPcgrlEnv:
         shape, _, tdt = self._action_layout()
         return torch.empty(shape, dtype=tdt, pin_memory=True) if name is None else self._pinned_buf(name, shape, tdt)
 
+    def _host_io(self):
+        """Per-env constants of the host-buffer path, built once: action layout, pinned result buffers and their
+        numpy views (step_host runs every ~0.4 ms at the headline size, so it must not rebuild any of this)."""
+        h = self._hio
+        if h is None:
+            shape, dt, tdt = self._action_layout()
+            h = SimpleNamespace(shape=shape, dt=dt, tdt=tdt, numel=int(np.prod(shape)), known={})
+            h.nbytes = h.numel * np.dtype(dt).itemsize
+            h.act_dev = torch.empty(shape, dtype=tdt, device=self.device)
+            if self.compact_host_io:
+                h.rec = torch.empty((self.n_envs, self.record_stride), dtype=torch.uint8, pin_memory=True)
+                v = h.rec.numpy().view(self.record_dtype()).reshape(self.n_envs)
+                h.views = (v["reward"], v["done"], v["stats"], v["changed"])
+            else:
+                h.r = torch.empty(self.n_envs, dtype=torch.float32, pin_memory=True)
+                h.d = torch.empty(self.n_envs, dtype=torch.uint8, pin_memory=True)
+                h.s = torch.empty((self.n_envs, self.K), dtype=torch.int32, pin_memory=True)
+                h.views = (h.r.numpy(), h.d.numpy(), h.s.numpy())
+            self._hio = h
+        return h
+
     def step_host(self, actions, want_stats=True):
         """End-to-end step with HOST buffers (the call timed as `e2e`): actions are copied H2D from pinned
         memory, the fused kernel runs, reward / done / stats are copied back, and the stream is synchronised.
         Large binary / zelda shards are cut into chunks whose upload, kernel and download overlap on helper
         streams (pcgrl_step_host).  `actions`: numpy array (staged through a pinned buffer) or an already
         pinned torch tensor of the action layout (used in place).
-        Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats [N,K] or None).  By default these
-        are three dense arrays (stats int32); with compact_host_io they are strided views of ONE packed record
-        array (stats uint8 / int16 as the problem's bounds allow, see record_dtype()), downloaded with a single
-        copy per pipeline chunk (pcgrl_step_host_packed)."""
-        shape, dt, tdt = self._action_layout()
-        if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() and \
-                actions.dtype == tdt and actions.is_contiguous() and actions.numel() == int(np.prod(shape)):
-            a_pin = actions
+        Returns numpy views of pinned buffers (reward f32[N], done u8[N], stats [N,K] or None), overwritten by the
+        next call.  By default these are three dense arrays (stats int32); with compact_host_io they are strided
+        views of ONE packed record array (stats uint8 / int16 as the problem's bounds allow, see record_dtype()),
+        downloaded with a single copy per pipeline chunk (pcgrl_step_host_packed)."""
+        h = self._host_io()
+        a_ptr = h.known.get(id(actions))
+        if a_ptr is None:
+            if torch.is_tensor(actions) and actions.device.type == "cpu" and actions.is_pinned() and \
+                    actions.dtype == h.tdt and actions.is_contiguous() and actions.numel() == h.numel:
+                if len(h.known) < 4096:     # remember validated pinned buffers (and keep them alive)
+                    h.known[id(actions)] = (actions, actions.data_ptr())
+                a_ptr = actions.data_ptr()
+            else:
+                a_pin = self._pinned_buf("actions", h.shape, h.tdt)
+                a_pin.view(torch.uint8).numpy().view(h.dt).reshape(h.shape)[...] = \
+                    np.asarray(actions).astype(h.dt, copy=False).reshape(h.shape)
+                a_ptr = a_pin.data_ptr()
         else:
-            a_pin = self._pinned_buf("actions", shape, tdt)
-            a_pin.view(torch.uint8).numpy().view(dt).reshape(shape)[...] = np.asarray(actions).astype(dt, copy=False).reshape(shape)
-        if self._actions_dev is None:
-            self._actions_dev = torch.empty(shape, dtype=tdt, device=self.device)
-        if self.compact_host_io:
-            rec = self._pinned_buf("records", (self.n_envs, self.record_stride), torch.uint8)
-            with self._on_device():
-                _lib.check(self.lib.pcgrl_step_host_packed(self._cc, self._st, a_pin.data_ptr(),
-                                                           self._actions_dev.data_ptr(),
-                                                           a_pin.numel() * a_pin.element_size(), rec.data_ptr(),
-                                                           self._stream()), "pcgrl_step_host_packed")
-            self._after_step()
-            v = rec.numpy().view(self.record_dtype()).reshape(self.n_envs)
-            return v["reward"], v["done"], (v["stats"] if want_stats else None)
-        r = self._pinned_buf("reward", (self.n_envs,), torch.float32)
-        d = self._pinned_buf("done", (self.n_envs,), torch.uint8)
-        s = self._pinned_buf("stats", (self.n_envs, self.K), torch.int32) if want_stats else None
+            a_ptr = a_ptr[1]
         with self._on_device():
-            _lib.check(self.lib.pcgrl_step_host(self._cc, self._st, a_pin.data_ptr(), self._actions_dev.data_ptr(),
-                                                a_pin.numel() * a_pin.element_size(), r.data_ptr(), d.data_ptr(),
-                                                _ptr(s), self._stream()), "pcgrl_step_host")
+            if self.compact_host_io:
+                rc = self.lib.pcgrl_step_host_packed(self._cc, self._st, a_ptr, h.act_dev.data_ptr(), h.nbytes,
+                                                     h.rec.data_ptr(), self._stream())
+            else:
+                rc = self.lib.pcgrl_step_host(self._cc, self._st, a_ptr, h.act_dev.data_ptr(), h.nbytes,
+                                              h.r.data_ptr(), h.d.data_ptr(), h.s.data_ptr() if want_stats else None,
+                                              self._stream())
+        if rc:
+            _lib.check(rc, "pcgrl_step_host")
         self._after_step()
-        return r.numpy(), d.numpy(), (s.numpy() if s is not None else None)
+        return h.views[0], h.views[1], (h.views[2] if want_stats else None)
 
     def host_io_bytes(self, want_stats=True):
         """(h2d, d2h) bytes one step_host call moves over PCIe, counted from the buffers it copies."""
@@ -559,7 +600,7 @@ class BatchedPcgrlEnv:
         return OrderedDict(zip(self.stat_names, row))
 
     _STATE_TENSORS = ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes",
-                      "records")
+                      "records", "cache")
 
     def state_dict(self):
         """Everything needed to reconstruct the env state (checkpoint row), including the
@@ -567,11 +608,12 @@ class BatchedPcgrlEnv:
         sd = {k: getattr(self, k).clone() for k in self._STATE_TENSORS if getattr(self, k) is not None}
         sd["_epoch"] = int(self._epoch)
         sd["seed"] = int(self.seed)
+        sd["_synced_steps"] = self._synced_steps
         return sd
 
     def load_state_dict(self, sd):
         want = {k for k in self._STATE_TENSORS if getattr(self, k) is not None}
-        have = {k for k in sd if k not in ("_epoch", "seed")}
+        have = {k for k in sd if k not in ("_epoch", "seed", "_synced_steps")}
         if want != have:
             raise KeyError(f"state_dict keys differ: missing {sorted(want - have)}, unexpected {sorted(have - want)}")
         for k in want:
@@ -582,4 +624,4 @@ class BatchedPcgrlEnv:
             getattr(self, k).copy_(sd[k])
         self._epoch = int(sd.get("_epoch", self._epoch))
         self.seed = int(sd.get("seed", self.seed))
-        self._synced_steps = None
+        self._synced_steps = sd.get("_synced_steps")     # lock-step episode clock (None: envs are out of step)

@@ -11,6 +11,8 @@
 
 namespace pcgrl {
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
+cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, bool incremental, bool& supported);
+int bitboard_cache_stride(int problem, int ndim, int d0, int d1, int rep, int action_kind);
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported);
@@ -18,6 +20,10 @@ int64_t sokoban_scratch_bytes();
 int64_t smb_scratch_bytes();
 int64_t maze3d_scratch_bytes();
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
+
+// split step path: up to WL_CHUNKS host-pipeline chunks, one 16-int work-list header each at the front of
+// pcgrl_state.worklist
+constexpr int WL_CHUNKS = 64, WL_HDR_INTS = 16 * WL_CHUNKS;
 
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
@@ -84,6 +90,19 @@ static int check(const pcgrl_config* c) {
     if (sb != 0 && sb != 1 && sb != 2 && sb != 4) return fail(PCGRL_E_ARG, "record_stat_bytes must be 0, 1, 2 or 4");
     return 0;
 }
+static bool is_bitboard(const pcgrl_config* c) {
+    return c->problem == PCGRL_PROB_BINARY || c->problem == PCGRL_PROB_ZELDA || c->problem == PCGRL_PROB_BINARY_HOLEY;
+}
+static int cache_stride(const pcgrl_config* c) {
+    return bitboard_cache_stride(c->problem, c->ndim, c->dims[0], c->dims[1], c->representation, c->action_kind);
+}
+// PCGRL_STEP_PATH = fused | split | inc (default inc): which of the equivalent step paths pcgrl_step takes when the
+// caller supplied the buffers for all of them (A/B runs and the path-equivalence tests)
+static int step_path() {
+    const char* e = getenv("PCGRL_STEP_PATH");
+    if (!e) return 2;
+    return !strcmp(e, "fused") ? 0 : !strcmp(e, "split") ? 1 : 2;
+}
 static int action_elem(const pcgrl_config* c) { return c->action_elem_bytes ? c->action_elem_bytes : 4; }
 static int record_stride(const pcgrl_config* c) {
     return c->record_stat_bytes ? (4 + c->n_stats * c->record_stat_bytes + 2 + 3) / 4 * 4 : 0;
@@ -146,6 +165,11 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
         p.static_mask = st->static_mask;
         p.holes = st->holes;
         p.records = p.rec_sb ? st->records : nullptr;
+        // split path: headers of up to WL_CHUNKS pipeline chunks at the front (16 ints each), bodies behind them
+        p.wl_hdr = st->worklist;
+        p.worklist = st->worklist ? st->worklist + WL_HDR_INTS : nullptr;
+        p.cache_stride = cache_stride(c);
+        p.cache = p.cache_stride && st->worklist ? st->cache : nullptr;
     }
 }
 
@@ -169,8 +193,18 @@ static int run(const KParams& p, int problem, void* stream) {
         e = launch_sokoban(p, (cudaStream_t)stream, supported);
     else if (problem == PCGRL_PROB_SMB)
         e = launch_smb(p, (cudaStream_t)stream, supported);
-    else
+    else {
+        const int path = step_path();
+        if (p.mode == MODE_STEP && p.worklist && path > 0) {
+            e = launch_bitboard_split(p, problem, (cudaStream_t)stream, path == 2, supported);
+            if (supported) {
+                if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+                g_launches.fetch_add(3, std::memory_order_relaxed);
+                return 0;
+            }
+        }
         e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
+    }
     if (!supported)
         return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet (or scratch is NULL although "
                                          "pcgrl_scratch_bytes() > 0)");
@@ -196,7 +230,7 @@ static int host_chunks(const pcgrl_config* cfg, int64_t n, bool packed) {
         return 1;
     if (const char* e = getenv("PCGRL_HOST_CHUNKS")) {
         const int v = atoi(e);
-        if (v >= 1) return (int)std::min<int64_t>(v, std::max<int64_t>(1, n / 256));
+        if (v >= 1) return (int)std::min<int64_t>(std::min(v, WL_CHUNKS), std::max<int64_t>(1, n / 256));
     }
     // measured on B200 (binary 16x16, e2e env-steps/s): 64 Ki envs 1 chunk best (2 / 4 chunks: 3.3 / 2.4e8); 256 Ki
     // 1 / 2 / 4 chunks -> 8.5 / 9.1 / 7.1e8; 512 Ki -> 1.07 / 1.26 / 1.09e9; 1 Mi 2 / 4 / 8 -> 1.77 / 2.0 / 1.77e9.
@@ -243,12 +277,28 @@ int64_t pcgrl_step_bytes(const pcgrl_config* c) {
     return 2 * G + A + 8 * K + 5 + (c->targets_per_env ? 16 * K : 0);
 }
 
+int64_t pcgrl_worklist_ints(const pcgrl_config* cfg, int64_t n_envs) {
+    if (check(cfg) || n_envs < 0) return -1;
+    if (!is_bitboard(cfg) || cfg->representation == PCGRL_REP_CELLULAR || cfg->ndim != 2) return 0;
+    // header + (env, cell) + new stats per env, plus one header per host-pipeline chunk (up to 64)
+    return (2 + (int64_t)cfg->n_stats) * n_envs + WL_HDR_INTS;
+}
+
+int32_t pcgrl_cache_stride(const pcgrl_config* cfg) {
+    if (check(cfg)) return -1;
+    return cache_stride(cfg);
+}
+
 int32_t pcgrl_record_stride(const pcgrl_config* cfg) {
     if (check(cfg)) return -1;
     return record_stride(cfg);
 }
 
-int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream) {
+// One step launch over `st`.  wl_chunk / wl_off place this launch's work list inside the PARENT shard's
+// pcgrl_state.worklist (host pipeline: st is a sub-range starting wl_off envs into the shard and `wl_base` is the
+// parent's buffer); a plain pcgrl_step is chunk 0 at offset 0 of its own buffer.
+static int32_t step_launch(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream,
+                           int32_t* wl_base, int wl_chunk, int64_t wl_off) {
     int r = check(cfg);
     if (r) return r;
     if ((r = check_state(st))) return r;
@@ -256,9 +306,17 @@ int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* a
     if (is_holey(cfg) && !st->holes) return fail(PCGRL_E_ARG, "a holey problem needs pcgrl_state.holes");
     KParams p;
     fill(p, cfg, st);
+    if (wl_base) {
+        p.wl_hdr = wl_base + 16 * wl_chunk;
+        p.worklist = wl_base + WL_HDR_INTS + (2 + (int64_t)cfg->n_stats) * wl_off;
+    }
     p.mode = MODE_STEP;
     p.actions = actions;
     return run(p, cfg->problem, stream);
+}
+
+int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream) {
+    return step_launch(cfg, st, actions, stream, st ? st->worklist : nullptr, 0, 0);
 }
 
 int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_t* mask, const int8_t* src_grids,
@@ -398,6 +456,7 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
         sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
         sub.holes = st->holes ? st->holes + off * 4 : nullptr;
         sub.records = st->records ? st->records + off * rs : nullptr;
+        sub.cache = st->cache ? st->cache + off * cache_stride(cfg) : nullptr;
         int64_t a_stride = a_env;
         if (!actions_host) {   // actions already on the device: per-env stride from the action layout
             a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)
@@ -410,7 +469,8 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
         if (actions_host &&
             (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
             return cuda_fail(e, "H2D actions");
-        if ((r = pcgrl_step(cfg, &sub, a_dev, cs))) return r;
+        // every chunk gets its own header and its own body range of the shard's work list
+        if ((r = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off))) return r;
         if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
             return cuda_fail(e, "D2H records");
         if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)

@@ -70,6 +70,11 @@ struct KParams {
     int32_t act_bytes;            // 4, 1 or 2: element size of PCGRL_ACT_INT32 / PCGRL_ACT_WIDE_FLAT actions
     int32_t rec_stride, rec_sb;   // bytes per record / per stat in it (rec_sb == 0: no records)
     uint8_t* records;             // [N, rec_stride] or NULL
+    // split step path (step_split.cu): work list of changed envs + per-env search cache (both may be NULL)
+    int32_t* wl_hdr;              // 16 header ints of this launch's work list
+    int32_t* worklist;            // its body: [2 ints per env (env, cell) | n_stats ints per env]
+    uint8_t* cache;               // [N, cache_stride]
+    int32_t cache_stride;
 };
 
 // one scalar action (narrow / turtle / flat wide) in the width the caller chose (cfg.action_elem_bytes)

@@ -18,6 +18,7 @@
 //   D  thread-per-env: fp64 loss(new stats) - loss(old stats), write stats / reward / done / counters.
 #include "pcgrl_device.cuh"
 #include "step_common.cuh"
+#include "bitboard_machines.cuh"
 
 namespace pcgrl {
 
@@ -39,6 +40,14 @@ namespace pcgrl {
 #ifndef PCGRL_EXPAND_R
 #define PCGRL_EXPAND_R 3
 #endif
+#ifndef PCGRL_THETA_F
+#define PCGRL_THETA_F 0     // expand while >= THETA_F/32 of a warp's active lanes are alive (0: fixed windows of PCGRL_EXPAND_R);
+                            // A/B 8 / 12 / 16 / 20: 0.60 / 0.53 / 0.47 / 0.45 ms per step against 0.385 with fixed windows
+#endif
+#ifndef PCGRL_CONVERGE
+#define PCGRL_CONVERGE 0    // 1: every lane of a warp starts every search trip together (vote at the loop head); A/B in the
+                            // fused kernel 0.393 against 0.385 ms without (it does pay in the split kernel: 0.381 / 0.432)
+#endif
 #ifndef PCGRL_WARP_BATCH
 #define PCGRL_WARP_BATCH 0  // 1: warps claim batches of 32 changed envs; 0: per-thread claims
 #endif
@@ -51,369 +60,6 @@ namespace pcgrl {
 constexpr int THREADS = PCGRL_THREADS;
 // envs per CTA, bounded so the shared-memory bit-boards stay under the 48 KB static limit
 __host__ __device__ constexpr int tile_for(int bbw) { return bbw == 8 ? PCGRL_TILE8 : bbw < 8 ? 256 : (bbw <= 32 ? 256 : (bbw <= 80 ? 128 : 64)); }
-
-// ------------------------------------------------------------------------------------------------
-// Problem policies: planes (tile-code sets packed to bit-boards) + the per-thread stats state machine.
-// Each machine is a flat loop: one board expansion per trip, with rare transitions -- so the 32 grids
-// that share a warp execute the same instruction stream whatever phase each of them is in.
-// ------------------------------------------------------------------------------------------------
-struct BinaryProb {
-    static constexpr int P = 1;
-    static constexpr int K = 2;  // regions, path-length
-    __host__ __device__ static constexpr uint32_t plane_mask(int p) { return 0x1u; }  // {empty}
-};
-
-struct ZeldaProb {
-    static constexpr int P = 5;
-    static constexpr int K = 7;  // player key door enemies regions nearest-enemy path-length
-    // tiles: empty 0, solid 1, player 2, key 3, door 4, bat 5, scorpion 6, spider 7 (zelda_prob.py:20)
-    __host__ __device__ static constexpr uint32_t plane_mask(int p) {
-        return p == 0 ? 0xEDu   /* walkable {0,2,3,5,6,7}  zelda_ctrl_prob.py:101-104 */
-             : p == 1 ? 0x04u   /* player */
-             : p == 2 ? 0x08u   /* key */
-             : p == 3 ? 0x10u   /* door */
-             :          0xE0u;  /* enemies {5,6,7} */
-    }
-};
-
-struct BinaryHoleyProb {
-    static constexpr int P = 2;  // plane 0 {empty}; plane 1 holds no tile: the machine keeps the exit cell there
-    static constexpr int K = 3;  // regions, path-length, connected-path-length
-    __host__ __device__ static constexpr uint32_t plane_mask(int p) { return p == 0 ? 0x1u : 0x0u; }
-};
-
-// binary: regions + double-sweep longest path over the {empty} plane.
-//   helper.calc_longest_path runs, per component, BFS(first tile) -> far tile -> BFS(far) and keeps the max.
-//   Exact restatement used here: (1) isolated cells are components with eccentricity 0: count them with a
-//   popcount; (2) for the other components run the first sweep one component at a time (start = lowest
-//   remaining cell, far = lowest cell of the last non-empty level == np.argmax); (3) the second sweeps of
-//   all components run at once as a single multi-source BFS from the set of far tiles -- components are
-//   disconnected, so the number of levels until the joint frontier dies is max_c ecc(far_c).
-template <int NW, bool TWO>
-struct BinaryMachine {
-    using Prob = BinaryProb;
-    using B = Board<NW, TWO>;
-    uint32_t avail[NW], front[NW], fars[NW];
-    uint32_t* base;  // shared-memory copy of the non-isolated passable cells (re-read for the joint sweep)
-    int phase, level, ncomp;
-
-    __device__ __forceinline__ void init(uint32_t* bb /* [P][NW] in shared memory */, const KParams&, int64_t) {
-        uint32_t pass[NW], ones[NW], nb[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            pass[i] = bb[i];
-            ones[i] = 0xFFFFFFFFu;
-        }
-        B::expand_and(pass, ones, nb);
-        ncomp = 0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t iso = pass[i] & ~nb[i];
-            ncomp += __popc(iso);
-            avail[i] = pass[i] & ~iso;
-            bb[i] = avail[i];
-            front[i] = 0;
-            fars[i] = 0;
-        }
-        base = bb;
-        phase = 0;
-        level = 0;
-    }
-    // one board expansion; returns false (and changes nothing) when the frontier has died
-    __device__ __forceinline__ bool expand() {
-        uint32_t n[NW];
-        if (!B::expand_and(front, avail, n)) return false;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            avail[i] = B::minus_subset(avail[i], n[i]);
-            front[i] = n[i];
-        }
-        ++level;
-        return true;
-    }
-    // the frontier died: next component / next phase; returns true when out[] holds the K stats
-    __device__ __forceinline__ bool transition(int* out) {
-        if (phase == 0) {
-#if PCGRL_OPT_BORROW
-            uint32_t t[NW];
-            B::minus_one(front, t);           // far tile of the component just swept (nothing on entry)
-#pragma unroll
-            for (int i = 0; i < NW; ++i) fars[i] |= front[i] & ~t[i];
-            if (B::minus_one(avail, t)) {     // first tile of the next component
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    front[i] = avail[i] & ~t[i];
-                    avail[i] &= t[i];
-                }
-                ++ncomp;
-                return false;
-            }
-#else
-            uint32_t lo[NW];
-            B::lowest(front, lo);             // far tile of the component just swept (nothing on entry)
-#pragma unroll
-            for (int i = 0; i < NW; ++i) fars[i] |= lo[i];
-            B::lowest(avail, lo);             // first tile of the next component
-            if (B::any(lo)) {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    front[i] = lo[i];
-                    avail[i] ^= lo[i];
-                }
-                ++ncomp;
-                return false;
-            }
-#endif
-            phase = 1;  // joint second sweep from every far tile
-            uint32_t any = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                front[i] = fars[i];
-                avail[i] = base[i] & ~fars[i];
-                any |= fars[i];
-            }
-            level = 0;
-            if (any) return false;
-        }
-        out[0] = ncomp;
-        out[1] = level;
-        return true;
-    }
-};
-
-// binary_holey (envs/probs/binary/binary_holey_prob.py:59-93): the stats are taken on the BORDERED map
-// (pcgrl_holey_env.py:52-53) whose border is solid except for the entrance and the exit.  The board built by
-// phase B holds the level (one row per word); init() moves it one cell down-right into the border frame and
-// digs the two holes.  regions = flood fill over the bordered board; then ONE BFS from the entrance:
-// path-length = its last level (np.max of the dijkstra map), connected-path-length = the level that reaches
-// the exit (0 when it never does: the reference maps -1 to 0, :69-77).
-template <int NW, bool TWO>
-struct BinaryHoleyMachine {
-    static_assert(!TWO, "the bordered board keeps one row per word");
-    using Prob = BinaryHoleyProb;
-    using B = Board<NW, TWO>;
-    uint32_t avail[NW], front[NW];
-    uint32_t* bb;   // plane 0: bordered passable board, plane 1: the exit cell
-    int phase, level, regions, connected, ey, ex;
-
-    __device__ __forceinline__ void init(uint32_t* planes, const KParams& p, int64_t env) {
-        bb = planes;
-        const int32_t* h = p.holes + env * 4;
-        ey = h[0];
-        ex = h[1];
-        const int xy = h[2], xx = h[3];
-        uint32_t pass[NW], ones[NW], nb[NW];
-#pragma unroll
-        for (int i = 0; i < NW; ++i) pass[i] = i > 0 ? planes[i - 1] << 1 : 0u;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            uint32_t xm = 0;
-            if (i == xy && (unsigned)xx < 32u) xm = 1u << xx;
-            if (i == ey && (unsigned)ex < 32u) pass[i] |= 1u << ex;
-            pass[i] |= xm;
-            planes[i] = pass[i];
-            planes[NW + i] = xm;
-            ones[i] = 0xFFFFFFFFu;
-        }
-        B::expand_and(pass, ones, nb);
-        regions = 0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t iso = pass[i] & ~nb[i];
-            regions += __popc(iso);
-            avail[i] = pass[i] & ~iso;
-            front[i] = 0;
-        }
-        phase = 0;
-        level = 0;
-        connected = 0;
-    }
-    __device__ __forceinline__ bool expand() {
-        uint32_t n[NW];
-        if (!B::expand_and(front, avail, n)) return false;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            avail[i] = B::minus_subset(avail[i], n[i]);
-            front[i] = n[i];
-        }
-        ++level;
-        if (phase == 1) {
-            uint32_t hit = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) hit |= n[i] & bb[NW + i];
-            if (hit) connected = level;
-        }
-        return true;
-    }
-    __device__ __forceinline__ bool transition(int* out) {
-        if (phase == 0) {
-            uint32_t t[NW];
-            if (B::minus_one(avail, t)) {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    front[i] = avail[i] & ~t[i];
-                    avail[i] &= t[i];
-                }
-                ++regions;
-                return false;
-            }
-            phase = 1;   // BFS from the entrance over the whole bordered board
-            level = 0;
-#pragma unroll
-            for (int i = 0; i < NW; ++i) {
-                front[i] = (i == ey && (unsigned)ex < 32u) ? 1u << ex : 0u;
-                avail[i] = bb[i] & ~front[i];
-            }
-            return false;
-        }
-        out[0] = regions;
-        out[1] = level;
-        out[2] = connected;
-        return true;
-    }
-};
-
-// zelda: tile counts, regions over the walkable plane, then (player == 1) BFS from the player:
-// nearest-enemy = first level >= 1 that touches an enemy, d(player->key) = level that touches the key;
-// then (key == 1 && door == 1) BFS from the key over walkable+door: d(key->door).  Unreached = -1 each
-// (run_dijkstra's fill value), added raw (zelda_ctrl_prob.py:134-150).
-template <int NW, bool TWO>
-struct ZeldaMachine {
-    using Prob = ZeldaProb;
-    using B = Board<NW, TWO>;
-    uint32_t avail[NW], front[NW];
-    const uint32_t* bb;  // planes in shared memory: walk, player, key, door, enemy
-    int phase, level, regions, near, dkey, ddoor;
-    int n_player, n_key, n_door, n_enemy;
-
-    __device__ __forceinline__ void load(int plane, uint32_t (&x)[NW]) const {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) x[i] = bb[plane * NW + i];
-    }
-    __device__ __forceinline__ void init(uint32_t* planes, const KParams&, int64_t) {
-        bb = planes;
-        uint32_t walk[NW], t[NW], ones[NW], nb[NW];
-        load(0, walk);
-        load(1, t);
-        n_player = B::popcount(t);
-        load(2, t);
-        n_key = B::popcount(t);
-        load(3, t);
-        n_door = B::popcount(t);
-        load(4, t);
-        n_enemy = B::popcount(t);
-#pragma unroll
-        for (int i = 0; i < NW; ++i) ones[i] = 0xFFFFFFFFu;
-        B::expand_and(walk, ones, nb);
-        regions = 0;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            const uint32_t iso = walk[i] & ~nb[i];
-            regions += __popc(iso);
-            avail[i] = walk[i] & ~iso;
-            front[i] = 0;
-        }
-        phase = 0;
-        level = 0;
-        near = 0;
-        dkey = -1;
-        ddoor = -1;
-    }
-    __device__ __forceinline__ bool expand() {
-        uint32_t n[NW];
-        if (!B::expand_and(front, avail, n)) return false;
-#pragma unroll
-        for (int i = 0; i < NW; ++i) {
-            avail[i] ^= n[i];
-            front[i] = n[i];
-        }
-        ++level;
-        if (phase == 1) {
-            uint32_t t[NW];
-            load(4, t);
-            if (near == 0 && B::any_and(n, t)) near = level;
-            load(2, t);
-            if (B::any_and(n, t)) dkey = level;
-        } else if (phase == 2) {
-            uint32_t t[NW];
-            load(3, t);
-            if (B::any_and(n, t)) ddoor = level;
-        }
-        return true;
-    }
-    __device__ __forceinline__ bool transition(int* out) {
-        if (phase == 0) {  // region flood fill, one component at a time
-            uint32_t t[NW];
-            if (B::minus_one(avail, t)) {
-#pragma unroll
-                for (int i = 0; i < NW; ++i) {
-                    front[i] = avail[i] & ~t[i];
-                    avail[i] &= t[i];
-                }
-                ++regions;
-                return false;
-            }
-            if (n_player == 1 && (n_enemy > 0 || (n_key == 1 && n_door == 1))) {
-                phase = 1;  // BFS from the player over the walkable plane
-                uint32_t walk[NW];
-                load(0, walk);
-                load(1, front);
-#pragma unroll
-                for (int i = 0; i < NW; ++i) avail[i] = walk[i] & ~front[i];
-                level = 0;
-                return false;
-            }
-            phase = 3;
-        } else if (phase == 1) {
-            if (n_key == 1 && n_door == 1) {
-                phase = 2;  // BFS from the key over walkable + door
-                uint32_t walk[NW], door[NW];
-                load(0, walk);
-                load(3, door);
-                load(2, front);
-#pragma unroll
-                for (int i = 0; i < NW; ++i) avail[i] = (walk[i] | door[i]) & ~front[i];
-                level = 0;
-                return false;
-            }
-            phase = 3;
-        }
-        out[0] = n_player;
-        out[1] = n_key;
-        out[2] = n_door;
-        out[3] = n_enemy;
-        out[4] = regions;
-        out[5] = near;
-        out[6] = (n_player == 1 && n_key == 1 && n_door == 1) ? dkey + ddoor : 0;
-        return true;
-    }
-};
-
-// ------------------------------------------------------------------------------------------------
-// 16 tile codes (one 128-bit load) -> one 16-bit membership mask per plane (bit i = cell i in the plane).
-// Tile codes are < 8 for every bit-board problem, so a plane is an 8-entry 0/1 table that PRMT looks up
-// for 4 cells at once; the multiply then gathers the four 0/1 bytes into bits 24..27.
-// ------------------------------------------------------------------------------------------------
-__host__ __device__ constexpr uint32_t lut_bytes(uint32_t mask, int first) {
-    return ((mask >> first) & 1u) | (((mask >> (first + 1)) & 1u) << 8) | (((mask >> (first + 2)) & 1u) << 16) |
-           (((mask >> (first + 3)) & 1u) << 24);
-}
-template <class Prob>
-__device__ __forceinline__ void pack16(const uint4 v, uint32_t (&out)[Prob::P]) {
-    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int q = 0; q < Prob::P; ++q) out[q] = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t t = w4[k] | (w4[k] >> 4);
-        const uint32_t sel = ((t & 0xFFu) | ((t >> 8) & 0xFF00u)) & 0x7777u;  // 4 nibbles = 4 tile codes
-#pragma unroll
-        for (int q = 0; q < Prob::P; ++q) {
-            const uint32_t b = __byte_perm(lut_bytes(Prob::plane_mask(q), 0), lut_bytes(Prob::plane_mask(q), 4), sel);
-            out[q] |= ((b * 0x01020408u) >> 24) << (4 * k);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
@@ -577,6 +223,64 @@ __global__ void __launch_bounds__(THREADS, NW <= 8 ? PCGRL_MIN_CTAS : 1) k_step_
             }
         }
 #else
+#if PCGRL_THETA_F > 0
+        // Rounds: the warp keeps expanding while at least PCGRL_THETA_F/32 of its active lanes still have a live
+        // frontier (the others wait), then every waiting lane takes its transition (and claims its next grid) in
+        // ONE pass of the transition stream, so both streams run with many lanes.
+        bool alive = false;   // a fresh machine has an empty frontier: its first act is a transition
+        for (;;) {
+            const unsigned act = __ballot_sync(0xffffffffu, active);
+            if (!act) break;
+            const int need = max(1, (__popc(act) * PCGRL_THETA_F) >> 5);
+            for (;;) {
+                if (__popc(__ballot_sync(0xffffffffu, active && alive)) < need) break;
+                if (active && alive) alive = m.expand();
+            }
+            if (active && !alive) {
+                int out[K];
+                if (m.transition(out)) {
+#pragma unroll
+                    for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                    if constexpr (Machine::HAS_CACHE)
+                        if (p.cache && p.mode != MODE_STATS)
+                            m.store_cache((uint32_t*)(p.cache + (base + s_list[item]) * p.cache_stride));
+                    item = PCGRL_NEXT_ITEM(item);
+                    active = item < M;
+                    if (active) m.init(s_bb + item * BBW, p, base + s_list[item]);
+                } else {
+                    alive = true;
+                }
+            }
+        }
+#elif PCGRL_CONVERGE
+        // One trip = PCGRL_EXPAND_R board expansions, then the transition stream for the lanes whose frontier died.
+        // The warp-wide vote at the top makes every lane start every trip together (finished lanes stay in the
+        // loop until the whole warp is done): without it the lanes that loop back early run ahead of the ones in a
+        // transition and the warp falls apart into groups that issue both streams separately.
+        for (;;) {
+            if (!__any_sync(0xffffffffu, active)) break;
+            bool dead = false;
+            if (active) {
+                bool alive = m.expand();
+#pragma unroll
+                for (int r = 1; r < PCGRL_EXPAND_R; ++r)
+                    if (alive) alive = m.expand();
+                dead = !alive;
+            }
+            __syncwarp();
+            int out[K];
+            if (dead && m.transition(out)) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                if constexpr (Machine::HAS_CACHE)
+                    if (p.cache && p.mode != MODE_STATS)
+                        m.store_cache((uint32_t*)(p.cache + (base + s_list[item]) * p.cache_stride));
+                item = PCGRL_NEXT_ITEM(item);
+                active = item < M;
+                if (active) m.init(s_bb + item * BBW, p, base + s_list[item]);
+            }
+        }
+#else
         while (active) {
             int out[K];
             // PCGRL_EXPAND_R expansions per trip: the transition stream (a few lanes) is then paid once per R
@@ -590,11 +294,15 @@ __global__ void __launch_bounds__(THREADS, NW <= 8 ? PCGRL_MIN_CTAS : 1) k_step_
             if (m.transition(out)) {
 #pragma unroll
                 for (int k = 0; k < K; ++k) s_stats[item * K + k] = out[k];
+                if constexpr (Machine::HAS_CACHE)
+                    if (p.cache && p.mode != MODE_STATS)
+                        m.store_cache((uint32_t*)(p.cache + (base + s_list[item]) * p.cache_stride));
                 item = PCGRL_NEXT_ITEM(item);
                 active = item < M;
                 if (active) m.init(s_bb + item * BBW, p, base + s_list[item]);
             }
         }
+#endif
 #endif
 #endif
     }

@@ -17,11 +17,13 @@ __device__ __forceinline__ int cell_index(const KParams& p, int a0, int a1, int 
 // differ only under StaticTileRepresentation (envs/reps/wrappers.py:358-376): an edit of a frozen cell is
 // undone (`np.where(static_tiles < 1, new, old)`), but `change = np.any(old_state != new_state)` compares
 // against the pre-undo array, so it still counts as a change (and the reference recomputes identical stats).
-__device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
+// *cell_out (optional): linear index of the one cell the action addressed, -1 for multi-cell actions (patch).
+__device__ __forceinline__ int apply_action(const KParams& p, int64_t gid, int* cell_out = nullptr) {
     int8_t* grid = p.grids + gid * p.row_stride;
     int32_t* pos = p.pos + gid * 3;
     const uint8_t* frozen = p.static_mask ? p.static_mask + gid * p.row_stride : nullptr;
     int change = 0, wrote = 0;
+    if (cell_out) *cell_out = -1;
     if (p.rep == PCGRL_REP_NARROW && p.action_kind == PCGRL_ACT_PATCH) {
         // MultiActionRepresentation.update (envs/reps/wrappers.py:466-528): the patch action.reshape(act_window)
         // replaces map[pos - l_pad : pos + r_pad + 1], l_pad = floor((a-1)/2), r_pad = ceil((a-1)/2) (:404-411);
@@ -65,6 +67,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
         // reps/narrow_rep.py:89-102: write at _pos, then _pos = coords[n_step % N], then n_step += 1
         const int a = load_action(p, gid);
         const int c = cell_index(p, pos[0], pos[1], pos[2]);
+        if (cell_out) *cell_out = c;
         if ((unsigned)a >= (unsigned)p.n_tiles) {
             if (p.status) atomicOr(p.status, 1);
         } else {
@@ -89,6 +92,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
             pos[axis] = v < 0 ? 0 : (v > lim ? lim : v);
         } else if (a >= 4 && a - 4 < p.n_tiles) {
             const int c = cell_index(p, pos[0], pos[1], pos[2]);
+            if (cell_out) *cell_out = c;
             const int t = a - 4;
             const int old = grid[c];
             change = old != t;
@@ -120,6 +124,7 @@ __device__ __forceinline__ int apply_action(const KParams& p, int64_t gid) {
             if (p.status) atomicOr(p.status, 1);
         } else {
             const int c = cell_index(p, q0, q1, q2);
+            if (cell_out) *cell_out = c;
             const int old = grid[c];
             change = old != v;
             wrote = change;   // the reference's wide / cellular reps do not run under StaticTileRepresentation
@@ -326,6 +331,50 @@ __device__ static void reset_env(const KParams& p, int64_t gid) {
 }
 
 
+// PcgrlEnv.step's bookkeeping for env `gid` after its representation update returned `cw` (bit0 change, bit1 the
+// grid was modified): iteration / changes counters, done, change flag, zero reward for an unchanged map.
+// Returns true when the stats must be recomputed (pcgrl_env.py:314).
+__device__ __forceinline__ bool step_counters(const KParams& p, int64_t gid, int cw) {
+    const int change = cw & 1;
+    const int it = p.iteration[gid] + 1;   // pcgrl_env.py:279
+    const int ch = p.changes[gid] + change;
+    p.iteration[gid] = it;
+    if (change) p.changes[gid] = ch;
+    bool done = it > p.max_iterations;     // :307
+    if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
+    p.done[gid] = done;
+    if (p.changed) p.changed[gid] = change != 0;
+    record_flags(p, gid, done, change);
+    const bool need = (cw & 2) != 0;       // :314 stats only when the map changed (an undone edit of a frozen
+                                           // tile leaves map, stats and loss as they were)
+    if (!need) {
+        p.reward[gid] = 0.f;
+        record_reward(p, gid, 0.f);
+    }
+    return need;
+}
+
+// Phase D for one env: reward = loss(new stats) - loss(old stats) in fp64 (or the range-reward sum), then the new
+// stats replace the old ones (int32 view and packed record).
+template <int K>
+__device__ __forceinline__ void finish_env(const KParams& p, int64_t gid, const int32_t (&nw)[K]) {
+    int32_t* st = p.stats + gid * K;
+    if (p.mode == MODE_STEP) {
+        int32_t od[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) od[k] = st[k];
+        const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
+        const double r = p.reward_mode == PCGRL_REWARD_RANGE
+                             ? range_reward_sum(nw, od, trg, p.weights, K)
+                             : control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
+        p.reward[gid] = (float)r;
+        record_reward(p, gid, (float)r);
+    }
+    record_stats<K>(p, gid, nw);
+#pragma unroll
+    for (int k = 0; k < K; ++k) st[k] = nw[k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // phase A (whole CTA): apply the actions of the TILE envs starting at `base` (or reset them, or just list
 // them in MODE_STATS), advance the counters, decide done, and build the compact list of envs whose map
@@ -383,22 +432,7 @@ __device__ __forceinline__ void phase_a(const KParams& p, int64_t base, int tile
             const int64_t gid = base + e;
             if (p.mode == MODE_STEP) {
                 const int cw = (p.rep == PCGRL_REP_CELLULAR) ? 3 * (int)s_flag[e] : apply_action(p, gid);
-                const int change = cw & 1;
-                const int it = p.iteration[gid] + 1;   // pcgrl_env.py:279
-                const int ch = p.changes[gid] + change;
-                p.iteration[gid] = it;
-                if (change) p.changes[gid] = ch;
-                bool done = it > p.max_iterations;     // :307
-                if (p.max_changes >= 0) done = done || ch > p.max_changes;  // :308-309
-                p.done[gid] = done;
-                if (p.changed) p.changed[gid] = change != 0;
-                record_flags(p, gid, done, change);
-                need = (cw & 2) != 0;                  // :314 stats only when the map changed (an undone edit of a
-                                                       // frozen tile leaves map, stats and loss as they were)
-                if (!need) {
-                    p.reward[gid] = 0.f;
-                    record_reward(p, gid, 0.f);
-                }
+                need = step_counters(p, gid, cw);
             } else if (p.mode == MODE_RESET) {
                 need = p.mask == nullptr || p.mask[gid] != 0;
                 if (need) reset_env(p, gid);
@@ -443,21 +477,7 @@ __device__ __forceinline__ void phase_d(const KParams& p, int64_t base, int tile
             for (int k = 0; k < K; ++k) p.stats_out[gid * K + k] = nw[k];
             continue;
         }
-        int32_t* st = p.stats + gid * K;
-        if (p.mode == MODE_STEP) {
-            int32_t od[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) od[k] = st[k];
-            const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
-            const double r = p.reward_mode == PCGRL_REWARD_RANGE
-                                 ? range_reward_sum(nw, od, trg, p.weights, K)
-                                 : control_loss(nw, trg, p.weights, K) - control_loss(od, trg, p.weights, K);
-            p.reward[gid] = (float)r;
-            record_reward(p, gid, (float)r);
-        }
-        record_stats<K>(p, gid, nw);
-#pragma unroll
-        for (int k = 0; k < K; ++k) st[k] = nw[k];
+        finish_env<K>(p, gid, nw);
     }
 }
 

@@ -153,6 +153,18 @@ typedef struct pcgrl_state {
                               written by step next to reward / done / stats (which stay the int32 view of the same
                               values); resets refresh the stats part only.  One contiguous device range per env range,
                               so a host step needs ONE device-to-host copy (pcgrl_step_host_packed) */
+    int32_t* worklist;     /* [pcgrl_worklist_ints(cfg, N)] int32 (ABI 5) or NULL, zero-filled once before its first
+                              use and not shared by concurrent launches: scratch of the SPLIT step path of the
+                              bit-board problems (binary, zelda, binary_holey; not the cellular representation) --
+                              pcgrl_step then runs three kernels (representation update + global list of changed
+                              envs; stat searches with every lane busy; reward / outputs) instead of the fused one.
+                              NULL: the fused single-kernel path.  Results are identical either way */
+    uint8_t* cache;        /* [N, pcgrl_cache_stride(cfg)] (ABI 5) or NULL; only with worklist, and only where
+                              pcgrl_cache_stride(cfg) > 0 (binary, maps up to 16x16, one-cell actions): per-env
+                              search state (passable bit-board, one far tile per component, a cell of a longest-path
+                              component) that lets step recompute regions / path-length INCREMENTALLY around the
+                              edited cell.  Written by reset and by every step; derived state, bit-identical stats.
+                              The grids of a shard with a cache must only change through pcgrl_step / pcgrl_reset */
 } pcgrl_state;
 
 /* -- queries (host only, no CUDA calls) ------------------------------------------------------- */
@@ -167,6 +179,11 @@ int64_t     pcgrl_step_bytes(const pcgrl_config* cfg);
 /* Bytes per env of pcgrl_state.records: 4 + n_stats * record_stat_bytes + 2 rounded up to a multiple of 4
  * (0 when cfg.record_stat_bytes == 0). */
 int32_t     pcgrl_record_stride(const pcgrl_config* cfg);
+
+/* Sizes of pcgrl_state.worklist (in int32 elements; 0 = this config has no split path) and of one env's row
+ * of pcgrl_state.cache (bytes; 0 = no incremental search for this config). */
+int64_t     pcgrl_worklist_ints(const pcgrl_config* cfg, int64_t n_envs);
+int32_t     pcgrl_cache_stride(const pcgrl_config* cfg);
 
 /* -- launches ---------------------------------------------------------------------------------- */
 /* One env-step for every env of the shard.  `actions` layout depends on cfg->action_kind. */

@@ -295,15 +295,14 @@ def test_compact_host_io_equals_int32_outputs(problem, rep, shape, controls, mon
             monkeypatch.delenv("PCGRL_HOST_CHUNKS", raising=False)
         act = rng.integers(0, n_act, size=n)
         r, d, s = a.step_host(act.astype(want_act))
-        changed_a = a._pinned["records"].numpy().view(a.record_dtype()).reshape(n)["changed"].copy()
+        changed_a = a._host_io().views[3].copy()
         r, d, s = r.copy(), d.copy(), s.copy()
         rb, db, sb = b.step_host(act.astype(np.int32))
         np.testing.assert_array_equal(r, rb)
         np.testing.assert_array_equal(d, db)
-        # b's int32 stats are copied after its auto-reset ran inside step_host? no: step_host downloads before the
-        # auto-reset launches, like the packed path
+        # both paths download before the auto-reset launches
         np.testing.assert_array_equal(s.astype(np.int32), sb)
-        np.testing.assert_array_equal(changed_a, b.changed.cpu().numpy()) if not d.any() else None
+        np.testing.assert_array_equal(changed_a, b.changed.cpu().numpy())
         assert torch.equal(a.grids, b.grids) and torch.equal(a.stats, b.stats)
         # the device-side int32 views stay valid next to the records
         assert torch.equal(a.reward, b.reward) and torch.equal(a.done, b.done)
