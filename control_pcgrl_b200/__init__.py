@@ -5,6 +5,7 @@ Public surface (mirrors the reference's names):
     make_env(cfg)                          wrapped env as rl/envs.py builds it
     BatchedPcgrlEnv(cfg, n_envs)           N grids on one GPU, one fused launch per step
     PcgrlVectorEnv(cfg, num_envs)          vector-env seam with auto-reset and device observations
+    make_rllib_vector_env(cfg, num_envs)   ray.rllib VectorEnv (vector_reset / reset_at / vector_step) over one shard
     make_config(...)                       dataclass with the reference's cfg field names
 Importing this package never touches CUDA; constructing an env loads libpcgrl_sm100.so and fails
 loudly if it (or a GPU) is missing.
@@ -18,9 +19,9 @@ def __getattr__(name):
     if name in ("BatchedPcgrlEnv",):
         from .batched_env import BatchedPcgrlEnv
         return BatchedPcgrlEnv
-    if name in ("PcgrlVectorEnv",):
-        from .vector_env import PcgrlVectorEnv
-        return PcgrlVectorEnv
+    if name in ("PcgrlVectorEnv", "make_rllib_vector_env"):
+        from . import vector_env
+        return getattr(vector_env, name)
     if name in ("PcgrlEnv", "PcgrlCtrlEnv", "PcgrlEnv3D", "ControlWrapper", "UniformNoiseyTargets", "make_env",
                 "CroppedImagePCGRLWrapper", "ActionMapImagePCGRLWrapper", "CAactionWrapper"):
         from . import envs

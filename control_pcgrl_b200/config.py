@@ -69,6 +69,8 @@ TASK_DEFAULTS = {
                          "jumps-dist": 2, "dist-win": 5, "sol-length": 1}),
     "binary_holey": dict(map_shape=(16, 16), obs_window=(32, 32),
                          weights={"regions": 1, "path-length": 0, "connected-path-length": 1}),
+    # Minecraft2DmazeProblem's own size (minecraft_2D_maze_prob.py:17-18) and reward weights (:24-27)
+    "minecraft_2D_maze": dict(map_shape=(14, 14), obs_window=(28, 28), weights={"regions": 5, "path-length": 1}),
     "minecraft_3D_maze": dict(map_shape=(15, 15, 15), obs_window=(30, 30, 30),
                               weights={"path-length": 100, "n_jump": 100, "regions": 0}),
 }

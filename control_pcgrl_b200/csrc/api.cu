@@ -50,8 +50,8 @@ static int check(const pcgrl_config* c) {
         return fail(PCGRL_E_ARG, "unknown representation");
     const int cells = cells_of(c);
     if (c->row_stride < cells || c->row_stride % 16) return fail(PCGRL_E_ARG, "row_stride must be >= cells and a multiple of 16");
-    static const int k_of[] = {2, 7, 7, 9, 3, 3};
-    if (c->problem < 0 || c->problem > PCGRL_PROB_BINARY_HOLEY) return fail(PCGRL_E_ARG, "unknown problem");
+    static const int k_of[] = {2, 7, 7, 9, 3, 3, 2};
+    if (c->problem < 0 || c->problem > PCGRL_PROB_MINECRAFT_2D_MAZE) return fail(PCGRL_E_ARG, "unknown problem");
     if (c->hole_mode < PCGRL_HOLES_GIVEN || c->hole_mode > PCGRL_HOLES_RANDOM) return fail(PCGRL_E_ARG, "unknown hole_mode");
     if (c->problem == PCGRL_PROB_BINARY_HOLEY && c->ndim != 2) return fail(PCGRL_E_ARG, "binary_holey is a 2D problem");
     if (c->n_stats != k_of[c->problem]) return fail(PCGRL_E_ARG, "n_stats does not match the problem");
@@ -90,11 +90,15 @@ static int check(const pcgrl_config* c) {
     if (sb != 0 && sb != 1 && sb != 2 && sb != 4) return fail(PCGRL_E_ARG, "record_stat_bytes must be 0, 1, 2 or 4");
     return 0;
 }
+// minecraft_2D_maze runs the binary kernels: same stats, its passable tile "AIR" is code 0 like binary's "empty"
+static int kernel_problem(int problem) { return problem == PCGRL_PROB_MINECRAFT_2D_MAZE ? PCGRL_PROB_BINARY : problem; }
 static bool is_bitboard(const pcgrl_config* c) {
-    return c->problem == PCGRL_PROB_BINARY || c->problem == PCGRL_PROB_ZELDA || c->problem == PCGRL_PROB_BINARY_HOLEY;
+    const int k = kernel_problem(c->problem);
+    return k == PCGRL_PROB_BINARY || k == PCGRL_PROB_ZELDA || k == PCGRL_PROB_BINARY_HOLEY;
 }
 static int cache_stride(const pcgrl_config* c) {
-    return bitboard_cache_stride(c->problem, c->ndim, c->dims[0], c->dims[1], c->representation, c->action_kind);
+    return bitboard_cache_stride(kernel_problem(c->problem), c->ndim, c->dims[0], c->dims[1], c->representation,
+                                 c->action_kind);
 }
 // PCGRL_STEP_PATH = fused | split | inc (default inc): which of the equivalent step paths pcgrl_step takes when the
 // caller supplied the buffers for all of them (A/B runs and the path-equivalence tests)
@@ -184,7 +188,8 @@ static int check_state(const pcgrl_state* st) {
     return 0;
 }
 
-static int run(const KParams& p, int problem, void* stream) {
+static int run(const KParams& p, int cfg_problem, void* stream) {
+    const int problem = kernel_problem(cfg_problem);
     bool supported = false;
     cudaError_t e;
     if (problem == PCGRL_PROB_MINECRAFT_3D_MAZE)
@@ -226,8 +231,7 @@ static thread_local HostPipe g_pipe[16];
 
 static int host_chunks(const pcgrl_config* cfg, int64_t n, bool packed) {
     (void)packed;
-    if (cfg->problem != PCGRL_PROB_BINARY && cfg->problem != PCGRL_PROB_ZELDA && cfg->problem != PCGRL_PROB_BINARY_HOLEY)
-        return 1;
+    if (!is_bitboard(cfg)) return 1;
     if (const char* e = getenv("PCGRL_HOST_CHUNKS")) {
         const int v = atoi(e);
         if (v >= 1) return (int)std::min<int64_t>(std::min(v, WL_CHUNKS), std::max<int64_t>(1, n / 256));

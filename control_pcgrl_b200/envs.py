@@ -187,12 +187,21 @@ class PcgrlEnv(spaces.GymEnv):
 
     def __init__(self, cfg, prob=None, rep=None, device="cuda:0"):
         c = normalise(cfg)
+        # the reference builds the problem / representation from the `prob` / `rep` kwargs of the env id
+        # (control_pcgrl/__init__.py:8-37, pcgrl_env.py:44-46); a cfg that names a different pair is a caller bug
+        if prob is not None and prob != c.problem:
+            raise ValueError(f"env id problem {prob!r} != cfg.task.problem {c.problem!r}")
+        if rep is not None and REPRESENTATION_ALIASES[rep] != REPRESENTATION_ALIASES[c.representation]:
+            raise ValueError(f"env id representation {rep!r} != cfg.representation {c.representation!r}")
         self.cfg = cfg
         self.render_mode = None
         self._repr_name = REPRESENTATION_ALIASES[rep or c.representation]
         self.map_shape = c.map_shape
         self.obs_window = c.obs_window
-        action_kind = {"narrow": "int32", "turtle": "int32", "wide": "wide_coords", "cellular": "ca_logits"}[self._repr_name]
+        # MultiActionRepresentation (cfg.act_window, envs/reps/wrappers.py:397-545): the batched env picks the
+        # patch action kind itself
+        action_kind = None if c.act_window is not None else \
+            {"narrow": "int32", "turtle": "int32", "wide": "wide_coords", "cellular": "ca_logits"}[self._repr_name]
         self._b = BatchedPcgrlEnv(cfg, 1, device=device, action_kind=action_kind)
         self._prob = _ProblemProxy(self)
         self._rep = _RepProxy(self)
@@ -205,7 +214,9 @@ class PcgrlEnv(spaces.GymEnv):
         self.static_trgs = self._b.metric_trgs
         self.metric_trgs = self._b.metric_trgs
         sp = self._b.spec
-        self._reward_weights = {k: v / (sp.cond_bounds[k][1] - sp.cond_bounds[k][0]) for k, v in sp.reward_weights.items()}
+        # pcgrl_env.py:82-88; problems without cond_bounds (minecraft_2D_maze) keep their raw weights
+        self._reward_weights = {k: (v / (sp.cond_bounds[k][1] - sp.cond_bounds[k][0]) if k in sp.cond_bounds else v)
+                                for k, v in sp.reward_weights.items()}
         self._ctrl_reward_weights = dict(self._reward_weights)
         self._np_random = np.random.default_rng()
         self.adjust_param(cfg)
@@ -225,7 +236,9 @@ class PcgrlEnv(spaces.GymEnv):
         self._max_iterations = b.max_iterations
         n_tiles, dims = b.n_tiles, b.map_shape
         rep = self._repr_name
-        if rep == "narrow":
+        if b.act_window is not None:                                           # wrappers.py:438-443
+            self.action_space = spaces.MultiDiscrete([n_tiles] * int(np.prod(b.act_window)))
+        elif rep == "narrow":
             self.action_space = spaces.Discrete(n_tiles)                       # narrow_rep.py:65-68
         elif rep == "turtle":
             self.action_space = spaces.Discrete(4 + n_tiles)                   # turtle_rep.py:70-71
@@ -298,7 +311,9 @@ class PcgrlEnv(spaces.GymEnv):
     def _launch_step(self, action):
         b = self._b
         rep = self._repr_name
-        if rep in ("narrow", "turtle"):
+        if b.act_window is not None:
+            a = torch.tensor(np.asarray(action, dtype=np.int32).reshape(1, -1), device=b.device)
+        elif rep in ("narrow", "turtle"):
             a = torch.tensor([int(np.asarray(action).reshape(-1)[0])], dtype=torch.int32, device=b.device)
         elif rep == "wide":
             a = torch.tensor(np.asarray(action, dtype=np.int32).reshape(1, -1), device=b.device)
@@ -350,9 +365,11 @@ class _ObsWrapper(spaces.GymWrapper):
         super().__init__(env)
         b = env.unwrapped._b
         self._crop = b.representation in ("narrow", "turtle")
-        dims = b.obs_window if self._crop else b.map_shape
-        ch = b.n_tiles + 1 if self._crop else b.n_tiles
-        self.observation_space = spaces.Box(low=0, high=1, shape=(*dims, ch), dtype=np.float64)
+        # what _obs() returns: the batched observation (holey problems: window + 2 for the border frame; frozen
+        # tiles: the extra static_builds plane) without ControlWrapper's target planes, which that wrapper adds
+        shp = b.obs_shape()
+        self.observation_space = spaces.Box(low=0, high=1, shape=(*shp[:-1], shp[-1] - 2 * len(b.ctrl_metrics)),
+                                            dtype=np.float64)
         self.action_space = env.action_space
 
     def _obs(self):

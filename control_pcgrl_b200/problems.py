@@ -85,6 +85,19 @@ def binary_holey_spec(map_shape):
     return s
 
 
+def minecraft_2d_maze_spec(map_shape):
+    """minecraft/minecraft_2D_maze_prob.py:15-33, 87-93, 106-115: the binary stats over the tiles
+    AIR / DIRT.  The class is not a controllable problem upstream (no static_trgs / cond_bounds, and its
+    constructor calls Problem.__init__ without the cfg it now requires), so there are no ControlWrapper targets to
+    mirror: the reward it defines is the legacy range reward (regions -> 1, the longer the path the better)."""
+    return ProblemSpec(
+        name="minecraft_2D_maze", tiles=["AIR", "DIRT"], stat_names=["regions", "path-length"],
+        init_probs=[0.5, 0.5], border_tile="DIRT", ndim=2,
+        static_trgs=OrderedDict(), cond_bounds={}, reward_weights={"regions": 5, "path-length": 1},
+        range_bands={"regions": (1, 1), "path-length": (INF, INF)},
+        range_weights={"regions": 5, "path-length": 1})
+
+
 def zelda_spec(map_shape):
     """zelda/zelda_prob.py:20-45 + zelda/zelda_ctrl_prob.py:17-75."""
     h, w = map_shape[0], map_shape[1]
@@ -168,7 +181,8 @@ def minecraft_3d_maze_spec(map_shape):
 
 
 _SPECS = {"binary": binary_spec, "zelda": zelda_spec, "sokoban": sokoban_spec, "smb": smb_spec,
-          "minecraft_3D_maze": minecraft_3d_maze_spec, "binary_holey": binary_holey_spec}
+          "minecraft_3D_maze": minecraft_3d_maze_spec, "binary_holey": binary_holey_spec,
+          "minecraft_2D_maze": minecraft_2d_maze_spec}
 
 
 def get_spec(problem: str, map_shape) -> ProblemSpec:
@@ -182,7 +196,7 @@ def register_spec(name, fn):
     _SPECS[name] = fn
 
 
-PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze", "binary_holey"]
+PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze", "binary_holey", "minecraft_2D_maze"]
 HOLEY_PROBLEMS = ("binary_holey",)
 # envs/reps/__init__.py:11-23 (+ the stale 3D spellings)
 REPRESENTATION_ALIASES = {"narrow": "narrow", "turtle": "turtle", "wide": "wide", "cellular": "cellular",

@@ -80,3 +80,154 @@ class PcgrlVectorEnv:
                 self.episode_length[d] = 0
         obs = b.observe(out=self._obs)
         return obs, reward, torch.zeros_like(done), done, info
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# RLlib seam: rl/train.py:251 registers `make_env` and RLlib then builds
+# num_rollout_workers x num_envs_per_worker Python envs (rl/utils.py:402-415), wrapping each worker's list in its own
+# _VectorizedGymEnv.  This class is that VectorEnv directly: one object, N grids on the GPU, the same
+# vector_reset / reset_at / restart_at / vector_step / get_sub_environments surface, host (numpy) observations.
+# ------------------------------------------------------------------------------------------------------------------
+class _SubEnvView:
+    """What the reference's callbacks and evaluation code read from a sub-environment (rl/callbacks.py:30-116,
+    rl/evaluate.py): metrics, targets and bounds of env `index` of the batch."""
+
+    def __init__(self, owner, index):
+        self._o, self._i = owner, index
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def metrics(self):
+        return self._o.env.stats_dict(self._i)
+
+    _rep_stats = metrics
+
+    @property
+    def ctrl_metrics(self):
+        return self._o.env.ctrl_metrics
+
+    @property
+    def cond_bounds(self):
+        return self._o.env.cond_bounds
+
+    @property
+    def static_trgs(self):
+        return self._o.env.static_trgs
+
+    @property
+    def metric_trgs(self):
+        b = self._o.env
+        row = b.targets[self._i if b.ctrl_metrics else 0].cpu().numpy()
+        return {k: (float(row[j, 0]) if np.isnan(row[j, 1]) else (float(row[j, 0]), float(row[j, 1])))
+                for j, k in enumerate(b.stat_names) if k in b.all_metrics}
+
+    def get_map(self):
+        return self._o.env.maps[self._i].cpu().numpy()
+
+
+def _rllib_base():
+    try:                                             # a real ray install (absent from this image)
+        from ray.rllib.env.vector_env import VectorEnv
+        return VectorEnv
+    except Exception:                                # noqa: BLE001 -- same surface without the base class
+        return object
+
+
+def make_rllib_vector_env(cfg, num_envs: int, device="cuda:0", obs_dtype=np.float32, seed=0, env_offset=0):
+    """-> an RLlib `VectorEnv` (a subclass of ray.rllib.env.vector_env.VectorEnv when ray is importable) whose
+    `num_envs` sub-environments are one BatchedPcgrlEnv shard.  Register it instead of the per-env creator:
+
+        register_env("pcgrl", lambda env_ctx: make_rllib_vector_env(env_ctx, env_ctx["num_envs_per_worker"]))
+
+    Observations are what make_env's wrapper stack returns per env (rl/envs.py:28-66: cropped / full one-hot image
+    with the ControlWrapper target planes), as numpy rows of one pinned host array; rewards / truncation flags /
+    info stats come back in one packed record array (compact host I/O)."""
+    Base = _rllib_base()
+
+    class PcgrlRLlibVectorEnv(Base):
+        def __init__(self):
+            self.env = BatchedPcgrlEnv(cfg, num_envs, device=device, env_offset=env_offset, seed=seed,
+                                       auto_reset=False, compact_host_io=True)
+            b = self.env
+            shp = b.obs_shape()
+            tdt = {np.float32: torch.float32, np.float64: torch.float64, np.uint8: torch.uint8}[np.dtype(obs_dtype).type]
+            self.observation_space = spaces.Box(0, 1, shape=shp, dtype=obs_dtype)
+            rep = b.representation
+            if b.act_window is not None:
+                self.action_space = spaces.MultiDiscrete([b.n_tiles] * int(np.prod(b.act_window)))
+            elif rep == "narrow":
+                self.action_space = spaces.Discrete(b.n_tiles)
+            elif rep == "turtle":
+                self.action_space = spaces.Discrete(4 + b.n_tiles)
+            elif rep == "wide":
+                self.action_space = spaces.Discrete(b.obs_window[0] * b.obs_window[1] * b.n_tiles)
+            else:
+                self.action_space = spaces.Box(0, 1, shape=(b.n_tiles * b.cells,), dtype=np.float32)
+            if Base is not object:
+                super().__init__(self.observation_space, self.action_space, num_envs)
+            self.num_envs = num_envs
+            self._obs_dev = torch.empty((num_envs, *shp), dtype=tdt, device=b.device)
+            self._obs_host = torch.empty((num_envs, *shp), dtype=tdt, pin_memory=True)      # current observations
+            self._new_host = torch.empty((num_envs, *shp), dtype=tdt, pin_memory=True)      # first obs after auto-reset
+            self._fresh = np.zeros(num_envs, dtype=bool)    # envs reset inside the last vector_step, not yet handed out
+            self._views = [_SubEnvView(self, i) for i in range(num_envs)]
+
+        def _observe_into(self, host):
+            self.env.observe(out=self._obs_dev)
+            host.copy_(self._obs_dev, non_blocking=True)
+            torch.cuda.current_stream(self.env.device).synchronize()
+            return host.numpy()
+
+        def vector_reset(self, *, seeds=None, options=None):
+            b = self.env
+            if seeds is not None and seeds[0] is not None:
+                b.seed = int(seeds[0])
+            if b.ctrl_metrics:
+                b.sample_uniform_targets()
+            b.reset()
+            self._fresh[:] = False
+            obs = self._observe_into(self._obs_host)
+            return [obs[i] for i in range(self.num_envs)], [{} for _ in range(self.num_envs)]
+
+        def reset_at(self, index=None, *, seed=None, options=None):
+            i = 0 if index is None else int(index)
+            if self._fresh[i]:                     # already reset (with every other finished env) by vector_step
+                self._fresh[i] = False
+                self._obs_host[i].copy_(self._new_host[i])
+                return self._obs_host.numpy()[i], {}
+            mask = torch.zeros(self.num_envs, dtype=torch.uint8, device=self.env.device)
+            mask[i] = 1
+            self.env.reset(mask=mask)
+            return self._observe_into(self._obs_host)[i], {}
+
+        def restart_at(self, index=None):
+            self.reset_at(index)
+
+        def vector_step(self, actions):
+            b = self.env
+            shape, dt, _ = b._action_layout()
+            r, d, s = b.step_host(np.asarray(actions).astype(dt, copy=False).reshape(shape))
+            obs = self._observe_into(self._obs_host)
+            rewards, dones = r.tolist(), d.astype(bool).tolist()
+            names = b.stat_names
+            it = b.iteration.cpu().numpy()
+            infos = [dict(zip(names, row), iterations=int(k), max_iterations=b.max_iterations)
+                     for row, k in zip(s.tolist(), it.tolist())]
+            if d.any():
+                # RLlib calls reset_at(i) for every finished env next: reset them all in ONE launch now and keep
+                # their first observations ready (the terminal observations above are already on the host)
+                self._fresh[:] = d.astype(bool)
+                b.reset(mask=b.done)
+                self._observe_into(self._new_host)
+            return [obs[i] for i in range(self.num_envs)], rewards, [False] * self.num_envs, dones, infos
+
+        def get_sub_environments(self):
+            return self._views
+
+        def try_render_at(self, index=None):
+            return None
+
+    return PcgrlRLlibVectorEnv()

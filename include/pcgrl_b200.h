@@ -33,7 +33,10 @@ enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGR
        PCGRL_PROB_MINECRAFT_3D_MAZE = 4,
        /* SURVEY 8f rank 2 -- holey problems: stats on the bordered map with an entrance and an exit dug into the
           border (envs/probs/binary/binary_holey_prob.py:59-93, envs/pcgrl_holey_env.py:44-53) */
-       PCGRL_PROB_BINARY_HOLEY = 5 };
+       PCGRL_PROB_BINARY_HOLEY = 5,
+       /* SURVEY 8f rank 4 -- minecraft_2D_maze (envs/probs/minecraft/minecraft_2D_maze_prob.py:87-93): regions and
+          longest path over the "AIR" tile (code 0), i.e. the binary stats under other tile names */
+       PCGRL_PROB_MINECRAFT_2D_MAZE = 6 };
 /* where reset takes the entrance / exit holes of a holey problem from (envs/probs/holey_prob.py:32-60 gen_holes) */
 enum {
     PCGRL_HOLES_GIVEN = 0,   /* leave pcgrl_state.holes as the caller set them (the reference's _hole_queue) */

@@ -251,6 +251,47 @@ def save_stats_fixture(problem, grids, name=None):
     print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
 
 
+# ------------------------------------------------------------------------------------------ minecraft_2D_maze
+def minecraft_2d_maze_fixture():
+    """Minecraft2DmazeProblem.get_stats / get_reward (minecraft_2D_maze_prob.py:87-115), run verbatim.  The class
+    cannot be constructed at this commit (its __init__ calls Problem.__init__() without the cfg it now requires,
+    :15-16, and never sets the render_path its get_stats reads, :29), so the instance is made without __init__ and
+    given the attributes those two methods read."""
+    R.install()
+    H = R.load_helpers()
+    sys.modules["control_pcgrl.envs.probs.minecraft.mc_render"].spawn_2D_maze = lambda *a, **k: None
+    sys.modules["control_pcgrl.envs.probs.minecraft.mc_render"].spawn_2D_path = lambda *a, **k: None
+    sys.modules.setdefault("PIL", __import__("types").ModuleType("PIL")).Image = object
+    from control_pcgrl.envs.probs.minecraft.minecraft_2D_maze_prob import Minecraft2DmazeProblem
+    p = object.__new__(Minecraft2DmazeProblem)
+    p.render_path = False
+    p._reward_weights = {"regions": 5, "path-length": 1}
+    rng = np.random.default_rng(77)
+    arrays = {}
+    for i, (shape, n, dens) in enumerate([((14, 14), 240, (0.2, 0.35, 0.5, 0.65, 0.8)), ((16, 16), 60, (0.5, 0.7)),
+                                           ((9, 13), 60, (0.4, 0.6)), ((5, 5), 40, (0.5,))]):
+        gs = np.stack([(rng.random(shape) < dens[k % len(dens)]).astype(np.int8) for k in range(n)])
+        gs[0][:] = 0
+        gs[1][:] = 1
+        st = []
+        for g in gs:
+            smap = H.h2.get_string_map(g, ["AIR", "DIRT"])
+            s = p.get_stats(smap)
+            st.append([int(s["regions"]), int(s["path-length"])])
+        arrays[f"grids_{i}"], arrays[f"stats_{i}"] = gs, np.array(st, dtype=np.int64)
+    arrays["stat_names"] = np.array(STAT_NAMES["minecraft_2D_maze"])
+    path = os.path.join(OUT, "stats_minecraft_2D_maze.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
+    new = np.stack([rng.integers(0, 60, size=300), rng.integers(0, 100, size=300)], axis=1)
+    old = np.stack([rng.integers(0, 60, size=300), rng.integers(0, 100, size=300)], axis=1)
+    rew = [float(p.get_reward(dict(zip(STAT_NAMES["minecraft_2D_maze"], a.tolist())),
+                              dict(zip(STAT_NAMES["minecraft_2D_maze"], b.tolist())))) for a, b in zip(new, old)]
+    path = os.path.join(OUT, "legacy_reward_minecraft_2D_maze.npz")
+    np.savez_compressed(path, new=new, old=old, reward=np.array(rew))
+    print("wrote", path)
+
+
 # ------------------------------------------------------------------------------------------ holey problems
 def ref_holey_problem(h, w):
     """The reference's BinaryHoleyProblem cannot be constructed at this commit (its __init__ calls
@@ -578,6 +619,7 @@ def main(which=None):
                                                          n_envs=3, obs_every=17),
     })
     jobs["stats_binary_holey"] = binary_holey_fixture
+    jobs["stats_minecraft_2D_maze"] = minecraft_2d_maze_fixture
     jobs["stats_maze3d_holey"] = maze3d_holey_fixture
     for k, fn in jobs.items():
         if which and k not in which:

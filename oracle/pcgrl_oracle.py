@@ -30,6 +30,7 @@ TILES = {
     "smb": ["empty", "solid", "enemy", "brick", "question", "coin", "tube"],        # smb_prob.py:12
     "minecraft_3D_maze": ["AIR", "DIRT"],                                           # minecraft_3D_maze_prob.py:26
     "binary_holey": ["empty", "solid"],                                             # binary_holey_prob.py:12-14
+    "minecraft_2D_maze": ["AIR", "DIRT"],                                           # minecraft_2D_maze_prob.py:40-41
 }
 STAT_NAMES = {
     "binary": ["regions", "path-length"],
@@ -39,6 +40,7 @@ STAT_NAMES = {
             "dist-win", "sol-length"],
     "minecraft_3D_maze": ["regions", "path-length", "n_jump"],
     "binary_holey": ["regions", "path-length", "connected-path-length"],
+    "minecraft_2D_maze": ["regions", "path-length"],
 }
 # tile init probabilities used by reset when no grid is supplied
 INIT_PROBS = {
@@ -47,6 +49,7 @@ INIT_PROBS = {
     "sokoban": [0.45, 0.4, 0.05, 0.05, 0.05],                           # sokoban_prob.py:32-38
     "smb": [0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02],                   # smb_prob.py:18
     "minecraft_3D_maze": [1.0, 0.0],                                    # minecraft_3D_maze_prob.py:37
+    "minecraft_2D_maze": [0.5, 0.5],                                    # minecraft_2D_maze_prob.py:19
 }
 
 _ZELDA_WALK = [0, 2, 3, 5, 7, 6]        # empty, player, key, bat, spider, scorpion (zelda_ctrl_prob.py:101-104)
@@ -173,6 +176,7 @@ RANGE_BANDS = {
                 "dist-win": (-_INF, -_INF), "sol-length": (_INF, _INF)},
     "smb": {"dist-floor": (0, 0), "disjoint-tubes": (0, 0), "enemies": (10, 30), "empty": (900, _INF),
             "noise": (0, 0), "jumps": (20, _INF), "jumps-dist": (0, 0), "dist-win": (0, 0)},
+    "minecraft_2D_maze": {"regions": (1, 1), "path-length": (_INF, _INF)},   # minecraft_2D_maze_prob.py:106-115
 }
 RANGE_WEIGHTS = {
     "binary": {"regions": 100, "path-length": 100},
@@ -180,6 +184,7 @@ RANGE_WEIGHTS = {
     "sokoban": {"player": 3, "crate": 2, "target": 2, "regions": 5, "ratio": 2, "dist-win": 0.0, "sol-length": 1},
     "smb": {"dist-floor": 2, "disjoint-tubes": 1, "enemies": 1, "empty": 1, "noise": 4, "jumps": 2, "jumps-dist": 2,
             "dist-win": 5},
+    "minecraft_2D_maze": {"regions": 5, "path-length": 1},                   # minecraft_2D_maze_prob.py:24-27
 }
 
 
@@ -279,7 +284,8 @@ def valid_holes(entrance, exit_, h, w):
 def get_stats(problem, grid, holes=None):
     if problem == "binary_holey":
         return binary_holey_stats(grid, holes)
-    if problem == "binary":
+    if problem in ("binary", "minecraft_2D_maze"):
+        # minecraft_2D_maze_prob.py:87-93: the same two helpers over ["AIR"], tile code 0 like binary's "empty"
         return binary_stats(grid)
     if problem == "zelda":
         return zelda_stats(grid)
@@ -316,6 +322,9 @@ def problem_constants(problem, map_shape):
         return dict(static_trgs={"regions": 1, "path-length": mp},
                     cond_bounds={"regions": (0, w * np.ceil(h / 2)), "path-length": (0, mp)},
                     default_weights={"regions": 100, "path-length": 100})
+    if problem == "minecraft_2D_maze":
+        # minecraft_2D_maze_prob.py:15-33: not a controllable problem upstream (no static_trgs / cond_bounds)
+        return dict(static_trgs={}, cond_bounds={}, default_weights={"regions": 5, "path-length": 1})
     if problem == "binary_holey":
         # binary_holey_prob.py:19-42 on top of BinaryProblem's constructor
         h, w = map_shape

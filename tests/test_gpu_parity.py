@@ -23,7 +23,8 @@ def _mk(problem, rep, map_shape, n, **kw):
 
 
 @pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
-                                          ("maze3d", "minecraft_3D_maze"), ("sokoban", "sokoban"), ("smb", "smb")])
+                                          ("maze3d", "minecraft_3D_maze"), ("sokoban", "sokoban"), ("smb", "smb"),
+                                          ("minecraft_2D_maze", "minecraft_2D_maze")])
 def test_stats_kernel_matches_reference_fixtures(name, problem):
     _, groups = load_stats(name)
     total = 0

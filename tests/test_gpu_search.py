@@ -160,7 +160,9 @@ def test_search_full_size_properties(problem, rep, shape, n, n_steps):
 
 
 @pytest.mark.parametrize("problem,rep,shape,n_act", [("binary", "narrow", (16, 16), 2), ("zelda", "turtle", (7, 11), 12),
-                                                     ("sokoban", "narrow", (5, 5), 5), ("smb", "narrow", (12, 10), 7)])
+                                                     ("sokoban", "narrow", (5, 5), 5), ("smb", "narrow", (12, 10), 7),
+                                                     ("minecraft_2D_maze", "narrow", (14, 14), 2),
+                                                     ("minecraft_2D_maze", "turtle", (14, 14), 6)])
 def test_legacy_range_reward_mode(problem, rep, shape, n_act):
     """reward_mode='range' (Problem.get_reward / helper.get_range_reward) vs the oracle, step by step, and the
     kernel's band arithmetic vs the reference-generated legacy_reward fixture."""

@@ -7,7 +7,8 @@ from tests.golden_util import TRACES, TRACES_OPEN_ENDED, TRACES_SEARCH, TRACES_W
 
 
 @pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
-                                          ("sokoban", "sokoban"), ("smb", "smb"), ("maze3d", "minecraft_3D_maze")])
+                                          ("sokoban", "sokoban"), ("smb", "smb"), ("maze3d", "minecraft_3D_maze"),
+                                          ("minecraft_2D_maze", "minecraft_2D_maze")])
 def test_stats_match_reference(name, problem):
     names, groups = load_stats(name)
     assert names == O.STAT_NAMES[problem]
@@ -92,3 +93,9 @@ def test_legacy_range_reward_matches_reference():
         for a, b, want in zip(z[f"{problem}_new"], z[f"{problem}_old"], z[f"{problem}_reward"]):
             got = O.legacy_reward(problem, dict(zip(names, a.tolist())), dict(zip(names, b.tolist())))
             assert got == want, (problem, a, b, got, want)
+    # minecraft_2D_maze: Minecraft2DmazeProblem.get_reward, minecraft_2D_maze_prob.py:106-115
+    z = np.load(os.path.join(GOLDEN, "legacy_reward_minecraft_2D_maze.npz"))
+    names = O.STAT_NAMES["minecraft_2D_maze"]
+    for a, b, want in zip(z["new"], z["old"], z["reward"]):
+        got = O.legacy_reward("minecraft_2D_maze", dict(zip(names, a.tolist())), dict(zip(names, b.tolist())))
+        assert got == want, (a, b, got, want)
