@@ -441,6 +441,13 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
                obs=[], obs_step=[], obs0=[], changes=[], trg=[], grids_step=[], static=[])
     for e in range(n_envs):
         env = R.make_wrapped_env(cfg, raw_only=raw_only)
+        # every random draw of the reference itself (turtle start, frozen-tile mask and walls; the env's own
+        # generator and the global numpy / python ones some wrappers use) is seeded, so a trace regenerates byte
+        # for byte and a change of the generator cannot be mistaken for a change of the reference
+        env.unwrapped.seed(100003 * seed + 17 * e + 1)
+        np.random.seed(100003 * seed + 17 * e + 2)
+        import random as _random
+        _random.seed(100003 * seed + 17 * e + 3)
         if init_p is None:
             g0 = rng.integers(0, n_tiles, size=map_shape).astype(np.uint8)
         else:

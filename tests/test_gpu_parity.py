@@ -151,6 +151,59 @@ def test_full_size_properties_binary_narrow():
     assert int(env.stats[:, 0].max()) <= 128 and int(env.stats[:, 1].max()) <= 136 and int(env.stats.min()) >= 0
 
 
+@pytest.mark.parametrize("problem,rep,shape,controls", [
+    ("binary", "wide", (16, 16), ["regions", "path-length"]),     # BASELINE config 2 at its stated size
+    ("zelda", "turtle", (7, 11), None),                           # BASELINE config 3 at its stated size
+])
+def test_full_size_properties_configs_2_and_3(problem, rep, shape, controls):
+    """65 536 envs of binary-wide + ControlWrapper targets (per-env regions / path-length) and of zelda-turtle:
+    size-independent properties on the whole batch plus the oracle on a 256-env sample, step by step (stats and
+    maps bit-exact, rewards to 1e-6 of the oracle's fp64 loss difference under the env's own targets)."""
+    from oracle import pcgrl_oracle as O
+    n, n_or = 65536, 256
+    kw = dict(obs_window=shape) if rep == "wide" else {}
+    env = _mk(problem, rep, shape, n, seed=9, controls=controls, **kw)
+    if controls:
+        g0 = torch.Generator(device=env.device).manual_seed(2)
+        env.sample_uniform_targets(generator=g0)
+    env.reset()
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    sample = np.linspace(0, n - 1, n_or).astype(np.int64)
+    maps0, pos0 = env.maps.cpu().numpy(), env.pos.cpu().numpy()
+    trg = env.targets.cpu().numpy()
+    weights = {k: v for k, v in env.metric_weights.items()}
+    oracles = []
+    for e in sample:
+        o = O.OracleEnv(problem, rep, shape, weights=weights, controls=controls)
+        targets = {k: float(trg[e, env.stat_names.index(k), 0]) for k in (controls or [])}
+        o.reset(maps0[e], pos=pos0[e, :2], targets=targets)
+        oracles.append(o)
+    n_act = {"turtle": 4 + env.n_tiles, "wide": shape[0] * shape[1] * env.n_tiles}[rep]
+    g = torch.Generator(device=env.device).manual_seed(0)
+    prev_stats, prev_maps = env.stats.clone(), env.maps.clone()
+    for t in range(48):
+        a = torch.randint(0, n_act, (n,), generator=g, device=env.device, dtype=torch.int32)
+        reward, done = env.step(a)
+        ch = env.changed.bool()
+        assert torch.equal(env.stats[~ch], prev_stats[~ch]) and float(reward[~ch].abs().max()) == 0.0
+        diff = (env.maps != prev_maps).flatten(1).sum(1)
+        assert torch.equal(diff, ch.long())                       # one cell per changed env, none elsewhere
+        assert not bool(done.any())
+        prev_stats, prev_maps = env.stats.clone(), env.maps.clone()
+        a_h, r_h, st_h, maps_h = a.cpu().numpy(), reward.cpu().numpy(), env.stats.cpu().numpy(), env.maps.cpu().numpy()
+        for e, o in zip(sample, oracles):
+            act = int(a_h[e])
+            if rep == "wide":
+                act = O.actionmap_unravel(act, shape[0], shape[1], env.n_tiles)
+            r, _, _ = o.step(act)
+            assert st_h[e].tolist() == O.stats_vector(problem, o.stats), (t, e)
+            assert np.array_equal(maps_h[e], o.grid), (t, e)
+            assert r_h[e] == pytest.approx(float(r), rel=1e-6, abs=1e-7), (t, e)
+    assert torch.equal(env.compute_stats(env.maps), env.stats)    # incremental == recomputed from scratch
+    assert torch.equal(env.iteration, torch.full_like(env.iteration, 48))
+    env.check_status()
+
+
 def test_episode_end_and_auto_reset():
     n = 512
     env = _mk("binary", "narrow", (16, 16), n, auto_reset=True, max_board_scans=0.05)   # 256*0.05+1 = 13.8
