@@ -214,7 +214,8 @@ static int run(const KParams& p, int cfg_problem, void* stream) {
         return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet (or scratch is NULL although "
                                          "pcgrl_scratch_bytes() > 0)");
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    // sokoban: step kernel + BFS jobs + A* jobs + combine (step_sokoban.cu)
+    g_launches.fetch_add(problem == PCGRL_PROB_SOKOBAN ? 4 : 1, std::memory_order_relaxed);
     return 0;
 }
 // Chunked, stream-pipelined host step: the shard is cut into chunks of whole CTA tiles; chunk c's action

@@ -356,13 +356,16 @@ __device__ __forceinline__ bool step_counters(const KParams& p, int64_t gid, int
 
 // Phase D for one env: reward = loss(new stats) - loss(old stats) in fp64 (or the range-reward sum), then the new
 // stats replace the old ones (int32 view and packed record).
+// `old` (optional): the stats the reward is measured from, when p.stats no longer holds them (sokoban's deferred
+// solver jobs: the step kernel already stored provisional stats there).
 template <int K>
-__device__ __forceinline__ void finish_env(const KParams& p, int64_t gid, const int32_t (&nw)[K]) {
+__device__ __forceinline__ void finish_env(const KParams& p, int64_t gid, const int32_t (&nw)[K],
+                                           const int32_t* old = nullptr) {
     int32_t* st = p.stats + gid * K;
     if (p.mode == MODE_STEP) {
         int32_t od[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) od[k] = st[k];
+        for (int k = 0; k < K; ++k) od[k] = old ? old[k] : st[k];
         const double* trg = p.targets + (p.targets_per_env ? gid * K * 2 : 0);
         const double r = p.reward_mode == PCGRL_REWARD_RANGE
                              ? range_reward_sum(nw, od, trg, p.weights, K)
