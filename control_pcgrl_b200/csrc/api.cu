@@ -11,7 +11,8 @@
 
 namespace pcgrl {
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
-cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, bool incremental, bool& supported);
+cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, int incremental, bool& supported,
+                                  int& n_launches);
 int bitboard_cache_stride(int problem, int ndim, int d0, int d1, int rep, int action_kind);
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
@@ -100,13 +101,21 @@ static int cache_stride(const pcgrl_config* c) {
     return bitboard_cache_stride(kernel_problem(c->problem), c->ndim, c->dims[0], c->dims[1], c->representation,
                                  c->action_kind);
 }
-// PCGRL_STEP_PATH = fused | split | inc (default inc): which of the equivalent step paths pcgrl_step takes when the
-// caller supplied the buffers for all of them (A/B runs and the path-equivalence tests)
-static int step_path() {
-    const char* e = getenv("PCGRL_STEP_PATH");
-    if (!e) return 2;
-    return !strcmp(e, "fused") ? 0 : !strcmp(e, "split") ? 1 : 2;
+// PCGRL_STEP_PATH = fused | split | inc | incfused (default incfused): which of the equivalent step paths pcgrl_step
+// takes when the caller supplied the buffers for all of them (A/B runs and the path-equivalence tests)
+static int path_of(const char* e, int dflt) {
+    if (!e) return dflt;
+    return !strcmp(e, "fused") ? 0 : !strcmp(e, "split") ? 1 : !strcmp(e, "inc") ? 2 : !strcmp(e, "incfused") ? 3 : dflt;
 }
+// Measured on B200, binary 16x16, ms per step of a shard of 64 Ki / 256 Ki / 512 Ki / 1 Mi envs:
+//   fused 0.066 / 0.131 / 0.220 / 0.385   inc (3 launches) 0.063 / 0.114 / 0.175 / 0.304   incfused 0.058 / 0.122 / 0.203 / 0.367
+// so a plain pcgrl_step takes the one-launch incremental kernel for small shards and the three-launch one above.
+static int step_path(int64_t n_envs) { return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (160 << 10) ? 3 : 2); }
+// Chunks of the host pipeline run on different streams.  With the search kernel of the three-launch incremental
+// path limited to 3 CTAs per SM (PCGRL_INC_CTAS_PER_SM_HOST) the memory-bound update / output kernels of the
+// neighbouring chunks run NEXT TO it: e2e 2.60e9 env-steps/s at 4 chunks, against 2.24e9 with the fused kernel and
+// 2.11e9 when the search holds every SM for itself (8 CTAs per SM); shards without a search cache keep the fused kernel
+static int host_chunk_path(bool has_cache) { return has_cache ? path_of(getenv("PCGRL_HOST_PATH"), 2) : 0; }
 static int action_elem(const pcgrl_config* c) { return c->action_elem_bytes ? c->action_elem_bytes : 4; }
 static int record_stride(const pcgrl_config* c) {
     return c->record_stat_bytes ? (4 + c->n_stats * c->record_stat_bytes + 2 + 3) / 4 * 4 : 0;
@@ -188,7 +197,7 @@ static int check_state(const pcgrl_state* st) {
     return 0;
 }
 
-static int run(const KParams& p, int cfg_problem, void* stream) {
+static int run(const KParams& p, int cfg_problem, void* stream, int force_path = -1) {
     const int problem = kernel_problem(cfg_problem);
     bool supported = false;
     cudaError_t e;
@@ -199,12 +208,13 @@ static int run(const KParams& p, int cfg_problem, void* stream) {
     else if (problem == PCGRL_PROB_SMB)
         e = launch_smb(p, (cudaStream_t)stream, supported);
     else {
-        const int path = step_path();
+        const int path = force_path >= 0 ? force_path : step_path(p.n_envs);
         if (p.mode == MODE_STEP && p.worklist && path > 0) {
-            e = launch_bitboard_split(p, problem, (cudaStream_t)stream, path == 2, supported);
+            int n_launches = 0;
+            e = launch_bitboard_split(p, problem, (cudaStream_t)stream, path - 1, supported, n_launches);
             if (supported) {
                 if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-                g_launches.fetch_add(3, std::memory_order_relaxed);
+                g_launches.fetch_add(n_launches, std::memory_order_relaxed);
                 return 0;
             }
         }
@@ -303,7 +313,7 @@ int32_t pcgrl_record_stride(const pcgrl_config* cfg) {
 // pcgrl_state.worklist (host pipeline: st is a sub-range starting wl_off envs into the shard and `wl_base` is the
 // parent's buffer); a plain pcgrl_step is chunk 0 at offset 0 of its own buffer.
 static int32_t step_launch(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream,
-                           int32_t* wl_base, int wl_chunk, int64_t wl_off) {
+                           int32_t* wl_base, int wl_chunk, int64_t wl_off, int force_path = -1) {
     int r = check(cfg);
     if (r) return r;
     if ((r = check_state(st))) return r;
@@ -317,7 +327,8 @@ static int32_t step_launch(const pcgrl_config* cfg, const pcgrl_state* st, const
     }
     p.mode = MODE_STEP;
     p.actions = actions;
-    return run(p, cfg->problem, stream);
+    p.host_chunk = force_path >= 0;
+    return run(p, cfg->problem, stream, force_path);
 }
 
 int32_t pcgrl_step(const pcgrl_config* cfg, const pcgrl_state* st, const void* actions, void* stream) {
@@ -475,7 +486,8 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
             (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
             return cuda_fail(e, "H2D actions");
         // every chunk gets its own header and its own body range of the shard's work list
-        if ((r = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off))) return r;
+        if ((r = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off,
+                             host_chunk_path(st->worklist && st->cache && cache_stride(cfg) > 0)))) return r;
         if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
             return cuda_fail(e, "D2H records");
         if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)

@@ -75,6 +75,7 @@ struct KParams {
     int32_t* worklist;            // its body: [2 ints per env (env, cell) | n_stats ints per env]
     uint8_t* cache;               // [N, cache_stride]
     int32_t cache_stride;
+    int32_t host_chunk;           // 1: this launch is one chunk of the host pipeline (other chunks run beside it)
 };
 
 // one scalar action (narrow / turtle / flat wide) in the width the caller chose (cfg.action_elem_bytes)

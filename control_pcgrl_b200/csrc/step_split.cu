@@ -24,6 +24,7 @@
 // Reference path replaced: the same as step_bitboard.cu (envs/pcgrl_env.py:267-342, envs/reps/*_rep.py,
 // envs/probs/binary/binary_prob.py:152-158, envs/probs/zelda/zelda_ctrl_prob.py:90-168, envs/helper.py:200-276,
 // control_wrappers.py:216-244, 318-345).
+#include <cstdlib>
 #include "pcgrl_device.cuh"
 #include "step_common.cuh"
 #include "bitboard_machines.cuh"
@@ -36,6 +37,11 @@ namespace pcgrl {
 #ifndef PCGRL_INC_CTAS_PER_SM
 #define PCGRL_INC_CTAS_PER_SM 8      // 128-thread CTAs of the incremental search resident per SM (A/B 4 / 6 / 8 / 12 at
                                      // R=3: 0.412 / 0.393 / 0.384 / 0.378 ms per step)
+#endif
+#ifndef PCGRL_INC_CTAS_PER_SM_HOST
+#define PCGRL_INC_CTAS_PER_SM_HOST 3 // the same inside the host pipeline: most of the SM's registers stay free, so the
+                                     // update / output kernels of the neighbouring chunks run next to the search
+                                     // (e2e at 4 chunks, 2 / 3 / 4 / 5 / 8 CTAs per SM: 2.48 / 2.60 / 2.51 / 2.36 / 2.11e9)
 #endif
 #ifndef PCGRL_INC_MIN_CLAIM
 #define PCGRL_INC_MIN_CLAIM 12       // lanes that must be waiting before a warp hands out new items: the claim / init
@@ -502,6 +508,121 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_step_inc: the whole binary env step in ONE launch around the incremental search (no global work list).
+// Every warp owns a contiguous slice of the shard's envs and loops over three kinds of work, each issued with
+// (nearly) all 32 lanes:
+//   update  the next 32 envs of the slice: representation update, counters, done, zero reward for unchanged
+//           maps (thread-per-env, as k_split_act); the changed ones go into the warp's item ring in shared memory;
+//   search  lanes pick items from the ring as they become free (at least PCGRL_INC_MIN_CLAIM at a time) and run
+//           BinaryIncMachine trips; a finished lane writes its env's cache row and parks (env, regions,
+//           path-length) in the warp's result ring;
+//   output  once 32 results wait (or nothing else is left): one lane per result does the fp64 reward and writes
+//           stats / reward / packed record (as k_split_out).
+// The update and output passes are memory-latency work; in the split path they were two separate kernels (42 +
+// 30 us of the 303 us step at 1 Mi envs) during which the ALU pipes idled, here other warps' searches cover them.
+// ------------------------------------------------------------------------------------------------
+__device__ __noinline__ bool inc_update_env(const KParams& p, int64_t gid, int* cell) {
+    return step_counters(p, gid, apply_action(p, gid, cell));
+}
+__device__ __noinline__ void inc_output_env(const KParams& p, int64_t env, int regions, int path) {
+    const int32_t nw[2] = {regions, path};
+    finish_env<2>(p, env, nw);
+}
+
+#ifndef PCGRL_STEP_INC_MIN_CTAS
+#define PCGRL_STEP_INC_MIN_CTAS 6
+#endif
+template <int NW, bool TWO>
+__global__ void __launch_bounds__(STAT_THREADS, PCGRL_STEP_INC_MIN_CTAS) k_step_inc(const __grid_constant__ KParams p) {
+    using M = BinaryIncMachine<NW, TWO>;
+    constexpr int WARPS = STAT_THREADS / 32;
+    constexpr int RING = 64;
+    __shared__ uint32_t s_work[STAT_THREADS * M::SMEM_WORDS];
+    __shared__ int2 s_items[WARPS][RING];     // (env, cell) waiting for a lane
+    __shared__ int4 s_res[WARPS][RING];       // (env, regions, path-length, -) waiting for the output pass
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+    const int64_t gw = (int64_t)blockIdx.x * WARPS + warp;
+    const int64_t per = ((p.n_envs + n_warps - 1) / n_warps + 31) / 32 * 32;
+    int64_t e_next = min(p.n_envs, gw * per);
+    const int64_t e_hi = min(p.n_envs, e_next + per);
+    if (e_next >= e_hi) return;
+    int2* items = s_items[warp];
+    int4* res = s_res[warp];
+    const int W = p.d1;
+    int it_head = 0, it_cnt = 0, res_head = 0, res_cnt = 0;     // warp-uniform
+    M m;
+    bool active = false;
+    int64_t env = 0;
+    for (;;) {
+        // ---- update: refill the item ring from the warp's env slice
+        if (it_cnt < 32 && e_next < e_hi) {
+            const int64_t gid = e_next + lane;
+            int cell = -1;
+            const bool need = gid < e_hi && inc_update_env(p, gid, &cell);
+            const unsigned bal = __ballot_sync(0xffffffffu, need);
+            if (need) items[(it_head + it_cnt + __popc(bal & lt)) & (RING - 1)] = make_int2((int)gid, cell);
+            it_cnt += __popc(bal);
+            e_next += 32;
+            __syncwarp();
+        }
+        const bool drained = e_next >= e_hi;
+        // ---- hand items to free lanes
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && it_cnt > 0 && (__popc(idle) >= PCGRL_INC_MIN_CLAIM || idle == 0xffffffffu || drained)) {
+            const int rank = __popc(idle & lt);
+            if (!active && rank < it_cnt) {
+                const int2 it = items[(it_head + rank) & (RING - 1)];
+                env = it.x;
+                const int y = it.y / W, x = it.y - y * W;
+                const int bitpos = TWO ? y * 16 + x : y * 32 + x;
+                const int32_t* st = p.stats + env * 2;
+                m.init(s_work + tid * M::SMEM_WORDS, (const uint32_t*)(p.cache + env * p.cache_stride), bitpos, st[0], st[1]);
+                active = true;
+            }
+            const int taken = min(__popc(idle), it_cnt);
+            it_head += taken;
+            it_cnt -= taken;
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        // ---- output: 32 results at a time, or whatever is left at the end
+        if (res_cnt >= 32 || (res_cnt > 0 && !act && it_cnt == 0 && drained)) {
+            const int n_out = min(32, res_cnt);
+            if (lane < n_out) {
+                const int4 r = res[(res_head + lane) & (RING - 1)];
+                inc_output_env(p, r.x, r.y, r.z);
+            }
+            res_head += n_out;
+            res_cnt -= n_out;
+            __syncwarp();
+        }
+        if (!act) {
+            if (it_cnt == 0 && drained && res_cnt == 0) break;
+            continue;
+        }
+        // ---- search: one trip of every active lane
+        bool finished = false;
+        int out[2] = {0, 0};
+        if (active) {
+            bool alive = m.expand();
+#pragma unroll
+            for (int r = 1; r < PCGRL_INC_EXPAND_R; ++r)
+                if (alive) alive = m.expand();
+            if (!alive && m.transition()) {
+                m.finish(out, (uint32_t*)(p.cache + env * p.cache_stride));
+                finished = true;
+                active = false;
+            }
+        }
+        const unsigned fin = __ballot_sync(0xffffffffu, finished);
+        if (finished) res[(res_head + res_cnt + __popc(fin & lt)) & (RING - 1)] = make_int4((int)env, out[0], out[1], 0);
+        res_cnt += __popc(fin);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_split_out
 // ------------------------------------------------------------------------------------------------
 template <int K>
@@ -530,6 +651,16 @@ __global__ void __launch_bounds__(OUT_THREADS) k_split_out(const KParams p) {
 // ------------------------------------------------------------------------------------------------
 // host-side dispatch
 // ------------------------------------------------------------------------------------------------
+// resident CTAs per SM of the persistent incremental kernels; PCGRL_INC_CPS overrides the compiled default (A/B)
+static int inc_ctas_per_sm(bool host_chunk) {
+    static int env_v = -1;
+    if (env_v < 0) {
+        const char* e = getenv("PCGRL_INC_CPS");
+        env_v = e ? atoi(e) : 0;
+    }
+    if (env_v > 0) return env_v;
+    return host_chunk ? PCGRL_INC_CTAS_PER_SM_HOST : PCGRL_INC_CTAS_PER_SM;
+}
 static int g_n_sm = 0;
 static cudaError_t sm_count(int& n) {
     if (!g_n_sm) {
@@ -543,20 +674,30 @@ static cudaError_t sm_count(int& n) {
 }
 
 template <class Machine, int NW, bool TWO>
-static cudaError_t launch_split(const KParams& p, cudaStream_t s, bool incremental) {
+static cudaError_t launch_split(const KParams& p, cudaStream_t s, int incremental) {
     constexpr int K = Machine::Prob::K;
     const int64_t n = p.n_envs;
     if (n == 0) return cudaSuccess;
     cudaError_t e;
+    if constexpr (Machine::HAS_CACHE && TWO) {
+        if (incremental == 2) {     // the whole step in one launch (k_step_inc)
+            int n_sm = 0;
+            if ((e = sm_count(n_sm)) != cudaSuccess) return e;
+            const int64_t want = (n + STAT_THREADS - 1) / STAT_THREADS;
+            const int64_t cap = (int64_t)n_sm * inc_ctas_per_sm(p.host_chunk != 0);
+            k_step_inc<NW, TWO><<<(unsigned)(want < cap ? want : cap), STAT_THREADS, 0, s>>>(p);
+            return cudaGetLastError();
+        }
+    }
     k_split_act<<<(unsigned)((n + ACT_THREADS - 1) / ACT_THREADS), ACT_THREADS, 0, s>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     bool ran_inc = false;
     if constexpr (Machine::HAS_CACHE && TWO) {
-        if (incremental) {
+        if (incremental == 1) {
             int n_sm = 0;
             if ((e = sm_count(n_sm)) != cudaSuccess) return e;
             const int64_t want = (n + STAT_THREADS - 1) / STAT_THREADS;
-            const int64_t cap = (int64_t)n_sm * PCGRL_INC_CTAS_PER_SM;
+            const int64_t cap = (int64_t)n_sm * inc_ctas_per_sm(p.host_chunk != 0);
             k_split_stats_inc<NW, TWO><<<(unsigned)(want < cap ? want : cap), STAT_THREADS, 0, s>>>(p);
             ran_inc = true;
         }
@@ -571,7 +712,7 @@ static cudaError_t launch_split(const KParams& p, cudaStream_t s, bool increment
 }
 
 template <template <int, bool> class Machine>
-static cudaError_t dispatch_split(const KParams& p, cudaStream_t s, bool incremental, bool& supported) {
+static cudaError_t dispatch_split(const KParams& p, cudaStream_t s, int incremental, bool& supported) {
     const int H = p.d0, W = p.d1;
     supported = p.ndim == 2;
     if (!supported) return cudaSuccess;
@@ -583,8 +724,8 @@ static cudaError_t dispatch_split(const KParams& p, cudaStream_t s, bool increme
         return launch_split<Machine<8, true>, 8, true>(p, s, incremental);
     }
     if (W <= 32 && H <= 32) {
-        if (H <= 16) return launch_split<Machine<16, false>, 16, false>(p, s, false);
-        return launch_split<Machine<32, false>, 32, false>(p, s, false);
+        if (H <= 16) return launch_split<Machine<16, false>, 16, false>(p, s, 0);
+        return launch_split<Machine<32, false>, 32, false>(p, s, 0);
     }
     supported = false;
     return cudaSuccess;
@@ -592,16 +733,24 @@ static cudaError_t dispatch_split(const KParams& p, cudaStream_t s, bool increme
 
 // MODE_STEP of a bit-board problem through the split path.  `incremental` asks for the cached incremental search
 // (binary only; needs p.cache).  Three kernels are launched: *launches is incremented by the caller accordingly.
-cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, bool incremental, bool& supported) {
+// incremental: 0 = from-scratch searches, 1 = incremental search as the middle kernel of the split path, 2 = the
+// fused incremental step (k_step_inc, one launch).  *n_launches = kernels launched.
+cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, int incremental, bool& supported,
+                                  int& n_launches) {
     supported = false;
+    n_launches = 3;
     if (p.mode != MODE_STEP || !p.worklist || p.rep == PCGRL_REP_CELLULAR) return cudaSuccess;
-    if (problem == PCGRL_PROB_BINARY) return dispatch_split<BinaryMachine>(p, s, incremental && p.cache != nullptr, supported);
-    if (problem == PCGRL_PROB_ZELDA) return dispatch_split<ZeldaMachine>(p, s, false, supported);
+    if (problem == PCGRL_PROB_BINARY) {
+        const int inc = p.cache != nullptr && p.d0 <= 16 && p.d1 <= 16 ? incremental : 0;
+        if (inc == 2) n_launches = 1;
+        return dispatch_split<BinaryMachine>(p, s, inc, supported);
+    }
+    if (problem == PCGRL_PROB_ZELDA) return dispatch_split<ZeldaMachine>(p, s, 0, supported);
     if (problem == PCGRL_PROB_BINARY_HOLEY) {
         supported = p.ndim == 2 && p.d1 + 2 <= 32 && p.d0 + 2 <= 32;
         if (!supported) return cudaSuccess;
-        if (p.d0 + 2 <= 18) return launch_split<BinaryHoleyMachine<18, false>, 18, false>(p, s, false);
-        return launch_split<BinaryHoleyMachine<32, false>, 32, false>(p, s, false);
+        if (p.d0 + 2 <= 18) return launch_split<BinaryHoleyMachine<18, false>, 18, false>(p, s, 0);
+        return launch_split<BinaryHoleyMachine<32, false>, 32, false>(p, s, 0);
     }
     return cudaSuccess;
 }

@@ -3,6 +3,7 @@
   fused  k_step_bitboard (one launch: update, searches, reward) -- pinned on the reference fixtures elsewhere
   split  k_split_act / k_split_stats / k_split_out (global work list, from-scratch searches with full warps)
   inc    the same with the incremental binary search from the per-env cache (BinaryIncMachine)
+  incfused  k_step_inc: update, incremental search and reward in one launch, every warp on its own env slice
 
 PCGRL_STEP_PATH selects the path per pcgrl_step call.  Besides path-vs-path equality, every few steps the stats of
 EVERY env are recomputed from scratch from the current grids (pcgrl_stats), which is what pins the incremental
@@ -48,7 +49,7 @@ def test_step_paths_agree_and_match_fresh_stats(problem, rep, shape, controls, m
     kw = dict(controls=controls, max_board_scans=0.6)
     if rep == "wide":
         kw["obs_window"] = shape
-    paths = ["fused", "split", "inc"]
+    paths = ["fused", "split", "inc", "incfused"]
     envs = _envs(problem, rep, shape, n, paths, **kw)
     has_cache = envs[2].cache is not None
     assert has_cache == (problem == "binary" and max(shape) <= 16)
@@ -81,9 +82,9 @@ def test_step_paths_agree_and_match_fresh_stats(problem, rep, shape, controls, m
             assert torch.equal(e.changes, ref.changes) and torch.equal(e.iteration, ref.iteration), (path, t)
             assert torch.equal(e.changed, ref.changed), (path, t)
         if t % 16 == 5 or t == steps - 1:
-            e = envs[2]
-            fresh = e.compute_stats(e.maps, holes=e.holes) if e.holey else e.compute_stats(e.maps)
-            assert torch.equal(fresh, e.stats), (t, int((fresh != e.stats).any(dim=1).sum()))
+            for e in envs[2:]:
+                fresh = e.compute_stats(e.maps, holes=e.holes) if e.holey else e.compute_stats(e.maps)
+                assert torch.equal(fresh, e.stats), (t, int((fresh != e.stats).any(dim=1).sum()))
     for e in envs:
         e.check_status()
 
