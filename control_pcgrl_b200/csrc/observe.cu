@@ -150,12 +150,19 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
     const int64_t trips = (p.n_envs + envs_per_trip - 1) / envs_per_trip;
     const int o12 = p.o1 * p.o2;
     const int n_pl = 2 * p.n_ctrl;
+    // u8 one-hot records of 3 channels (binary behind a crop: the headline observation): 8 pixels are 24 bytes, built
+    // in registers and stored as three 64-bit words -- no zero fill, no byte stores
+    const bool pack3 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 3 && !p.raw && n_pl == 0;
+    // uint8 tile codes (one byte per pixel): 8 pixels are one 64-bit word
+    const bool pack1 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 1 && p.raw && n_pl == 0;
     for (int64_t trip = blockIdx.x; trip < trips; trip += gridDim.x) {
         const int64_t env0 = trip * envs_per_trip;
         const int n_here = (int)min((int64_t)envs_per_trip, p.n_envs - env0);
-        __syncthreads();                                             // the previous trip's copy-out is done
+        // the previous trip's bulk store has finished READING the stage (its global writes may still be in flight)
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
         {
-            const int nz = (int)(((int64_t)n_here * v.E * (int64_t)sizeof(T) + 15) / 16);
+            const int nz = (pack3 || pack1) ? 0 : (int)(((int64_t)n_here * v.E * (int64_t)sizeof(T) + 15) / 16);
             const uint4 z = make_uint4(0, 0, 0, 0);
             for (int i = tid; i < nz; i += OBS_THREADS) ((uint4*)stage)[i] = z;
             const int nv = n_here * (p.row_stride / 16);
@@ -216,6 +223,37 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 const int dl = D3 ? p.d2 : p.d1;
                 const int sl = D3 ? c2 + (int)q2 : c1 + (int)q1;
                 const int8_t* rowp = D3 ? grid + ((c0 + (int)q0) * p.d1 + (c1 + (int)q1)) * p.d2 : grid + (c0 + (int)q0) * p.d1;
+                if (sizeof(T) == 1 && ROWN == 8 && pack3) {
+                    // pixel k is the 24-bit value 1 << (8 * hot_k); four of them make three 32-bit words
+                    uint32_t px[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
+                        const int hot = inside ? rowp[sl + k] + (CROP ? 1 : 0) : 0;
+                        px[k] = 1u << (8 * hot);
+                    }
+                    uint32_t w[6];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        w[3 * h + 0] = px[4 * h] | (px[4 * h + 1] << 24);
+                        w[3 * h + 1] = (px[4 * h + 1] >> 8) | (px[4 * h + 2] << 16);
+                        w[3 * h + 2] = (px[4 * h + 2] >> 16) | (px[4 * h + 3] << 8);
+                    }
+                    uint2* o8 = (uint2*)o;       // byte offset first * 3 with first % 8 == 0: 8-byte aligned
+                    o8[0] = make_uint2(w[0], w[1]);
+                    o8[1] = make_uint2(w[2], w[3]);
+                    o8[2] = make_uint2(w[4], w[5]);
+                } else if (sizeof(T) == 1 && ROWN == 8 && pack1) {
+                    uint32_t lo = 0, hi = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
+                        const uint32_t hot = inside ? (uint32_t)(rowp[sl + k] + (CROP ? 1 : 0)) : 0u;
+                        if (k < 4) lo |= hot << (8 * k);
+                        else hi |= hot << (8 * (k - 4));
+                    }
+                    *(uint2*)o = make_uint2(lo, hi);
+                } else
 #pragma unroll
                 for (int k = 0; k < ROWN; ++k) {
                     const bool inside = row_ok && (!CROP || (unsigned)(sl + k) < (unsigned)dl);
@@ -303,17 +341,26 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
             }
             }
         }
+        // ---- copy-out: ONE bulk asynchronous copy of the whole stage (cp.async.bulk shared -> global, the TMA engine;
+        // SASS UBLKCP), issued by one thread, so no thread spends issue slots on the 128-bit load / store pairs and
+        // the next trip's staging overlaps the drain.  Generic-proxy writes to shared memory must be fenced for the
+        // async proxy before the barrier.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        // ---- copy-out: 128-bit coalesced stores ---------------------------------------------------------------
         const int64_t elems = (int64_t)n_here * v.E;
         const int n_vec = (int)(elems * (int64_t)sizeof(T) / 16);
         uint4* dst = (uint4*)((T*)p.out + env0 * v.E);
-        const uint4* src = (const uint4*)stage;
-        for (int i = tid; i < n_vec; i += OBS_THREADS) dst[i] = src[i];
+        if (tid == 0 && n_vec > 0) {
+            const uint32_t src_s = (uint32_t)__cvta_generic_to_shared(stage);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(src_s), "r"(n_vec * 16) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
         // a partly filled last group may end inside a vector: element-wise tail
         const int done = n_vec * (16 / (int)sizeof(T));
         for (int i = done + tid; i < (int)elems; i += OBS_THREADS) ((T*)p.out + env0 * v.E)[i] = stage[i];
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the stage must outlive its last reader
 }
 
 template <typename T>
