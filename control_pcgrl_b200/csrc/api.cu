@@ -11,6 +11,7 @@
 
 namespace pcgrl {
 cudaError_t launch_bitboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
+cudaError_t launch_bigboard(const KParams& p, int problem, cudaStream_t s, bool& supported);
 cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, int incremental, bool& supported,
                                   int& n_launches);
 int bitboard_cache_stride(int problem, int ndim, int d0, int d1, int rep, int action_kind);
@@ -219,6 +220,8 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
             }
         }
         e = launch_bitboard(p, problem, (cudaStream_t)stream, supported);
+        // maps beyond 32x32 (binary_bigger / zelda_bigger are 64x64): warp-per-grid boards
+        if (!supported) e = launch_bigboard(p, problem, (cudaStream_t)stream, supported);
     }
     if (!supported)
         return fail(PCGRL_E_UNSUPPORTED, "no kernel for this problem / map shape yet (or scratch is NULL although "
@@ -242,7 +245,7 @@ static thread_local HostPipe g_pipe[16];
 
 static int host_chunks(const pcgrl_config* cfg, int64_t n, bool packed) {
     (void)packed;
-    if (!is_bitboard(cfg)) return 1;
+    if (!is_bitboard(cfg) || cfg->dims[0] > 32 || cfg->dims[1] > 32) return 1;
     if (const char* e = getenv("PCGRL_HOST_CHUNKS")) {
         const int v = atoi(e);
         if (v >= 1) return (int)std::min<int64_t>(std::min(v, WL_CHUNKS), std::max<int64_t>(1, n / 256));
@@ -295,6 +298,7 @@ int64_t pcgrl_step_bytes(const pcgrl_config* c) {
 int64_t pcgrl_worklist_ints(const pcgrl_config* cfg, int64_t n_envs) {
     if (check(cfg) || n_envs < 0) return -1;
     if (!is_bitboard(cfg) || cfg->representation == PCGRL_REP_CELLULAR || cfg->ndim != 2) return 0;
+    if (cfg->dims[0] > 32 || cfg->dims[1] > 32) return 0;   // warp-per-grid boards (step_bigboard.cu): fused only
     // header + (env, cell) + new stats per env, plus one header per host-pipeline chunk (up to 64)
     return (2 + (int64_t)cfg->n_stats) * n_envs + WL_HDR_INTS;
 }

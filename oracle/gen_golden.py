@@ -251,6 +251,41 @@ def save_stats_fixture(problem, grids, name=None):
     print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
 
 
+# ------------------------------------------------------------------------------------------ maps beyond 32x32
+def binary_big_grids():
+    """configs/task/binary_bigger.yaml:5 is 64x64: random maps at four densities, odd shapes with one side above
+    32, the serpentine corridor (the longest possible path), all empty, all solid."""
+    rng = np.random.default_rng(2024)
+    bg = []
+    for shape, n in (((64, 64), 10), ((40, 50), 8), ((33, 20), 6), ((17, 64), 6)):
+        for k in range(n):
+            bg.append((rng.random(shape) < (0.35, 0.5, 0.65, 0.8)[k % 4]).astype(np.uint8))
+    g = np.ones((64, 64), np.uint8)
+    for y in range(0, 64, 2):
+        g[y, :] = 0
+        g[y + 1 if y + 1 < 64 else y, 63 if (y // 2) % 2 == 0 else 0] = 0
+    return bg + [g, np.zeros((64, 64), np.uint8), np.ones((64, 64), np.uint8)]
+
+
+def zelda_big_grids():
+    """configs/task/zelda_bigger.yaml:5 is 64x64: random levels, half of them with exactly one player / key / door so
+    that both path searches run, a quarter mostly open (long reachable paths)."""
+    rng = np.random.default_rng(2025)
+    p = np.array([0.58, 0.3, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02])
+    zg = []
+    for shape, n in (((64, 64), 8), ((40, 50), 6), ((33, 20), 6)):
+        for k in range(n):
+            g = rng.choice(8, size=shape, p=p).astype(np.uint8)
+            if k % 2 == 0:
+                g[(g == 2) | (g == 3) | (g == 4)] = 0
+                idx = rng.choice(g.size, 3, replace=False)
+                g.flat[idx[0]], g.flat[idx[1]], g.flat[idx[2]] = 2, 3, 4
+            if k % 4 == 0:
+                g[(g == 1) & (rng.random(shape) < 0.7)] = 0
+            zg.append(g)
+    return zg
+
+
 # ------------------------------------------------------------------------------------------ minecraft_2D_maze
 def minecraft_2d_maze_fixture():
     """Minecraft2DmazeProblem.get_stats / get_reward (minecraft_2D_maze_prob.py:87-115), run verbatim.  The class
@@ -625,6 +660,8 @@ def main(which=None):
                                                          SOK_W, seed=37, static_prob=0.6, init_p=SOK_AP, action_p=SOK_AP,
                                                          n_envs=3, obs_every=17),
     })
+    jobs["stats_binary_big"] = lambda: save_stats_fixture("binary", binary_big_grids(), "binary_big")
+    jobs["stats_zelda_big"] = lambda: save_stats_fixture("zelda", zelda_big_grids(), "zelda_big")
     jobs["stats_binary_holey"] = binary_holey_fixture
     jobs["stats_minecraft_2D_maze"] = minecraft_2d_maze_fixture
     jobs["stats_maze3d_holey"] = maze3d_holey_fixture

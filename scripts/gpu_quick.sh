@@ -1,10 +1,25 @@
 #!/bin/bash
-# quick iteration: parity tests + headline bench + ncu full capture of the step kernel
+# quick GPU check: the whole parity suite (+ optional extra command)
 set -u
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python bench.py --steps 800 --warmup 10 --no-cpu-baseline > gpurun_out/bench_narrow_1m.json 2> gpurun_out/bench.err; cut -c1-700 gpurun_out/bench_narrow_1m.json
-python bench.py --steps 400 --warmup 10 --workload zelda-turtle-7x11 --no-cpu-baseline --no-e2e > gpurun_out/bench_zelda.json 2>> gpurun_out/bench.err; cut -c1-200 gpurun_out/bench_zelda.json
-ncu --set full --clock-control none --import-source on -k regex:k_step_bitboard -s 8 -c 1 -f -o gpurun_out/prof_step \
-    python bench.py --steps 12 --warmup 2 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/bench.err
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -12 | tee gpurun_out/pytest_gpu_quick.txt
+for wl in "binary narrow 64 64" "zelda turtle 64 64"; do
+python - $wl <<'PY'
+import sys, time, torch
+sys.path.insert(0, ".")
+import control_pcgrl_b200 as P
+prob, rep, h, w = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+n = 65536
+env = P.BatchedPcgrlEnv(P.make_config(prob, rep, map_shape=(h, w)), n, auto_reset=True)
+env.reset()
+n_act = env.n_tiles + (4 if rep == "turtle" else 0)
+acts = torch.randint(0, n_act, (60, n), device=env.device, dtype=torch.int32)
+for t in range(10): env.step(acts[t])
+torch.cuda.synchronize(); e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for t in range(10, 60): env.step(acts[t])
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 50
+print(f"{prob}-{rep} {h}x{w}: {n} envs, {ms:.3f} ms/step, {n / ms * 1e3:.4g} env-steps/s")
+PY
+done | tee gpurun_out/r02_bigboard_rates.txt

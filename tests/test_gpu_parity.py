@@ -24,13 +24,14 @@ def _mk(problem, rep, map_shape, n, **kw):
 
 @pytest.mark.parametrize("name,problem", [("binary", "binary"), ("binary_shapes", "binary"), ("zelda", "zelda"),
                                           ("maze3d", "minecraft_3D_maze"), ("sokoban", "sokoban"), ("smb", "smb"),
-                                          ("minecraft_2D_maze", "minecraft_2D_maze")])
+                                          ("minecraft_2D_maze", "minecraft_2D_maze"),
+                                          ("binary_big", "binary"), ("zelda_big", "zelda")])
 def test_stats_kernel_matches_reference_fixtures(name, problem):
     _, groups = load_stats(name)
     total = 0
     for grids, stats in groups:
         shape = grids.shape[1:]
-        if max(shape) > 32 and problem in ("binary", "zelda"):
+        if max(shape) > 64 and problem in ("binary", "zelda"):
             continue
         env = _mk(problem, "narrow", shape, 1)
         got = env.compute_stats(grids).cpu().numpy()
@@ -38,7 +39,49 @@ def test_stats_kernel_matches_reference_fixtures(name, problem):
         assert bad.size == 0, (name, shape, bad[:5], got[bad[:5]], stats[bad[:5]])
         env.check_status()
         total += len(grids)
-    assert total > 100
+    assert total > (15 if name.endswith("_big") else 100)
+
+
+@pytest.mark.parametrize("problem,rep,shape", [("binary", "narrow", (64, 64)), ("zelda", "turtle", (64, 64)),
+                                               ("binary", "wide", (48, 48)), ("zelda", "narrow", (33, 20))])
+def test_big_board_rollout(problem, rep, shape):
+    """Maps beyond 32x32 (binary_bigger / zelda_bigger, configs/task/*_bigger.yaml:5) run on the warp-per-grid
+    boards of step_bigboard.cu: step-by-step properties on the batch, stats recomputed from scratch, and the
+    oracle on a few envs."""
+    from oracle import pcgrl_oracle as O
+    n, n_or, steps = 512, 4, 60
+    kw = dict(obs_window=shape) if rep == "wide" else {}
+    env = _mk(problem, rep, shape, n, seed=21, **kw)
+    env.reset()
+    assert env.worklist is None and env.cache is None
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    maps0, pos0 = env.maps.cpu().numpy(), env.pos.cpu().numpy()
+    oracles = []
+    for e in range(n_or):
+        o = O.OracleEnv(problem, rep, shape, weights=dict(env.metric_weights))
+        o.reset(maps0[e], pos=pos0[e, :2])
+        oracles.append(o)
+    n_act = {"narrow": env.n_tiles, "turtle": 4 + env.n_tiles, "wide": shape[0] * shape[1] * env.n_tiles}[rep]
+    g = torch.Generator(device=env.device).manual_seed(0)
+    prev = env.stats.clone()
+    for t in range(steps):
+        a = torch.randint(0, n_act, (n,), generator=g, device=env.device, dtype=torch.int32)
+        reward, _ = env.step(a)
+        ch = env.changed.bool()
+        assert torch.equal(env.stats[~ch], prev[~ch]) and float(reward[~ch].abs().max()) == 0.0
+        prev = env.stats.clone()
+        a_h, r_h, st_h = a.cpu().numpy(), reward.cpu().numpy(), env.stats.cpu().numpy()
+        for e, o in enumerate(oracles):
+            act = int(a_h[e])
+            if rep == "wide":
+                act = O.actionmap_unravel(act, shape[0], shape[1], env.n_tiles)
+            r, _, _ = o.step(act)
+            assert st_h[e].tolist() == O.stats_vector(problem, o.stats), (t, e)
+            assert r_h[e] == pytest.approx(float(r), rel=1e-6, abs=1e-7), (t, e)
+    assert torch.equal(env.compute_stats(env.maps), env.stats)
+    obs = env.observe(dtype=torch.uint8)
+    assert int(obs.sum()) == n * int(np.prod(obs.shape[1:-1]))
+    env.check_status()
 
 
 @pytest.mark.parametrize("name", TRACES + TRACES_SEARCH + TRACES_WRAPPED)
