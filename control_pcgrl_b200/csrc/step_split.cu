@@ -75,10 +75,24 @@ constexpr int STAT_THREADS = 128;
 // threads per CTA of the static search: as many warps as keep the staged bit-boards under 48 KB of shared memory
 __host__ __device__ constexpr int stat_threads(int bbw) { return bbw <= 96 ? 128 : 64; }
 constexpr int OUT_THREADS = 256;
-// Work list of one launch: p.wl_hdr = 16 header ints ([0] count of listed envs, [1] CTAs of k_split_out that are
-// done; both zero between steps), p.worklist = the body: (env, cell) pairs for up to n_envs items, then n_stats new
+// Work list of one launch: p.wl_hdr = 16 header ints, p.worklist = the body: (env, cell) pairs for up to n_envs items, then n_stats new
 // stats per item.  The headers of all pipeline chunks live together at the front of pcgrl_state.worklist, where no
 // body ever lands, so they stay zero whatever chunking the previous step used.
+// Header (all zero before the first step): [0], [1] item counters used alternately, [3] the step count, whose parity
+// picks the counter, [4] the step's final item count.  k_split_act adds to counter [par]; the search kernel clears
+// counter [par ^ 1] for the next step and publishes the count in [4]; k_split_out reads [4] and bumps [3] -- every
+// word is written by exactly one thread of a kernel none of whose CTAs reads it, so the three launches need no
+// "last CTA out" atomics or fences to hand the list over.
+__device__ __forceinline__ int wl_parity(const KParams& p) { return *(volatile const int*)(p.wl_hdr + 3) & 1; }
+__device__ __forceinline__ int wl_count_search(const KParams& p) {
+    const int par = wl_parity(p);
+    const int count = *(volatile const int*)(p.wl_hdr + par);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.wl_hdr[par ^ 1] = 0;
+        p.wl_hdr[4] = count;
+    }
+    return count;
+}
 __device__ __forceinline__ int2* wl_items(const KParams& p) { return (int2*)p.worklist; }
 __device__ __forceinline__ int32_t* wl_stats(const KParams& p) { return p.worklist + 2 * p.n_envs; }
 
@@ -104,7 +118,7 @@ __global__ void __launch_bounds__(ACT_THREADS) k_split_act(const KParams p) {
             s_warp[w] = tot;
             tot += c;
         }
-        s_base = tot ? atomicAdd(p.wl_hdr, tot) : 0;
+        s_base = tot ? atomicAdd(p.wl_hdr + wl_parity(p), tot) : 0;
     }
     __syncthreads();
     if (need) wl_items(p)[s_base + s_warp[warp] + __popc(bal & ((1u << lane) - 1u))] = make_int2((int)gid, cell);
@@ -123,7 +137,7 @@ k_split_stats(const KParams p) {
     constexpr int THREADS = stat_threads(BBW);
     __shared__ uint32_t s_bb[THREADS * BBW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int count = *(volatile const int*)p.wl_hdr;
+    const int count = wl_count_search(p);
     const int first = (blockIdx.x * (THREADS / 32) + warp) * 32;
     if (first >= count) return;   // warps are independent: no CTA-wide barrier anywhere in this kernel
     const int n_here = min(32, count - first);
@@ -441,7 +455,7 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
     using M = BinaryIncMachine<NW, TWO>;
     __shared__ uint32_t s_work[STAT_THREADS * M::SMEM_WORDS];
     const int tid = threadIdx.x, lane = tid & 31;
-    const int count = *(volatile const int*)p.wl_hdr;
+    const int count = wl_count_search(p);
     const int n_warps = gridDim.x * (STAT_THREADS / 32);
     const int gw = blockIdx.x * (STAT_THREADS / 32) + (tid >> 5);
     const int per = (count + n_warps - 1) / n_warps;
@@ -627,8 +641,9 @@ __global__ void __launch_bounds__(STAT_THREADS, PCGRL_STEP_INC_MIN_CTAS) k_step_
 // ------------------------------------------------------------------------------------------------
 template <int K>
 __global__ void __launch_bounds__(OUT_THREADS) k_split_out(const KParams p) {
-    const int count = *(volatile const int*)p.wl_hdr;
+    const int count = *(volatile const int*)(p.wl_hdr + 4);
     const int i = blockIdx.x * OUT_THREADS + threadIdx.x;
+    if (i == 0) p.wl_hdr[3] = p.wl_hdr[3] + 1;   // the next step uses the other counter (no CTA of this kernel reads [3])
     if (i < count) {
         const int64_t env = wl_items(p)[i].x;
         int32_t nw[K];
@@ -636,15 +651,6 @@ __global__ void __launch_bounds__(OUT_THREADS) k_split_out(const KParams p) {
 #pragma unroll
         for (int k = 0; k < K; ++k) nw[k] = o[k];
         finish_env<K>(p, env, nw);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {   // last CTA out re-arms the header for the next step on this work list
-        __threadfence();
-        if (atomicAdd((unsigned*)p.wl_hdr + 1, 1u) == gridDim.x - 1) {
-            p.wl_hdr[0] = 0;
-            p.wl_hdr[1] = 0;
-            __threadfence();
-        }
     }
 }
 
