@@ -13,7 +13,7 @@ MAX_STATS = 16
 MAX_TILES = 16
 
 PROB_IDS = {"binary": 0, "zelda": 1, "sokoban": 2, "smb": 3, "minecraft_3D_maze": 4, "binary_holey": 5,
-            "minecraft_2D_maze": 6}
+            "minecraft_2D_maze": 6, "minecraft_3D_holey_maze": 7, "minecraft_3D_dungeon_holey": 8}
 HOLES_GIVEN, HOLES_FIXED, HOLES_RANDOM = 0, 1, 2
 REP_IDS = {"narrow": 0, "turtle": 1, "wide": 2, "cellular": 3}
 ACT_INT32, ACT_WIDE_COORDS, ACT_WIDE_FLAT, ACT_CA_TILES, ACT_CA_LOGITS, ACT_PATCH = range(6)

@@ -173,7 +173,9 @@ class BatchedPcgrlEnv:
         self.static_mask = torch.zeros((N, self.row_stride), dtype=torch.uint8, device=dev) \
             if self.static_tile_wrapper else None
         # (entrance_y, entrance_x, exit_y, exit_x) in bordered coordinates (holey_prob.py:41-42)
-        self.holes = torch.zeros((N, 4), dtype=torch.int32, device=dev) if self.holey else None
+        # 3D holey problems: (ez, ey, ex, xz, xy, xx), the foot tiles (holey_prob_3D.py:72-92; the head is the tile above)
+        self.hole_ints = 6 if self.ndim == 3 else 4
+        self.holes = torch.zeros((N, self.hole_ints), dtype=torch.int32, device=dev) if self.holey else None
         self.record_stride = int(self.lib.pcgrl_record_stride(cc)) if self._rec_sb else 0
         self.records = torch.zeros((N, self.record_stride), dtype=torch.uint8, device=dev) if self._rec_sb else None
         # split step path of the bit-board problems (csrc/step_split.cu): a global work list of changed envs, and
@@ -340,7 +342,7 @@ class BatchedPcgrlEnv:
             if not self.holey:
                 raise ValueError("holes are only meaningful for a holey problem")
             hv = torch.as_tensor(np.asarray(holes) if not torch.is_tensor(holes) else holes)
-            hv = hv.to(self.device, torch.int32).reshape(self.n_envs, 4)
+            hv = hv.to(self.device, torch.int32).reshape(self.n_envs, self.hole_ints)
             if mask is None:
                 self.holes.copy_(hv)
             else:
@@ -498,9 +500,12 @@ class BatchedPcgrlEnv:
         return h2d, self.n_envs * (4 + 1 + (4 * self.K if want_stats else 0))
 
     # ------------------------------------------------------------------ stats / observations
-    def compute_stats(self, grids, holes=None) -> torch.Tensor:
-        """Problem.get_stats for arbitrary grids [n, *map_shape] (evolution's terminal call).  A holey problem
-        also needs holes [n, 4] (its get_stats reads entrance_coords / exit_coords)."""
+    def compute_stats(self, grids, holes=None, prev_path_length=None) -> torch.Tensor:
+        """Problem.get_stats for arbitrary grids [n, *map_shape] (evolution's terminal call).  A holey problem also
+        needs holes [n, 4] (3D: [n, 6], the foot tiles) -- its get_stats reads entrance_coords / exit_coords.
+        minecraft_3D_holey_maze reports as path-length what the PREVIOUS call on the same problem object found
+        (minecraft_3D_holey_maze_prob.py:92-93): pass those lengths as prev_path_length [n] (default 0); the
+        length this call finds comes back as the stat `_next-path-length`."""
         g = torch.as_tensor(np.asarray(grids) if not torch.is_tensor(grids) else grids)
         n = g.shape[0]
         g = g.to(device=self.device, dtype=torch.int8).reshape(n, self.cells)
@@ -512,9 +517,15 @@ class BatchedPcgrlEnv:
         out = torch.empty((n, self.K), dtype=torch.int32, device=self.device)
         if self.holey:
             if holes is None:
-                raise ValueError("a holey problem needs holes [n, 4] for compute_stats")
+                raise ValueError(f"a holey problem needs holes [n, {self.hole_ints}] for compute_stats")
             hv = torch.as_tensor(np.asarray(holes) if not torch.is_tensor(holes) else holes)
-            hv = hv.to(self.device, torch.int32).reshape(n, 4).contiguous()
+            hv = hv.to(self.device, torch.int32).reshape(n, self.hole_ints)
+            if self.problem == "minecraft_3D_holey_maze":
+                prev = torch.zeros(n, dtype=torch.int32, device=self.device) if prev_path_length is None else \
+                    torch.as_tensor(np.asarray(prev_path_length) if not torch.is_tensor(prev_path_length)
+                                    else prev_path_length).to(self.device, torch.int32).reshape(n)
+                hv = torch.cat([hv, prev[:, None]], dim=1)
+            hv = hv.contiguous()
             with self._on_device():
                 _lib.check(self.lib.pcgrl_stats_holey(self._cc, g.data_ptr(), hv.data_ptr(), out.data_ptr(), n,
                                                       _ptr(self.scratch), self._stream()), "pcgrl_stats_holey")
@@ -539,6 +550,9 @@ class BatchedPcgrlEnv:
         onehot=False (uint8 only, no controls): the tile codes of the crop instead of their one-hot records --
         Cropped's own output (wrappers.py:407-437: 0 = out of bounds, tile t -> t + 1), one channel, for policies
         that embed the tile themselves."""
+        if self.holey and self.ndim == 3:
+            raise NotImplementedError("observations of the 3D holey problems (the bordered 3D map) are not built yet; "
+                                      "env.maps / env.holes hold the level and the holes")
         if not onehot:
             if self.ctrl_metrics or (out is not None and out.dtype != torch.uint8):
                 raise ValueError("onehot=False is a uint8 observation without control planes")

@@ -71,6 +71,14 @@ TASK_DEFAULTS = {
                          weights={"regions": 1, "path-length": 0, "connected-path-length": 1}),
     # Minecraft2DmazeProblem's own size (minecraft_2D_maze_prob.py:17-18) and reward weights (:24-27)
     "minecraft_2D_maze": dict(map_shape=(14, 14), obs_window=(28, 28), weights={"regions": 5, "path-length": 1}),
+    # the 3D holey problems (weights: minecraft_3D_holey_maze_prob.py:33-41, minecraft_3D_holey_dungeon_prob.py:75-82);
+    # 7^3 is the size the reference's 3D experiments use and the bordered map must fit 16^3
+    "minecraft_3D_holey_maze": dict(map_shape=(7, 7, 7), obs_window=(14, 14, 14),
+                                    weights={"regions": 0, "path-length": 100, "connected-path-length": 120,
+                                             "n_jump": 150}),
+    "minecraft_3D_dungeon_holey": dict(map_shape=(7, 7, 7), obs_window=(14, 14, 14),
+                                       weights={"regions": 0, "path-length": 100, "chests": 300, "n_jump": 100,
+                                                "enemies": 100, "nearest-enemy": 200}),
     "minecraft_3D_maze": dict(map_shape=(15, 15, 15), obs_window=(30, 30, 30),
                               weights={"path-length": 100, "n_jump": 100, "regions": 0}),
 }

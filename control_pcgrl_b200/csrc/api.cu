@@ -16,6 +16,7 @@ cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s,
                                   int& n_launches);
 int bitboard_cache_stride(int problem, int ndim, int d0, int d1, int rep, int action_kind);
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
+cudaError_t launch_maze3d_holey(const KParams& p, int problem, cudaStream_t s, bool& supported);
 cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported);
 int64_t sokoban_scratch_bytes();
@@ -52,8 +53,10 @@ static int check(const pcgrl_config* c) {
         return fail(PCGRL_E_ARG, "unknown representation");
     const int cells = cells_of(c);
     if (c->row_stride < cells || c->row_stride % 16) return fail(PCGRL_E_ARG, "row_stride must be >= cells and a multiple of 16");
-    static const int k_of[] = {2, 7, 7, 9, 3, 3, 2};
-    if (c->problem < 0 || c->problem > PCGRL_PROB_MINECRAFT_2D_MAZE) return fail(PCGRL_E_ARG, "unknown problem");
+    static const int k_of[] = {2, 7, 7, 9, 3, 3, 2, 5, 6};
+    if (c->problem < 0 || c->problem > PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY) return fail(PCGRL_E_ARG, "unknown problem");
+    if ((c->problem == PCGRL_PROB_MINECRAFT_3D_HOLEY_MAZE || c->problem == PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY) && c->ndim != 3)
+        return fail(PCGRL_E_ARG, "the minecraft holey problems are 3D");
     if (c->hole_mode < PCGRL_HOLES_GIVEN || c->hole_mode > PCGRL_HOLES_RANDOM) return fail(PCGRL_E_ARG, "unknown hole_mode");
     if (c->problem == PCGRL_PROB_BINARY_HOLEY && c->ndim != 2) return fail(PCGRL_E_ARG, "binary_holey is a 2D problem");
     if (c->n_stats != k_of[c->problem]) return fail(PCGRL_E_ARG, "n_stats does not match the problem");
@@ -187,7 +190,11 @@ static void fill(KParams& p, const pcgrl_config* c, const pcgrl_state* st) {
     }
 }
 
-static bool is_holey(const pcgrl_config* c) { return c->problem == PCGRL_PROB_BINARY_HOLEY; }
+static bool is_holey3d(const pcgrl_config* c) {
+    return c->problem == PCGRL_PROB_MINECRAFT_3D_HOLEY_MAZE || c->problem == PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY;
+}
+static bool is_holey(const pcgrl_config* c) { return c->problem == PCGRL_PROB_BINARY_HOLEY || is_holey3d(c); }
+static int hole_ints(const pcgrl_config* c) { return is_holey3d(c) ? 6 : 4; }
 
 static int check_state(const pcgrl_state* st) {
     if (!st) return fail(PCGRL_E_ARG, "state is NULL");
@@ -204,6 +211,8 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
     cudaError_t e;
     if (problem == PCGRL_PROB_MINECRAFT_3D_MAZE)
         e = launch_maze3d(p, (cudaStream_t)stream, supported);
+    else if (problem == PCGRL_PROB_MINECRAFT_3D_HOLEY_MAZE || problem == PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY)
+        e = launch_maze3d_holey(p, problem, (cudaStream_t)stream, supported);
     else if (problem == PCGRL_PROB_SOKOBAN)
         e = launch_sokoban(p, (cudaStream_t)stream, supported);
     else if (problem == PCGRL_PROB_SMB)
@@ -279,7 +288,7 @@ int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
     // node pools / heaps / hash tables of the solver problems: one slice per resident search warp
     if (cfg->problem == PCGRL_PROB_SOKOBAN) return sokoban_scratch_bytes();
     if (cfg->problem == PCGRL_PROB_SMB) return smb_scratch_bytes();
-    if (cfg->problem == PCGRL_PROB_MINECRAFT_3D_MAZE) return maze3d_scratch_bytes();   // per-cell jump counts
+    if (cfg->problem == PCGRL_PROB_MINECRAFT_3D_MAZE || is_holey3d(cfg)) return maze3d_scratch_bytes();   // jump counts, parents
     return 0;  // binary / zelda keep all search state in registers / shared memory
 }
 
@@ -474,7 +483,7 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
         sub.done = st->done + off;
         sub.changed = st->changed ? st->changed + off : nullptr;
         sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
-        sub.holes = st->holes ? st->holes + off * 4 : nullptr;
+        sub.holes = st->holes ? st->holes + off * hole_ints(cfg) : nullptr;
         sub.records = st->records ? st->records + off * rs : nullptr;
         sub.cache = st->cache ? st->cache + off * cache_stride(cfg) : nullptr;
         int64_t a_stride = a_env;

@@ -211,6 +211,50 @@ __device__ static void gen_holes(const KParams& p, int64_t gid, uint64_t genv, u
     }
 }
 
+// HoleyProblem3D.gen_holes (envs/probs/holey_prob_3D.py:41-100): holes[gid] = (ez, ey, ex, xz, xy, xx), the foot tiles
+// in bordered coordinates.  Border cells (get_border_idxs, :16-35): the four side faces without their vertical
+// edges, z = 1 .. Z - 1 (the reference's `1:-2` leaves the top interior layer out), in argwhere order z, y, x.
+__device__ static void gen_holes3d(const KParams& p, int64_t gid, uint64_t genv, uint2 key) {
+    int32_t* h = p.holes + gid * 6;
+    const int Z = p.d0, Y = p.d1, X = p.d2;
+    if (p.hole_mode == PCGRL_HOLES_FIXED) {    // :66-69 diagonal corners
+        h[0] = 1, h[1] = 0, h[2] = X;
+        h[3] = 2, h[4] = Y + 1, h[5] = 1;
+        return;
+    }
+    const int per = 2 * (Y + X), nb = (Z - 1) * per;
+    const int want = nb < 26 ? nb : 26;        // :74-75 `potential` distinct random border cells
+    int pick[26], n = 0;
+    for (uint32_t c = 0; n < want && c < 64; ++c) {
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), (uint32_t)p.epoch, 0xD0000000u + c), key);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        for (int j = 0; j < 4 && n < want; ++j) {
+            const int k = (int)(rr[j] % (uint32_t)nb);
+            bool dup = false;
+            for (int q = 0; q < n; ++q) dup |= pick[q] == k;
+            if (!dup) pick[n++] = k;
+        }
+    }
+    auto cell = [&](int k, int& z, int& y, int& x) {
+        z = 1 + k / per;
+        border_cell(k % per, Y, X, y, x);
+    };
+    int ez = 1, ey = 0, ex = 1;
+    if (n > 0) cell(pick[0], ez, ey, ex);
+    h[0] = ez, h[1] = ey, h[2] = ex;
+    h[3] = h[4] = h[5] = 1;                    // :86 exit_coords = np.ones((2, 3)) when no candidate is accepted
+    for (int i = 1; i < n; ++i) {
+        int z, y, x;
+        cell(pick[i], z, y, x);
+        // _valid_holes (:96-100): np.max over |foot - xyz| and |head - xyz|, all three coordinates
+        const int d = max(max(max(abs(ez - z), abs(ez + 1 - z)), abs(ey - y)), abs(ex - x));
+        if (d > 1) {
+            h[3] = z, h[4] = y, h[5] = x;
+            break;
+        }
+    }
+}
+
 // Episode start for env `gid` (thread-per-env): grid from src or Philox, counters, start position.
 __device__ static void reset_env(const KParams& p, int64_t gid) {
     int8_t* grid = p.grids + gid * p.row_stride;
@@ -304,7 +348,10 @@ __device__ static void reset_env(const KParams& p, int64_t gid) {
             }
         }
     }
-    if (p.holes && p.hole_mode != PCGRL_HOLES_GIVEN) gen_holes(p, gid, genv, key);
+    if (p.holes && p.hole_mode != PCGRL_HOLES_GIVEN) {
+        if (p.ndim == 3) gen_holes3d(p, gid, genv, key);
+        else gen_holes(p, gid, genv, key);
+    }
     int32_t* pos = p.pos + gid * 3;
     pos[0] = pos[1] = pos[2] = 0;
     if (p.rep == PCGRL_REP_NARROW && p.action_kind == PCGRL_ACT_PATCH) {

@@ -26,288 +26,11 @@
 //   * visited_map[np.array(list(paths.keys()))] = 1 marks the z-planes whose index equals ANY coordinate of
 //     any recorded cell (helper_3D.py:531); a coordinate >= depth raises IndexError there, reported here
 //     as status bit 1.
-#include "step_search.cuh"
+#include "maze3d_search.cuh"
 
 namespace pcgrl {
 
-constexpr int MAZE_QCAP = 256;    // FIFO ring capacity (entries); measured maximum with push filtering: 50
-#ifndef PCGRL_UF_RUNS32
-#define PCGRL_UF_RUNS32 1   // A/B on B200 (14^3): u16 per-cell parents / u32 run parents -> 2.12 / 2.26e7 env-steps/s
-#endif
-#ifndef PCGRL_MAZE_WARPS
-#define PCGRL_MAZE_WARPS 6   // A/B on B200 (14^3, 65 536 envs): 4 / 6 / 8 / 16 warps per CTA -> 1.81 / 2.13 / 2.05 / 1.41e7 env-steps/s
-#endif
-constexpr int MAZE_WARPS = PCGRL_MAZE_WARPS;     // small CTAs, several per SM: finer-grained tile barriers
-constexpr int MAZE_CTAS_PER_SM = 32 / MAZE_WARPS;
-constexpr int MAZE_MAX_CTAS = 160 * MAZE_CTAS_PER_SM;   // sizes the global scratch (>= 148 SMs x 8 CTAs)
-constexpr int MAZE_NJ_SLICE = 16 * 16 * 16 * 2;         // bytes of nj per warp (maps up to 16^3)
-constexpr int MAZE_ORDER_SLICE = (16 / 2 + 1) * 16 * 16 * 2;   // bytes of the first-recording order list per warp
-constexpr int MAZE_SLICE = MAZE_NJ_SLICE + MAZE_ORDER_SLICE;
 int64_t maze3d_scratch_bytes() { return (int64_t)MAZE_SLICE * MAZE_MAX_CTAS * MAZE_WARPS; }
-
-struct MazeLayout {
-    int best, q_cl, nj, order, q_nj, col, row, total, order_cap, best_bytes;
-};
-__host__ __device__ inline MazeLayout maze_layout(int Z, int Y, int X, int row_stride) {
-    MazeLayout L;
-    const int cells = Z * Y * X;
-    int bb = 2 * cells;
-    if (bb < row_stride) bb = row_stride;      // the raw grid is staged here first
-#if PCGRL_UF_RUNS32
-    if (bb < Z * Y * 32) bb = Z * Y * 32;      // ... and the region count's 32-bit run parents live here last
-#endif
-    bb = (bb + 15) / 16 * 16;
-    L.best_bytes = bb;
-    L.order_cap = (Z / 2 + 1) * Y * X;
-    int o = 0;
-    L.best = o;  o += bb;
-    L.q_cl = o;  o += 4 * MAZE_QCAP;
-    L.nj = -1;   // global scratch, see make_ctx
-    L.order = -1;   // global scratch too: appended by lane 0, re-read a handful of times per grid
-    L.q_nj = o;  o += 2 * MAZE_QCAP;
-    L.col = o;   o += 2 * Y * X;
-    L.row = o;   o += 2 * Z * Y;
-    L.total = (o + 15) / 16 * 16;
-    return L;
-}
-
-struct Maze3DProb {
-    static constexpr int K = 3;   // regions, path-length, n_jump
-
-    struct Ctx {
-        int Z, Y, X, cells, R;
-        uint32_t magic_xy, magic_x;
-        uint16_t *best, *nj, *order, *q_nj, *col, *row;
-        uint32_t* q_cl;
-        int best_bytes, order_cap;
-        int32_t* status;
-    };
-
-    __device__ static Ctx make_ctx(const KParams& p, uint8_t* ws, int global_warp) {
-        Ctx c;
-        c.Z = p.d0; c.Y = p.d1; c.X = p.d2;
-        c.cells = p.cells;
-        c.R = c.Z * c.Y;
-        c.magic_xy = div_magic(c.X * c.Y);
-        c.magic_x = div_magic(c.X);
-        const MazeLayout L = maze_layout(c.Z, c.Y, c.X, p.row_stride);
-        c.best = (uint16_t*)(ws + L.best);
-        c.q_cl = (uint32_t*)(ws + L.q_cl);
-        c.nj = (uint16_t*)((uint8_t*)p.scratch + (size_t)global_warp * MAZE_SLICE);
-        c.order = (uint16_t*)((uint8_t*)p.scratch + (size_t)global_warp * MAZE_SLICE + MAZE_NJ_SLICE);
-        c.q_nj = (uint16_t*)(ws + L.q_nj);
-        c.col = (uint16_t*)(ws + L.col);
-        c.row = (uint16_t*)(ws + L.row);
-        c.best_bytes = L.best_bytes;
-        c.order_cap = L.order_cap;
-        c.status = p.status;
-        return c;
-    }
-
-    // ---- helper_3D._passable for one direction: foothold reached from (x, y, z) going (dx, dy) ----------
-    // Returns false if the direction offers no move; else the foothold cell index, the number of path
-    // entries the move appends (1 walk, 2 stairs / level jump, 3 jump up / down) and whether it is a jump.
-    __device__ static __forceinline__ bool move(const Ctx& c, int x, int y, int z, int dx, int dy, int& ncell,
-                                                int& cost, int& jump) {
-        const int nx = x + dx, ny = y + dy;
-        if (nx < 0 || ny < 0 || nx >= c.X || ny >= c.Y) return false;                    // :225
-        const int Z = c.Z;
-        const uint32_t cn = c.col[ny * c.X + nx], c0 = c.col[y * c.X + x];
-#define AIR(m, k) (((m) >> (k)) & 1u)
-        jump = 0;
-        if ((z == 0 || !AIR(cn, z - 1)) && AIR(cn, z) && AIR(cn, z + 1)) {               // :229-237 walk
-            ncell = (z * c.Y + ny) * c.X + nx;
-            cost = 1;
-            return true;
-        }
-        if ((z == 1 || (z > 1 && !AIR(cn, z - 2))) && z >= 1 && AIR(cn, z - 1) && AIR(cn, z) && AIR(cn, z + 1)) {
-            ncell = ((z - 1) * c.Y + ny) * c.X + nx;                                     // :243-252 step down
-            cost = 2;
-            return true;
-        }
-        if (z + 2 < Z && !AIR(cn, z) && AIR(cn, z + 1) && AIR(cn, z + 2) && AIR(c0, z + 2)) {
-            ncell = ((z + 1) * c.Y + ny) * c.X + nx;                                     // :259-266 step up
-            cost = 2;
-            return true;
-        }
-        const int jx = nx + dx, jy = ny + dy;
-        if (z >= 2 && z + 2 < Z && ((cn >> (z - 2)) & 0x1Fu) == 0x1Fu && AIR(c0, z + 2) && jx >= 0 && jy >= 0 &&
-            jx < c.X && jy < c.Y) {                                                      // :279-288 jump over a gap
-            const uint32_t cj = c.col[jy * c.X + jx];
-            jump = 1;
-            if (AIR(cj, z + 1) && AIR(cj, z + 2) && AIR(cj, z) && !AIR(cj, z - 1)) {     // :289-296 level
-                ncell = (z * c.Y + jy) * c.X + jx;
-                cost = 2;
-                return true;
-            }
-            if (z + 3 < Z && AIR(cj, z + 3) && AIR(cj, z + 2) && AIR(cj, z + 1) && !AIR(cj, z)) {
-                ncell = ((z + 1) * c.Y + jy) * c.X + jx;                                 // :297-304 up
-                cost = 3;
-                return true;
-            }
-            if (AIR(cj, z) && AIR(cj, z + 1) && AIR(cj, z - 1) && !AIR(cj, z - 2)) {     // :305-312 down
-                ncell = ((z - 1) * c.Y + jy) * c.X + jx;
-                cost = 3;
-                return true;
-            }
-        }
-#undef AIR
-        return false;
-    }
-
-    // ---- helper_3D.run_dijkstra from `start` (warp-uniform FIFO; lanes 0..3 evaluate the 4 directions) -----
-    // Leaves order[0..n) = cells in first-recording order, best[c] & 0x7FFF = len(paths[c]), nj[c] = jumps[c].
-    __device__ static int search(Ctx& c, int start, int lane, bool& overflow) {
-        const int XY = c.X * c.Y;
-        unsigned head = 0, tail = 1;
-        int n = 0;
-        if (lane == 0) {
-            c.q_cl[0] = (uint32_t)start | (1u << 12);
-            c.q_nj[0] = 0;
-            c.best[start] = 1;
-        }
-        __syncwarp();
-        const int dx = lane == 0 ? 1 : (lane == 2 ? -1 : 0);       // helper_3D.py:220 direction order
-        const int dy = lane == 1 ? 1 : (lane == 3 ? -1 : 0);
-        while (head != tail) {
-            const uint32_t cl = c.q_cl[head & (MAZE_QCAP - 1)];
-            const int nj_e = c.q_nj[head & (MAZE_QCAP - 1)];
-            ++head;
-            const int cell = cl & 0xFFF, ln = cl >> 12;
-            const int z = div_by(cell, c.magic_xy), rem = cell - z * XY, y = div_by(rem, c.magic_x), x = rem - y * c.X;
-            const uint16_t b = c.best[cell];
-            const bool first = !(b & 0x8000u);
-            if (lane == 0) {
-                if (first) {
-                    if (n < c.order_cap) c.order[n] = (uint16_t)cell;
-                    c.best[cell] = b | 0x8000u;
-                }
-                c.nj[cell] = (uint16_t)nj_e;
-            }
-            n += first;
-            bool valid = false;
-            int ncell = 0, cost = 0, jump = 0;
-            if (lane < 4) {
-                valid = move(c, x, y, z, dx, dy, ncell, cost, jump);
-                if (valid) {
-                    const int nb = c.best[ncell] & 0x7FFF;
-                    if (nb != 0 && nb <= ln + cost) valid = false;   // would be skipped at pop (:437-440)
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, valid);
-            if (valid) {
-                const unsigned pos = (tail + __popc(m & ((1u << lane) - 1u))) & (MAZE_QCAP - 1);
-                c.q_cl[pos] = (uint32_t)ncell | ((uint32_t)(ln + cost) << 12);
-                c.q_nj[pos] = (uint16_t)(nj_e + jump);
-                c.best[ncell] = (uint16_t)((c.best[ncell] & 0x8000u) | (ln + cost));
-            }
-            tail += __popc(m);
-            if (tail - head > (unsigned)MAZE_QCAP || n > c.order_cap) {
-                overflow = true;
-                break;
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-        return n < c.order_cap ? n : c.order_cap;
-    }
-
-    // first maximum of len(paths[.]) in insertion order (np.argmax, helper_3D.py:538-541)
-    __device__ static __forceinline__ void far_tile(const Ctx& c, int n, int lane, int& cell, int& dist) {
-        uint32_t key = 0;
-        for (int i = lane; i < n; i += 32) {
-            const uint32_t k = ((uint32_t)(c.best[c.order[i]] & 0x7FFF) << 16) | (uint32_t)(0xFFFF - i);
-            key = max(key, k);
-        }
-        key = __reduce_max_sync(0xffffffffu, key);
-        cell = c.order[0xFFFF - (key & 0xFFFF)];
-        dist = key >> 16;
-    }
-
-    __device__ static __forceinline__ void clear_search(Ctx& c, int n, int lane) {
-        for (int i = lane; i < n; i += 32) c.best[c.order[i]] = 0;
-        __syncwarp();
-    }
-
-    __device__ static void stats(const KParams& p, Ctx& c, const int8_t* grid, int lane, int32_t* out) {
-        const int Z = c.Z, Y = c.Y, X = c.X, R = c.R;
-        // ---- stage the grid (coalesced 128-bit loads), build the row / column AIR masks --------------------
-        {
-            uint4* stage = (uint4*)c.best;
-            const uint4* src = (const uint4*)grid;
-            for (int i = lane; i < p.row_stride / 16; i += 32) stage[i] = src[i];
-            __syncwarp();
-            const uint8_t* g = (const uint8_t*)c.best;
-            for (int r = lane; r < R; r += 32) {
-                uint32_t m = 0;
-                for (int x = 0; x < X; ++x) m |= (uint32_t)(g[r * X + x] == 0) << x;
-                c.row[r] = (uint16_t)m;
-            }
-            for (int q = lane; q < Y * X; q += 32) {
-                uint32_t m = 0;
-                for (int z = 0; z < Z; ++z) m |= (uint32_t)(g[z * Y * X + q] == 0) << z;
-                c.col[q] = (uint16_t)m;
-            }
-            __syncwarp();
-            uint4* bz = (uint4*)c.best;
-            for (int i = lane; i < c.best_bytes / 16; i += 32) bz[i] = make_uint4(0, 0, 0, 0);
-            __syncwarp();
-        }
-
-        // ---- calc_longest_path (helper_3D.py:503-563) ---------------------------------------------------------
-        int final_value = 0, last_far = -1;
-        uint32_t planes = 0;
-        bool overflow = false, index_error = false;
-        for (int z = 1; z + 1 < Z; ++z) {
-            if ((planes >> z) & 1u) continue;                                            // :515
-            // start tiles of this plane: AIR with head-room (:520) standing on a solid tile (:525)
-            uint32_t cand = 0;
-            if (lane < Y) cand = c.row[z * Y + lane] & c.row[(z + 1) * Y + lane] & ~(uint32_t)c.row[(z - 1) * Y + lane];
-            const unsigned rows_with = __ballot_sync(0xffffffffu, cand != 0);
-            if (!rows_with) continue;
-            const int y = __ffs(rows_with) - 1;
-            const int x = __ffs(__shfl_sync(0xffffffffu, cand, y)) - 1;
-            const int start = (z * Y + y) * X + x;
-
-            int n = search(c, start, lane, overflow);                                    // :529
-            uint32_t mark = 0;
-            for (int i = lane; i < n; i += 32) {                                          // :531
-                const int cell = c.order[i];
-                const int cz = div_by(cell, c.magic_xy), rem = cell - cz * X * Y, cy = div_by(rem, c.magic_x),
-                          cx = rem - cy * X;
-                mark |= (1u << cx) | (1u << cy) | (1u << cz);
-            }
-            mark = __reduce_or_sync(0xffffffffu, mark);
-            if (mark >> Z) index_error = true;
-            planes |= mark;
-            int far, dist;
-            far_tile(c, n, lane, far, dist);                                             // :538-541
-            clear_search(c, n, lane);
-            n = search(c, far, lane, overflow);                                          // :548
-            far_tile(c, n, lane, far, dist);                                             // :549-552
-            last_far = far;                                                              // :553 last component wins
-            if (dist > final_value) final_value = dist;                                  // :558
-            clear_search(c, n, lane);
-            if (overflow) break;
-        }
-
-        // ---- calc_num_regions (helper_3D.py:396-406): 6-neighbour AIR components by union-find over runs ---
-#if PCGRL_UF_RUNS32
-        const int regions = count_regions_runs32(c.row, Z, Y, X, (uint32_t*)c.best, lane);
-#else
-        const int regions = count_regions_rows(c.row, Z, Y, X, c.best, lane);
-#endif
-
-        if (lane == 0) {
-            // jumps[far] of the last processed component: nj[] still holds that search's recordings (lane 0
-            // wrote them, so its own load sees them)
-            out[0] = regions;
-            out[1] = final_value;
-            out[2] = last_far >= 0 ? c.nj[last_far] : 0;
-            if (p.status && (index_error || overflow)) atomicOr(p.status, (index_error ? 2 : 0) | (overflow ? 4 : 0));
-        }
-    }
-};
 
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported) {
     supported = p.ndim == 3 && p.d0 <= 16 && p.d1 <= 16 && p.d2 <= 16 && p.d0 >= 1 && p.scratch != nullptr;

@@ -180,9 +180,44 @@ def minecraft_3d_maze_spec(map_shape):
         reward_weights={"regions": 0, "path-length": 100, "n_jump": 100})
 
 
+def minecraft_3d_holey_maze_spec(map_shape):
+    """minecraft/minecraft_3D_holey_maze_prob.py:26-61 on top of Minecraft3DmazeProblem's constructor.  Five stats:
+    the four get_stats returns (:124-130) plus `_next-path-length`, the length found by this call, which the
+    reference reports as path-length one call late (:92-93) -- carried in the stats so the kernel needs no other
+    per-env state (weight 0, not a metric)."""
+    s = minecraft_3d_maze_spec(map_shape)
+    mp = s.cond_bounds["path-length"][1]
+    s.name = "minecraft_3D_holey_maze"
+    s.stat_names = ["regions", "path-length", "connected-path-length", "n_jump", "_next-path-length"]
+    s.static_trgs = OrderedDict([("regions", 1), ("path-length", 10 * mp), ("n_jump", 5),
+                                 ("connected-path-length", 10 * mp)])
+    s.cond_bounds = {"regions": s.cond_bounds["regions"], "path-length": (0, mp + 2),
+                     "connected-path-length": (0, mp + 2), "n_jump": (0, mp // 2)}
+    s.reward_weights = {"regions": 0, "path-length": 100, "connected-path-length": 120, "n_jump": 150}
+    return s
+
+
+def minecraft_3d_dungeon_holey_spec(map_shape):
+    """minecraft/minecraft_3D_holey_dungeon_prob.py:17-93 (sizes from Minecraft3DmazeProblem's hard-coded 15^3)."""
+    w = h = l = 15
+    mp = float(2 * (h // 3) * (math.ceil(w / 2) * l + math.floor(l / 2)))
+    max_any = w * h * l // 4
+    return ProblemSpec(
+        name="minecraft_3D_dungeon_holey", tiles=["AIR", "DIRT", "CHEST", "SKULL", "PUMPKIN"],
+        stat_names=["regions", "path-length", "chests", "enemies", "nearest-enemy", "n_jump"],
+        init_probs=[1.0, 0.0, 0.0, 0.0, 0.0], border_tile="DIRT", ndim=3,
+        static_trgs=OrderedDict([("enemies", (2, 5)), ("regions", 1), ("path-length", 10 * mp),
+                                 ("nearest-enemy", (5, mp // 2)), ("chests", 1), ("n_jump", (2, 5))]),
+        cond_bounds={"regions": (0, float(math.ceil(w * l / 2 * h))), "path-length": (0, mp), "chests": (0, max_any),
+                     "n_jump": (0, mp // 2), "nearest-enemy": (0, mp // 2), "enemies": (0, max_any)},
+        reward_weights={"regions": 0, "path-length": 100, "chests": 300, "n_jump": 100, "enemies": 100,
+                        "nearest-enemy": 200})
+
+
 _SPECS = {"binary": binary_spec, "zelda": zelda_spec, "sokoban": sokoban_spec, "smb": smb_spec,
           "minecraft_3D_maze": minecraft_3d_maze_spec, "binary_holey": binary_holey_spec,
-          "minecraft_2D_maze": minecraft_2d_maze_spec}
+          "minecraft_2D_maze": minecraft_2d_maze_spec, "minecraft_3D_holey_maze": minecraft_3d_holey_maze_spec,
+          "minecraft_3D_dungeon_holey": minecraft_3d_dungeon_holey_spec}
 
 
 def get_spec(problem: str, map_shape) -> ProblemSpec:
@@ -196,8 +231,9 @@ def register_spec(name, fn):
     _SPECS[name] = fn
 
 
-PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze", "binary_holey", "minecraft_2D_maze"]
-HOLEY_PROBLEMS = ("binary_holey",)
+PROBLEM_NAMES = ["binary", "zelda", "sokoban", "smb", "minecraft_3D_maze", "binary_holey", "minecraft_2D_maze",
+                 "minecraft_3D_holey_maze", "minecraft_3D_dungeon_holey"]
+HOLEY_PROBLEMS = ("binary_holey", "minecraft_3D_holey_maze", "minecraft_3D_dungeon_holey")
 # envs/reps/__init__.py:11-23 (+ the stale 3D spellings)
 REPRESENTATION_ALIASES = {"narrow": "narrow", "turtle": "turtle", "wide": "wide", "cellular": "cellular",
                           "narrow3D": "narrow", "turtle3D": "turtle", "wide3D": "wide", "cellular3D": "cellular"}

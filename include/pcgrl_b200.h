@@ -36,7 +36,12 @@ enum { PCGRL_PROB_BINARY = 0, PCGRL_PROB_ZELDA = 1, PCGRL_PROB_SOKOBAN = 2, PCGR
        PCGRL_PROB_BINARY_HOLEY = 5,
        /* SURVEY 8f rank 4 -- minecraft_2D_maze (envs/probs/minecraft/minecraft_2D_maze_prob.py:87-93): regions and
           longest path over the "AIR" tile (code 0), i.e. the binary stats under other tile names */
-       PCGRL_PROB_MINECRAFT_2D_MAZE = 6 };
+       PCGRL_PROB_MINECRAFT_2D_MAZE = 6,
+       /* SURVEY 8f rank 2, the 3D holey problems (envs/probs/minecraft/minecraft_3D_holey_maze_prob.py:71-130,
+          minecraft_3D_holey_dungeon_prob.py:95-146, envs/probs/holey_prob_3D.py): stats on the bordered 3D map with a
+          two-tile-high entrance and exit dug into its sides; maps up to 14^3.  The holey maze has FIVE stats: the four
+          the reference returns plus the length found by this call, which the reference reports one call late */
+       PCGRL_PROB_MINECRAFT_3D_HOLEY_MAZE = 7, PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY = 8 };
 /* where reset takes the entrance / exit holes of a holey problem from (envs/probs/holey_prob.py:32-60 gen_holes) */
 enum {
     PCGRL_HOLES_GIVEN = 0,   /* leave pcgrl_state.holes as the caller set them (the reference's _hole_queue) */
@@ -147,7 +152,9 @@ typedef struct pcgrl_state {
                               caller-supplied src_grids it is left as the caller set it */
     int32_t* holes;        /* [N, 4] (ABI 4), holey problems only, else NULL: (entrance_y, entrance_x, exit_y, exit_x)
                               in BORDERED coordinates, i.e. the reference's entrance_coords / exit_coords
-                              (holey_prob.py:41-42).  Read by step; written by reset per cfg.hole_mode */
+                              (holey_prob.py:41-42).  Read by step; written by reset per cfg.hole_mode.
+                              3D holey problems: [N, 6] = (ez, ey, ex, xz, xy, xx), the FOOT tiles of the entrance and
+                              the exit; the head tile is the one above (holey_prob_3D.py:72-92) */
     uint8_t* records;      /* [N, pcgrl_record_stride(cfg)] (ABI 5) or NULL: one packed result record per env, what
                               step() returns besides the observation (pcgrl_env.py:329-342: reward, done, info stats):
                                 offset 0            float32 reward
@@ -209,7 +216,9 @@ int32_t pcgrl_reset(const pcgrl_config* cfg, const pcgrl_state* st, const uint8_
 int32_t pcgrl_stats(const pcgrl_config* cfg, const int8_t* grids, int32_t* stats, int64_t n, void* scratch,
                     void* stream);
 /* Same for a holey problem: holes [n, 4] int32 as in pcgrl_state.holes (BinaryHoleyProblem.get_stats reads
- * self.entrance_coords / self.exit_coords, binary_holey_prob.py:62-63). */
+ * self.entrance_coords / self.exit_coords, binary_holey_prob.py:62-63); [n, 6] for minecraft_3D_dungeon_holey; [n, 7]
+ * for minecraft_3D_holey_maze: the six coordinates and the path length the previous get_stats call on the same
+ * problem object found (reported as this call's path-length, minecraft_3D_holey_maze_prob.py:92-93; 0 at first). */
 int32_t pcgrl_stats_holey(const pcgrl_config* cfg, const int8_t* grids, const int32_t* holes, int32_t* stats,
                           int64_t n, void* scratch, void* stream);
 

@@ -459,6 +459,68 @@ def maze3d_holey_fixture():
     print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
 
 
+def maze3d_holey_dungeon_fixture():
+    """minecraft_3D_dungeon_holey: Minecraft3DholeyDungeonProblem.get_stats run verbatim on bordered maps with the
+    holes dug (the instance is made without its constructor chain, broken upstream like the other holey problems)."""
+    R.install()
+    import sys as _sys
+    import types as _types
+    _sys.modules["ray"].get = lambda x: x
+    mr = _sys.modules["control_pcgrl.envs.probs.minecraft.mc_render"]
+    setattr(mr, "spawn_3D_doors", lambda *a, **k: None)
+    _sys.modules.setdefault("control_pcgrl.envs.probs.minecraft.minecraft_pb2",
+                            _types.SimpleNamespace(BEDROCK=0, WOODEN_SLAB=0, LEAVES=0, TORCH=0, PURPUR_SLAB=0, WOOL=0))
+    if "sklearn.utils" not in _sys.modules or not hasattr(_sys.modules["sklearn.utils"], "check_X_y"):
+        sk = _types.ModuleType("sklearn")
+        sku = _types.ModuleType("sklearn.utils")
+        sku.check_X_y = lambda *a, **k: None
+        _sys.modules.setdefault("sklearn", sk)
+        _sys.modules["sklearn.utils"] = sku
+    H = R.load_helpers()
+    from control_pcgrl.envs.probs.minecraft.minecraft_3D_holey_dungeon_prob import Minecraft3DholeyDungeonProblem
+    TILES5 = ["AIR", "DIRT", "CHEST", "SKULL", "PUMPKIN"]
+    rng = np.random.default_rng(321)
+    arrays = {}
+    for gi, (size, trials) in enumerate([(7, 120), (10, 40), (14, 16)]):
+        p = object.__new__(Minecraft3DholeyDungeonProblem)
+        p._height = p._width = p._length = size
+        p._passable = set({"AIR", "CHEST", "SKULL", "PUMPKIN"})
+        p._hole_queue, p.fixed_holes = [], False
+        p._border_idxs = p.get_border_idxs()
+        maps, holes, stats = [], [], []
+        for trial in range(trials):
+            np.random.seed(5000 * gi + trial)
+            p.fixed_holes = trial % 4 == 3
+            ent, ext = p.gen_holes()
+            ent, ext = np.asarray(ent).astype(np.int64), np.asarray(ext).astype(np.int64)
+            p.entrance_coords, p.exit_coords = ent, ext
+            pr = [(0.55, 0.35, 0.04, 0.03, 0.03), (0.75, 0.2, 0.02, 0.02, 0.01), (0.5, 0.45, 0.0, 0.03, 0.02),
+                  (0.6, 0.36, 0.04, 0.0, 0.0)][trial % 4]
+            g = rng.choice(5, size=(size,) * 3, p=pr).astype(np.int8)
+            if trial % 6 == 0:
+                g[:] = 1
+                g[0:3] = 0            # an open hall on the floor with a chest and enemies in it
+                g[0, size // 2, size // 2] = 2
+                g[0, 1, 1] = 3
+                g[0, size - 2, 2] = 4
+            b = np.ones((size + 2,) * 3, dtype=np.int8)
+            b[1:-1, 1:-1, 1:-1] = g
+            for hh in (ent, ext):
+                for c in hh:
+                    b[c[0], c[1], c[2]] = 0
+            st = p.get_stats(H.h3.get_string_map(b, TILES5))
+            maps.append(b)
+            holes.append(np.stack([ent, ext]))
+            stats.append([int(st[k]) for k in STAT_NAMES["minecraft_3D_dungeon_holey"]])
+        arrays[f"maps_{gi}"] = np.stack(maps)
+        arrays[f"holes_{gi}"] = np.stack(holes).astype(np.int32)
+        arrays[f"stats_{gi}"] = np.array(stats, dtype=np.int64)
+    arrays["stat_names"] = np.array(STAT_NAMES["minecraft_3D_dungeon_holey"])
+    path = os.path.join(OUT, "stats_maze3d_holey_dungeon.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, {k: v.shape for k, v in arrays.items() if k.startswith("stats_")})
+
+
 # ------------------------------------------------------------------------------------------ traces
 def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None, n_envs=4, seed=0,
               max_board_scans=3, change_percentage=None, raw_only=False, n_steps=None, init_p=None,
@@ -665,6 +727,7 @@ def main(which=None):
     jobs["stats_binary_holey"] = binary_holey_fixture
     jobs["stats_minecraft_2D_maze"] = minecraft_2d_maze_fixture
     jobs["stats_maze3d_holey"] = maze3d_holey_fixture
+    jobs["stats_maze3d_holey_dungeon"] = maze3d_holey_dungeon_fixture
     for k, fn in jobs.items():
         if which and k not in which:
             continue

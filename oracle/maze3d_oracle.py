@@ -168,7 +168,7 @@ def maze3d_stats(grid, counters=None):
 
 
 # --------------------------------------------------------------------------------------------
-# minecraft_3D_holey_maze -- oracle only so far; the CUDA path is round-2 work
+# minecraft_3D_holey_maze / minecraft_3D_holey_dungeon
 # --------------------------------------------------------------------------------------------
 def moves_with_traversed(a, x, y, z, Z, Y, X):
     """helper_3D.py:214-319 _passable with the tiles each move passes through (they are appended to the path
@@ -257,3 +257,37 @@ def maze3d_holey_stats(bordered, entrance, exit_, prev_path_len):
     new_len = len(remove_stacked(paths[best]))                        # :94
     return ({"regions": count_regions_3d(air), "path-length": int(prev_path_len),
              "connected-path-length": int(connected), "n_jump": int(n_jump)}, new_len)
+
+
+def maze3d_holey_dungeon_stats(bordered, entrance, exit_):
+    """probs/minecraft/minecraft_3D_holey_dungeon_prob.py:95-146 on the bordered map (holes already dug).
+    Tiles: AIR 0, DIRT 1, CHEST 2, SKULL 3, PUMPKIN 4; the player walks through everything but DIRT (:27), regions
+    are counted over AIR only (:99).  entrance / exit_: ((z, y, x) foot, (z, y, x) head)."""
+    g = np.asarray(bordered)
+    Z, Y, X = g.shape
+    a = (g != 1).tolist()
+    chests = [(int(x), int(y), int(z)) for z, y, x in np.argwhere(g == 2)]          # get_tile_locations order z, y, x
+    enemies = [(int(x), int(y), int(z)) for z, y, x in np.argwhere((g == 3) | (g == 4))]
+    st = {"regions": count_regions_3d(g == 0), "path-length": 0, "chests": len(chests), "enemies": len(enemies),
+          "nearest-enemy": 0, "n_jump": 0}
+    ez, ey, ex = (int(v) for v in entrance[0])
+    dist = nj = None
+    if enemies:                                                                    # :113-124
+        _, dist, nj = search(a, ex, ey, ez, Z, Y, X)
+        best = 0
+        for e in enemies:
+            d = dist.get(e, 0)
+            if d > 0 and (d < best or best == 0):
+                best = d
+        st["nearest-enemy"] = best
+    if chests:                                                                     # :127-142
+        c = chests[0]
+        if dist is None:
+            _, dist, nj = search(a, ex, ey, ez, Z, Y, X)
+        st["path-length"] += dist.get(c, 0)
+        st["n_jump"] += nj.get(c, 0)
+        xz, xy, xx = (int(v) for v in exit_[0])
+        _, dist2, nj2 = search(a, c[0], c[1], c[2], Z, Y, X)
+        st["path-length"] += dist2.get((xx, xy, xz), 0)
+        st["n_jump"] += nj2.get((xx, xy, xz), 0)
+    return st

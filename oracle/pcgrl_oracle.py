@@ -31,6 +31,8 @@ TILES = {
     "minecraft_3D_maze": ["AIR", "DIRT"],                                           # minecraft_3D_maze_prob.py:26
     "binary_holey": ["empty", "solid"],                                             # binary_holey_prob.py:12-14
     "minecraft_2D_maze": ["AIR", "DIRT"],                                           # minecraft_2D_maze_prob.py:40-41
+    "minecraft_3D_holey_maze": ["AIR", "DIRT"],
+    "minecraft_3D_dungeon_holey": ["AIR", "DIRT", "CHEST", "SKULL", "PUMPKIN"],     # minecraft_3D_holey_dungeon_prob.py:18
 }
 STAT_NAMES = {
     "binary": ["regions", "path-length"],
@@ -41,6 +43,11 @@ STAT_NAMES = {
     "minecraft_3D_maze": ["regions", "path-length", "n_jump"],
     "binary_holey": ["regions", "path-length", "connected-path-length"],
     "minecraft_2D_maze": ["regions", "path-length"],
+    # minecraft_3D_holey_maze_prob.py:124-130 (+ the carried length of the path found by THIS call, which the next
+    # call reports as path-length, :92-93)
+    "minecraft_3D_holey_maze": ["regions", "path-length", "connected-path-length", "n_jump", "_next-path-length"],
+    # minecraft_3D_holey_dungeon_prob.py:99-106
+    "minecraft_3D_dungeon_holey": ["regions", "path-length", "chests", "enemies", "nearest-enemy", "n_jump"],
 }
 # tile init probabilities used by reset when no grid is supplied
 INIT_PROBS = {
@@ -281,9 +288,34 @@ def valid_holes(entrance, exit_, h, w):
     return max(abs(pts[0][0] - pts[1][0]), abs(pts[0][1] - pts[1][1])) > 1
 
 
-def get_stats(problem, grid, holes=None):
+def bordered_with_holes_3d(grid, holes, border_tile=1, empty_tile=0):
+    """The bordered 3D map of the holey minecraft problems with entrance and exit dug (foot + head tile each).
+    holes = (ez, ey, ex, xz, xy, xx), the foot tiles; the head is the tile above -- except the reference's default
+    exit (1, 1, 1) when no candidate was valid, whose head is the same tile (holey_prob_3D.py:86)."""
+    g = np.asarray(grid)
+    b = np.full(tuple(d + 2 for d in g.shape), border_tile, dtype=np.int64)
+    b[1:-1, 1:-1, 1:-1] = g
+    ez, ey, ex, xz, xy, xx = (int(v) for v in holes)
+    ent = ((ez, ey, ex), (ez + 1, ey, ex))
+    ext = ((xz, xy, xx), (xz, xy, xx) if (xz, xy, xx) == (1, 1, 1) else (xz + 1, xy, xx))
+    for c in ent + ext:
+        b[c] = empty_tile
+    return b, ent, ext
+
+
+def get_stats(problem, grid, holes=None, prev_path_length=0):
     if problem == "binary_holey":
         return binary_holey_stats(grid, holes)
+    if problem == "minecraft_3D_holey_maze":
+        from . import maze3d_oracle
+        b, ent, ext = bordered_with_holes_3d(grid, holes)
+        st, new_len = maze3d_oracle.maze3d_holey_stats(b, ent, ext, prev_path_length)
+        st["_next-path-length"] = new_len
+        return st
+    if problem == "minecraft_3D_dungeon_holey":
+        from . import maze3d_oracle
+        b, ent, ext = bordered_with_holes_3d(grid, holes)
+        return maze3d_oracle.maze3d_holey_dungeon_stats(b, ent, ext)
     if problem in ("binary", "minecraft_2D_maze"):
         # minecraft_2D_maze_prob.py:87-93: the same two helpers over ["AIR"], tile code 0 like binary's "empty"
         return binary_stats(grid)
@@ -322,6 +354,22 @@ def problem_constants(problem, map_shape):
         return dict(static_trgs={"regions": 1, "path-length": mp},
                     cond_bounds={"regions": (0, w * np.ceil(h / 2)), "path-length": (0, mp)},
                     default_weights={"regions": 100, "path-length": 100})
+    if problem in ("minecraft_3D_holey_maze", "minecraft_3D_dungeon_holey"):
+        # minecraft_3D_holey_maze_prob.py:33-61 / minecraft_3D_holey_dungeon_prob.py:43-82 on the hard-coded 15^3
+        w = h = l = 15
+        mp = 2 * (h // 3) * (np.ceil(w / 2) * l + np.floor(l / 2))
+        if problem == "minecraft_3D_holey_maze":
+            return dict(static_trgs={"regions": 1, "path-length": 10 * mp, "n_jump": 5, "connected-path-length": 10 * mp},
+                        cond_bounds={"regions": (0, np.ceil(w * l / 2 * h)), "path-length": (0, mp + 2),
+                                     "connected-path-length": (0, mp + 2), "n_jump": (0, mp // 2)},
+                        default_weights={"regions": 0, "path-length": 100, "connected-path-length": 120, "n_jump": 150})
+        ma = w * h * l // 4
+        return dict(static_trgs={"enemies": (2, 5), "regions": 1, "path-length": 10 * mp, "nearest-enemy": (5, mp // 2),
+                                 "chests": 1, "n_jump": (2, 5)},
+                    cond_bounds={"regions": (0, np.ceil(w * l / 2 * h)), "path-length": (0, mp), "chests": (0, ma),
+                                 "n_jump": (0, mp // 2), "nearest-enemy": (0, mp // 2), "enemies": (0, ma)},
+                    default_weights={"regions": 0, "path-length": 100, "chests": 300, "n_jump": 100, "enemies": 100,
+                                     "nearest-enemy": 200})
     if problem == "minecraft_2D_maze":
         # minecraft_2D_maze_prob.py:15-33: not a controllable problem upstream (no static_trgs / cond_bounds)
         return dict(static_trgs={}, cond_bounds={}, default_weights={"regions": 5, "path-length": 1})
@@ -585,6 +633,16 @@ class OracleEnv:
         self.coords = narrow_coords(self.map_shape) if self.act_window is None else \
             multiaction_coords(self.map_shape, self.act_window)
 
+    def _get_stats(self):
+        if self.holes is None:
+            return get_stats(self.problem, self.grid)
+        if self.problem == "minecraft_3D_holey_maze":
+            # the problem object lives across resets: path-length reports the previous call's path (:92-93)
+            st = get_stats(self.problem, self.grid, self.holes, getattr(self, "_prev_len", 0))
+            self._prev_len = st["_next-path-length"]
+            return st
+        return get_stats(self.problem, self.grid, self.holes)
+
     def reset(self, grid, pos=None, targets=None, static=None, holes=None):
         self.holes = None if holes is None else [int(v) for v in holes]   # pcgrl_holey_env.py:44-45
         if targets:
@@ -597,8 +655,7 @@ class OracleEnv:
                       "pos": [0] * len(self.map_shape) if pos is None else [int(v) for v in pos]}
         if self.rep == "narrow":
             self.state["pos"] = [int(v) for v in self.coords[0]]               # narrow_rep.py:43-50
-        self.stats = get_stats(self.problem, self.grid, self.holes) if self.holes is not None else \
-            get_stats(self.problem, self.grid)                                  # pcgrl_env.py:174-175
+        self.stats = self._get_stats()                                          # pcgrl_env.py:174-175
         self.last_loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)
         return self.stats
 
@@ -613,8 +670,7 @@ class OracleEnv:
             done = done or self.changes > self.max_changes                      # :308-309
         old_stats = self.stats
         if changed:
-            self.stats = get_stats(self.problem, self.grid, self.holes) if self.holes is not None else \
-                get_stats(self.problem, self.grid)                              # :314-323
+            self.stats = self._get_stats()                                      # :314-323
         if self.reward_mode == "range":                                         # legacy Problem.get_reward
             return legacy_reward(self.problem, self.stats, old_stats), bool(done), changed
         loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)

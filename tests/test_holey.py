@@ -264,3 +264,128 @@ def test_maze3d_holey_oracle_matches_reference_get_stats():
             stale += stats[i][1] > 0
         gi += 1
     assert total >= 290 and connected >= 20 and stale >= 100
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the 3D holey problems on the GPU: minecraft_3D_holey_maze, minecraft_3D_dungeon_holey
+# ---------------------------------------------------------------------------------------------------------------
+import torch  # noqa: E402
+from oracle import pcgrl_oracle as O  # noqa: E402
+
+
+def _holes6(h):
+    """fixture holes [n, 2 (entrance, exit), 2 (foot, head), 3 (z, y, x)] -> the kernel's [n, 6] foot tiles"""
+    return np.concatenate([h[:, 0, 0, :], h[:, 1, 0, :]], axis=1).astype(np.int32)
+
+
+def test_maze3d_holey_dungeon_oracle_matches_reference_get_stats():
+    from oracle import maze3d_oracle as M
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "stats_maze3d_holey_dungeon.npz"))
+    n = 0
+    for gi in range(3):
+        for b, h, want in zip(z[f"maps_{gi}"], z[f"holes_{gi}"], z[f"stats_{gi}"]):
+            st = M.maze3d_holey_dungeon_stats(b, h[0], h[1])
+            assert [int(st[k]) for k in O.STAT_NAMES["minecraft_3D_dungeon_holey"]] == want.tolist()
+            n += 1
+    assert n == 176
+
+
+@pytest.mark.gpu
+def test_maze3d_holey_kernel_matches_reference_fixture():
+    """minecraft_3D_holey_maze get_stats on the GPU against 291 sequential calls of the reference's problem object:
+    path-length is the de-stacked longest path of the PREVIOUS call (minecraft_3D_holey_maze_prob.py:92-93), so each
+    trial's calls are replayed in order, carrying `_next-path-length`."""
+    import control_pcgrl_b200 as P
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "stats_maze3d_holey.npz"))
+    total = 0
+    for gi in range(3):
+        maps, holes, stats, steps = z[f"maps_{gi}"], z[f"holes_{gi}"], z[f"stats_{gi}"], int(z[f"steps_{gi}"])
+        size = maps.shape[1] - 2
+        trials = len(maps) // steps
+        env = P.BatchedPcgrlEnv(P.make_config("minecraft_3D_holey_maze", "narrow", map_shape=(size,) * 3), 1)
+        prev = np.zeros(trials, dtype=np.int32)
+        for s in range(steps):
+            sel = np.arange(trials) * steps + s
+            got = env.compute_stats(maps[sel][:, 1:-1, 1:-1, 1:-1], holes=_holes6(holes[sel]),
+                                    prev_path_length=prev).cpu().numpy()
+            bad = np.flatnonzero((got[:, :4] != stats[sel]).any(axis=1))
+            assert bad.size == 0, (gi, s, bad[:4], got[bad[:4]], stats[sel][bad[:4]])
+            prev = got[:, 4].astype(np.int32)
+            total += len(sel)
+        env.check_status()
+    assert total == 291
+
+
+@pytest.mark.gpu
+def test_maze3d_holey_dungeon_kernel_matches_reference_fixture():
+    import control_pcgrl_b200 as P
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "stats_maze3d_holey_dungeon.npz"))
+    total = 0
+    for gi in range(3):
+        maps, holes, stats = z[f"maps_{gi}"], z[f"holes_{gi}"], z[f"stats_{gi}"]
+        size = maps.shape[1] - 2
+        env = P.BatchedPcgrlEnv(P.make_config("minecraft_3D_dungeon_holey", "narrow", map_shape=(size,) * 3), 1)
+        got = env.compute_stats(maps[:, 1:-1, 1:-1, 1:-1], holes=_holes6(holes)).cpu().numpy()
+        bad = np.flatnonzero((got != stats).any(axis=1))
+        assert bad.size == 0, (gi, bad[:4], got[bad[:4]], stats[bad[:4]])
+        total += len(maps)
+        env.check_status()
+    assert total == 176
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem,rep,fixed", [("minecraft_3D_holey_maze", "narrow", False),
+                                               ("minecraft_3D_holey_maze", "turtle", True),
+                                               ("minecraft_3D_dungeon_holey", "narrow", False),
+                                               ("minecraft_3D_dungeon_holey", "wide", True)])
+def test_holey3d_rollout_matches_oracle(problem, rep, fixed):
+    """Random resets (device-drawn holes: distinct border cells, entrance = the first, exit = the first valid one,
+    holey_prob_3D.py:72-100; or the fixed pair), then random edits: every env's stats / reward against the oracle
+    env, which carries the holey maze's one-call-late path length across steps and resets."""
+    import control_pcgrl_b200 as P
+    n, steps, size = 24, 30, 7
+    cfg = P.make_config(problem, rep, map_shape=(size,) * 3, fixed_holes=fixed, max_board_scans=0.05)
+    env = P.BatchedPcgrlEnv(cfg, n, seed=5, action_kind="wide_coords" if rep == "wide" else None, auto_reset=False)
+    n_tiles = env.n_tiles
+    rng = np.random.default_rng(1)
+    probs = [0.5, 0.5] if n_tiles == 2 else [0.5, 0.38, 0.04, 0.04, 0.04]
+    grids = rng.choice(n_tiles, size=(n, size, size, size), p=probs).astype(np.int8)
+    env.reset(grids=grids)
+    holes = env.holes.cpu().numpy()
+    # the generated holes are legal: foot tiles on the side faces (not on a vertical edge, not on the top layer),
+    # entrance != exit, and the reference's validity rule between them (or its (1, 1, 1) default)
+    for hz in holes:
+        for f in (hz[:3], hz[3:]):
+            if tuple(f) == (1, 1, 1):
+                continue
+            on_x = f[2] in (0, size + 1) and 1 <= f[1] <= size
+            on_y = f[1] in (0, size + 1) and 1 <= f[2] <= size
+            assert 1 <= f[0] <= size - 1 and (on_x != on_y), hz
+        if fixed:
+            assert hz.tolist() == [1, 0, size, 2, size + 1, 1]
+        elif tuple(hz[3:]) != (1, 1, 1):
+            d = max(abs(hz[0] - hz[3]), abs(hz[0] + 1 - hz[3]), abs(hz[1] - hz[4]), abs(hz[2] - hz[5]))
+            assert d > 1, hz
+    pos0 = env.pos.cpu().numpy()
+    oracles = []
+    for e in range(n):
+        o = O.OracleEnv(problem, rep, (size,) * 3, weights=dict(env.metric_weights), max_board_scans=0.05)
+        o.reset(grids[e], pos=pos0[e], holes=holes[e])
+        oracles.append(o)
+    st0 = env.stats.cpu().numpy()
+    for e, o in enumerate(oracles):
+        assert st0[e].tolist() == O.stats_vector(problem, o.stats), (e, st0[e], o.stats)
+    n_act = {"narrow": n_tiles, "turtle": 4 + n_tiles}.get(rep)
+    for t in range(steps):
+        if rep == "wide":
+            a = np.concatenate([rng.integers(0, size, size=(n, 3)), rng.integers(0, n_tiles, size=(n, 1))], axis=1).astype(np.int32)
+        else:
+            a = rng.integers(0, n_act, size=n).astype(np.int32)
+        reward, done = env.step(torch.from_numpy(a).to(env.device))
+        r_h, st_h, d_h = reward.cpu().numpy(), env.stats.cpu().numpy(), done.cpu().numpy()
+        for e, o in enumerate(oracles):
+            r, d, _ = o.step(a[e].tolist() if rep == "wide" else int(a[e]))
+            assert st_h[e].tolist() == O.stats_vector(problem, o.stats), (t, e, st_h[e], o.stats)
+            assert r_h[e] == pytest.approx(float(r), rel=1e-6, abs=1e-6), (t, e)
+            assert bool(d_h[e]) == d
+    env.check_status()
