@@ -10,7 +10,8 @@ timed region cause.  Prints ONE JSON line on rank 0 (see the task contract):
   value     whole-job env-steps/s, actions already resident in HBM (device-timed, max over ranks)
   e2e       same metric through the public host-buffer API (BatchedPcgrlEnv.step_host -> pcgrl_step_host):
             actions H2D from pinned memory, reward/done/stats D2H, every step, inside the timed region
-  roofline  dominant kernel (k_step_bitboard) vs measured HBM peak: algorithmic bytes/launch / event time
+  roofline  the step's kernels (binary: k_split_act + k_split_stats_inc + k_split_out, the search 80 % of it) vs the
+            measured HBM peak: algorithmic bytes per pcgrl_step / event time around it
   cpu_baseline  the oracle (python port of the reference path) timed on this box's host cores (bounded sample)
   configs   the other BASELINE.json configs (binary-wide + controls and zelda-turtle at 65 536 envs, sokoban-cellular,
             smb-narrow, minecraft 14^3), each a short run of the same three measurements (value / e2e / roofline /
@@ -338,8 +339,14 @@ def run_workload(a, workload, n_envs, steps, warmup, e2e_steps, rank, world, loc
     step_bytes = env.step_bytes()
     per_launch_ms = kern_ms / steps
     achieved = step_bytes * n_envs / (per_launch_ms * 1e-3) / 1e9
-    kernel = {"binary": "k_step_bitboard", "zelda": "k_step_bitboard", "binary_holey": "k_step_bitboard"}.get(
-        problem, "k_step_search")
+    if env.cache is not None:      # binary with the incremental search (csrc/step_split.cu), path by shard size
+        kernel = "k_split_act + k_split_stats_inc + k_split_out" if n_envs >= (160 << 10) else "k_step_inc"
+    elif problem in ("binary", "zelda", "binary_holey"):
+        kernel = "k_step_bitboard"
+    elif problem == "sokoban":
+        kernel = "k_step_search<SokobanProb> + k_sokoban_solve + k_sokoban_astar + k_sokoban_combine"
+    else:
+        kernel = "k_step_search"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": kernel, "algorithmic_bytes_per_env_step": step_bytes,
                 "kernel_ms_per_launch": per_launch_ms, "peak_source": peak_src,
