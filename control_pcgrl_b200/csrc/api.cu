@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "pcgrl_device.cuh"
 
@@ -245,10 +246,36 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
 // chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (two copy engines + the SMs).
 // Only for kernels that keep no cross-launch device state (scratch == 0, i.e. not the persistent solvers).
 constexpr int PIPE_STREAMS = 3;
+struct HostGraphKey {            // everything the queued operations depend on (compared bytewise)
+    pcgrl_config cfg;
+    pcgrl_state st;
+    void* actions_dev;
+    int64_t action_bytes;
+    int64_t has_host_actions;
+    void *reward_host, *done_host, *stats_host, *records_host;
+    int32_t chunks, chunk_path;
+};
+struct HostGraph {
+    struct Upload {
+        cudaGraphNode_t node;
+        void* dst;
+        int64_t off;
+        size_t bytes;
+    };
+    HostGraphKey key;
+    cudaGraph_t graph = nullptr;     // kept alive: the upload nodes updated in `exec` are named by their handles in it
+    cudaGraphExec_t exec = nullptr;
+    std::vector<Upload> h2d;
+    const void* last_src = nullptr;
+    int64_t launches = 0;
+};
 struct HostPipe {
-    bool ready = false;
+    static constexpr int MAX_GRAPHS = 8;
+    bool ready = false, graph_broken = false;
     cudaStream_t s[PIPE_STREAMS];
     cudaEvent_t fork, join[PIPE_STREAMS];
+    HostGraph graphs[MAX_GRAPHS];
+    unsigned next_graph = 0;
 };
 static thread_local HostPipe g_pipe[16];
 
@@ -458,58 +485,170 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
         if ((e = cudaEventCreateWithFlags(&hp.fork, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
         hp.ready = true;
     }
-    // helper streams start after everything already queued on the caller's stream (e.g. an auto-reset)
+    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;   // whole CTA tiles per chunk
+    const int64_t a_env = actions_host ? action_bytes / n : 0;
+    const int chunk_path = host_chunk_path(st->worklist && st->cache && cache_stride(cfg) > 0);
+
+    // Queue every chunk on its helper stream: upload, step, download.
+    auto enqueue_chunks = [&]() -> int {
+        int c = 0;
+        for (int64_t off = 0; off < n; off += per, ++c) {
+            const int64_t m = std::min(per, n - off);
+            cudaStream_t cs = hp.s[c % PIPE_STREAMS];
+            pcgrl_state sub = *st;
+            sub.n_envs = m;
+            sub.env_offset = st->env_offset + off;
+            sub.grids = st->grids + off * cfg->row_stride;
+            sub.pos = st->pos + off * 3;
+            sub.n_step = st->n_step + off;
+            sub.iteration = st->iteration + off;
+            sub.changes = st->changes + off;
+            sub.stats = st->stats + off * K;
+            sub.targets = st->targets + (cfg->targets_per_env ? off * K * 2 : 0);
+            sub.reward = st->reward + off;
+            sub.done = st->done + off;
+            sub.changed = st->changed ? st->changed + off : nullptr;
+            sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
+            sub.holes = st->holes ? st->holes + off * hole_ints(cfg) : nullptr;
+            sub.records = st->records ? st->records + off * rs : nullptr;
+            sub.cache = st->cache ? st->cache + off * cache_stride(cfg) : nullptr;
+            int64_t a_stride = a_env;
+            if (!actions_host) {   // actions already on the device: per-env stride from the action layout
+                a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)
+                         : cfg->action_kind == PCGRL_ACT_PATCH
+                             ? 4 * (int64_t)cfg->act_window[0] * cfg->act_window[1] * (cfg->ndim == 3 ? cfg->act_window[2] : 1)
+                         : cfg->action_kind == PCGRL_ACT_CA_TILES ? cfg->row_stride
+                         : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : action_elem(cfg);
+            }
+            char* a_dev = (char*)actions_dev + off * a_stride;
+            if (actions_host &&
+                (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
+                return cuda_fail(e, "H2D actions");
+            // every chunk gets its own header and its own body range of the shard's work list
+            int rr = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off, chunk_path);
+            if (rr) return rr;
+            if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+                return cuda_fail(e, "D2H records");
+            if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+                return cuda_fail(e, "D2H reward");
+            if (done_host && (e = cudaMemcpyAsync(done_host + off, sub.done, m, cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+                return cuda_fail(e, "D2H done");
+            if (stats_host && (e = cudaMemcpyAsync(stats_host + off * K, sub.stats, m * K * sizeof(int32_t), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+                return cuda_fail(e, "D2H stats");
+        }
+        return 0;
+    };
+
+    // ---- CUDA graph of the whole pipeline -------------------------------------------------------------------------
+    // A step of the host pipeline is ~25 queue operations (copies, launches, events over 3 streams) whose CPU cost sits
+    // on the critical path of every step: the first kernel cannot start before its upload is queued, and the call
+    // cannot return before the last event is.  The operations only depend on the pointers, so they are captured ONCE
+    // (stream capture on helper stream 0, the other two forked / joined by events inside the capture) and replayed
+    // with one cudaGraphLaunch; only the source addresses of the uploads change from step to step
+    // (cudaGraphExecMemcpyNodeSetParams1D).  PCGRL_HOST_GRAPH=0 queues the operations directly, as before.
+    static const bool use_graph = !(getenv("PCGRL_HOST_GRAPH") && atoi(getenv("PCGRL_HOST_GRAPH")) == 0);
+    if (use_graph && !hp.graph_broken) {
+        HostGraphKey key;
+        std::memset(&key, 0, sizeof(key));
+        key.cfg = *cfg;
+        key.st = *st;
+        key.actions_dev = actions_dev;
+        key.action_bytes = action_bytes;
+        key.has_host_actions = actions_host != nullptr;
+        key.reward_host = reward_host;
+        key.done_host = done_host;
+        key.stats_host = stats_host;
+        key.records_host = records_host;
+        key.chunks = chunks;
+        key.chunk_path = chunk_path;
+        HostGraph* hg = nullptr;
+        for (auto& g : hp.graphs)
+            if (g.exec && !std::memcmp(&g.key, &key, sizeof(key))) hg = &g;
+        if (!hg) {
+            HostGraph& slot = hp.graphs[hp.next_graph++ % HostPipe::MAX_GRAPHS];
+            if (slot.exec) cudaGraphExecDestroy(slot.exec);
+            if (slot.graph) cudaGraphDestroy(slot.graph);
+            slot.exec = nullptr;
+            slot.graph = nullptr;
+            slot.h2d.clear();
+            cudaGraph_t graph = nullptr;
+            bool ok = cudaStreamBeginCapture(hp.s[0], cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+            if (ok) {
+                ok = cudaEventRecord(hp.fork, hp.s[0]) == cudaSuccess;
+                for (int i = 1; ok && i < PIPE_STREAMS; ++i) ok = cudaStreamWaitEvent(hp.s[i], hp.fork, 0) == cudaSuccess;
+                const int64_t l0 = g_launches.load(std::memory_order_relaxed);
+                const int rr = ok ? enqueue_chunks() : -1;
+                slot.launches = g_launches.load(std::memory_order_relaxed) - l0;
+                g_launches.fetch_sub(slot.launches, std::memory_order_relaxed);   // captured, not run: replays count them
+                ok = ok && rr == 0;
+                for (int i = 1; i < PIPE_STREAMS; ++i) {   // always join, so that the capture can end
+                    const bool j1 = cudaEventRecord(hp.join[i], hp.s[i]) == cudaSuccess;
+                    const bool j2 = cudaStreamWaitEvent(hp.s[0], hp.join[i], 0) == cudaSuccess;
+                    ok = ok && j1 && j2;
+                }
+                ok = (cudaStreamEndCapture(hp.s[0], &graph) == cudaSuccess) && ok && graph;
+            }
+            if (ok) ok = cudaGraphInstantiate(&slot.exec, graph, 0) == cudaSuccess;
+            if (ok && actions_host) {   // the upload nodes, by destination address = chunk
+                size_t nn = 0;
+                ok = cudaGraphGetNodes(graph, nullptr, &nn) == cudaSuccess;
+                std::vector<cudaGraphNode_t> nodes(nn);
+                if (ok && nn) ok = cudaGraphGetNodes(graph, nodes.data(), &nn) == cudaSuccess;
+                for (size_t k = 0; ok && k < nn; ++k) {
+                    cudaGraphNodeType ty;
+                    if (cudaGraphNodeGetType(nodes[k], &ty) != cudaSuccess || ty != cudaGraphNodeTypeMemcpy) continue;
+                    cudaMemcpy3DParms mp;
+                    if (cudaGraphMemcpyNodeGetParams(nodes[k], &mp) != cudaSuccess) continue;
+                    const char* dst = (const char*)mp.dstPtr.ptr;
+                    if (dst < (const char*)actions_dev || dst >= (const char*)actions_dev + action_bytes) continue;
+                    HostGraph::Upload u;
+                    u.node = nodes[k];
+                    u.dst = (void*)dst;
+                    u.off = dst - (const char*)actions_dev;     // a_stride == a_env when the actions come from the host
+                    u.bytes = mp.extent.width;
+                    slot.h2d.push_back(u);
+                }
+                ok = ok && !slot.h2d.empty();
+            }
+            if (!ok) {
+                if (graph) cudaGraphDestroy(graph);
+                if (slot.exec) cudaGraphExecDestroy(slot.exec);
+                slot.exec = nullptr;
+                hp.graph_broken = true;     // e.g. a driver that cannot capture one of the operations: stay on the direct path
+                cudaGetLastError();
+            } else {
+                slot.key = key;
+                slot.graph = graph;
+                slot.last_src = nullptr;
+                hg = &slot;
+            }
+        }
+        if (hg) {
+            if (actions_host && hg->last_src != actions_host) {
+                for (const auto& u : hg->h2d)
+                    if ((e = cudaGraphExecMemcpyNodeSetParams1D(hg->exec, u.node, u.dst, (const char*)actions_host + u.off, u.bytes,
+                                                                cudaMemcpyHostToDevice)) != cudaSuccess)
+                        return cuda_fail(e, "graph upload update");
+                hg->last_src = actions_host;
+            }
+            // after everything already queued on the caller's stream; the caller's stream continues after the graph
+            if ((e = cudaEventRecord(hp.fork, s)) != cudaSuccess) return cuda_fail(e, "event record");
+            if ((e = cudaStreamWaitEvent(hp.s[0], hp.fork, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+            if ((e = cudaGraphLaunch(hg->exec, hp.s[0])) != cudaSuccess) return cuda_fail(e, "graph launch");
+            if ((e = cudaEventRecord(hp.join[0], hp.s[0])) != cudaSuccess) return cuda_fail(e, "event record");
+            if ((e = cudaStreamWaitEvent(s, hp.join[0], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+            if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(e, "stream sync");
+            // the launches inside the graph are replayed, not re-issued: count them for pcgrl_launch_count
+            g_launches.fetch_add(hg->launches, std::memory_order_relaxed);
+            return 0;
+        }
+    }
+
+    // ---- direct path: helper streams start after everything already queued on the caller's stream --------------------
     if ((e = cudaEventRecord(hp.fork, s)) != cudaSuccess) return cuda_fail(e, "event record");
     for (int i = 0; i < PIPE_STREAMS; ++i)
         if ((e = cudaStreamWaitEvent(hp.s[i], hp.fork, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
-
-    const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;   // whole CTA tiles per chunk
-    const int64_t a_env = actions_host ? action_bytes / n : 0;
-    int c = 0;
-    for (int64_t off = 0; off < n; off += per, ++c) {
-        const int64_t m = std::min(per, n - off);
-        cudaStream_t cs = hp.s[c % PIPE_STREAMS];
-        pcgrl_state sub = *st;
-        sub.n_envs = m;
-        sub.env_offset = st->env_offset + off;
-        sub.grids = st->grids + off * cfg->row_stride;
-        sub.pos = st->pos + off * 3;
-        sub.n_step = st->n_step + off;
-        sub.iteration = st->iteration + off;
-        sub.changes = st->changes + off;
-        sub.stats = st->stats + off * K;
-        sub.targets = st->targets + (cfg->targets_per_env ? off * K * 2 : 0);
-        sub.reward = st->reward + off;
-        sub.done = st->done + off;
-        sub.changed = st->changed ? st->changed + off : nullptr;
-        sub.static_mask = st->static_mask ? st->static_mask + off * cfg->row_stride : nullptr;
-        sub.holes = st->holes ? st->holes + off * hole_ints(cfg) : nullptr;
-        sub.records = st->records ? st->records + off * rs : nullptr;
-        sub.cache = st->cache ? st->cache + off * cache_stride(cfg) : nullptr;
-        int64_t a_stride = a_env;
-        if (!actions_host) {   // actions already on the device: per-env stride from the action layout
-            a_stride = cfg->action_kind == PCGRL_ACT_WIDE_COORDS ? 4 * (cfg->ndim + 1)
-                     : cfg->action_kind == PCGRL_ACT_PATCH
-                         ? 4 * (int64_t)cfg->act_window[0] * cfg->act_window[1] * (cfg->ndim == 3 ? cfg->act_window[2] : 1)
-                     : cfg->action_kind == PCGRL_ACT_CA_TILES ? cfg->row_stride
-                     : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : action_elem(cfg);
-        }
-        char* a_dev = (char*)actions_dev + off * a_stride;
-        if (actions_host &&
-            (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
-            return cuda_fail(e, "H2D actions");
-        // every chunk gets its own header and its own body range of the shard's work list
-        if ((r = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off,
-                             host_chunk_path(st->worklist && st->cache && cache_stride(cfg) > 0)))) return r;
-        if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-            return cuda_fail(e, "D2H records");
-        if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-            return cuda_fail(e, "D2H reward");
-        if (done_host && (e = cudaMemcpyAsync(done_host + off, sub.done, m, cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-            return cuda_fail(e, "D2H done");
-        if (stats_host && (e = cudaMemcpyAsync(stats_host + off * K, sub.stats, m * K * sizeof(int32_t), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
-            return cuda_fail(e, "D2H stats");
-    }
+    if ((r = enqueue_chunks())) return r;
     // join: later work on the caller's stream (auto-reset, observe) is ordered after every chunk
     for (int i = 0; i < PIPE_STREAMS; ++i) {
         if ((e = cudaEventRecord(hp.join[i], hp.s[i])) != cudaSuccess) return cuda_fail(e, "event record");
