@@ -223,7 +223,17 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 const int dl = D3 ? p.d2 : p.d1;
                 const int sl = D3 ? c2 + (int)q2 : c1 + (int)q1;
                 const int8_t* rowp = D3 ? grid + ((c0 + (int)q0) * p.d1 + (c1 + (int)q1)) * p.d2 : grid + (c0 + (int)q0) * p.d1;
-                if (sizeof(T) == 1 && ROWN == 8 && pack3) {
+                // which of the 8 pixels lie inside the map: most of a crop is padding (a 32x32 window on a 16x16 map
+                // is 75 % out of bounds), and such pixels need no grid load -- a whole group outside is a constant
+                const bool none_in = !row_ok || (CROP && (sl + 7 < 0 || sl >= dl));
+                if (sizeof(T) == 1 && ROWN == 8 && pack3 && none_in) {
+                    uint2* o8 = (uint2*)o;       // eight records "1 0 0"
+                    o8[0] = make_uint2(0x01000001u, 0x00010000u);
+                    o8[1] = make_uint2(0x00000100u, 0x01000001u);
+                    o8[2] = make_uint2(0x00010000u, 0x00000100u);
+                } else if (sizeof(T) == 1 && ROWN == 8 && pack1 && none_in) {
+                    *(uint2*)o = make_uint2(0u, 0u);
+                } else if (sizeof(T) == 1 && ROWN == 8 && pack3) {
                     // pixel k is the 24-bit value 1 << (8 * hot_k); four of them make three 32-bit words
                     uint32_t px[8];
 #pragma unroll
