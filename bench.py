@@ -296,7 +296,8 @@ def run_workload(a, workload, n_envs, steps, warmup, e2e_steps, rank, world, loc
     e2e = None
     if not a.no_e2e:
         rng = np.random.default_rng(a.seed + 100 + rank)
-        k_e2e = max(3, min(steps, e2e_steps))
+        # at least 50 host steps for the headline workload (20 steps are 8 ms: too short to average the host side)
+        k_e2e = max(3, min(steps, e2e_steps)) if e2e_steps < 200 else max(50, min(steps, e2e_steps))
         HP = min(k_e2e + 3, max(8, int(2e9 // bytes_a)))
         if rep == "cellular":
             host_acts = [act_pool[i % POOL].cpu().pin_memory() for i in range(HP)]
