@@ -1,11 +1,6 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02m_bench_steps20.json 2> gpurun_out/r02m.err; tail -2 gpurun_out/r02m.err
-python - <<'PY'
-import json
-d = json.loads(open("gpurun_out/r02m_bench_steps20.json").read().strip().splitlines()[-1])
-print("value %.4g e2e %.4g frac %.3f kernel_ms %.4f launches %d" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["kernel_ms_per_launch"], d["gpu_launches"]))
-print(d["roofline"]["kernel"], d["e2e"]["h2d_bytes_per_step"], d["e2e"]["d2h_bytes_per_step"], d["cpu_baseline"]["kind"], d["cpu_baseline"]["value"])
-PY
+timeout 1500 python -m pytest tests -m gpu -x -q -k "maze3d or holey or trace or fixtures or search" 2>&1 | tail -5
+timeout 300 python bench.py --workload minecraft_3D_maze-narrow-14x14x14 --steps 40 --warmup 4 --no-cpu-baseline 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('maze3d batch: value %.4g e2e %.4g kernel_ms %.3f' % (d['value'], d['e2e']['value'], d['roofline']['kernel_ms_per_launch']))"
+tail -3 gpurun_out/ab.err
