@@ -47,7 +47,7 @@ WORKLOADS = {
     "minecraft_3D_maze-narrow-14x14x14": ("minecraft_3D_maze", "narrow", (14, 14, 14), (14, 14, 14), None, 1 << 16),
     "sokoban-cellular-5x5": ("sokoban", "cellular", (5, 5), (5, 5), None, 1 << 20),
     "sokoban-narrow-5x5": ("sokoban", "narrow", (5, 5), (10, 10), None, 1 << 20),
-    "smb-narrow-116x16": ("smb", "narrow", (116, 16), (32, 32), None, 1 << 16),
+    "smb-narrow-116x16": ("smb", "narrow", (116, 16), (32, 32), None, 1 << 18),
 }
 # BASELINE.json configs 2-5 as (workload, envs per GPU, timed steps, warm-up steps, e2e steps): short runs printed
 # under "configs" next to the headline (config 1's shape at 1 Mi envs per GPU)
@@ -55,7 +55,7 @@ SECONDARY = [
     ("binary-wide-ctrl-16x16", 1 << 16, 300, 10, 60),
     ("zelda-turtle-7x11", 1 << 16, 300, 10, 60),
     ("sokoban-cellular-5x5", 1 << 20, 12, 3, 4),
-    ("smb-narrow-116x16", 1 << 16, 20, 3, 6),
+    ("smb-narrow-116x16", 1 << 18, 12, 3, 4),
     ("minecraft_3D_maze-narrow-14x14x14", 1 << 16, 30, 3, 8),
 ]
 METRIC = "env-steps/sec"
@@ -346,6 +346,8 @@ def run_workload(a, workload, n_envs, steps, warmup, e2e_steps, rank, world, loc
         kernel = "k_step_bitboard"
     elif problem == "sokoban":
         kernel = "k_step_search<SokobanProb> + k_sokoban_solve + k_sokoban_astar + k_sokoban_combine"
+    elif problem == "smb":
+        kernel = "k_step_search<SmbProb> + k_smb_solve + k_smb_fallback"
     else:
         kernel = "k_step_search"
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

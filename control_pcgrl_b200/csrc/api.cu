@@ -19,9 +19,9 @@ int bitboard_cache_stride(int problem, int ndim, int d0, int d1, int rep, int ac
 cudaError_t launch_maze3d(const KParams& p, cudaStream_t s, bool& supported);
 cudaError_t launch_maze3d_holey(const KParams& p, int problem, cudaStream_t s, bool& supported);
 cudaError_t launch_sokoban(const KParams& p, cudaStream_t s, bool& supported);
-cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported);
+cudaError_t launch_smb(const KParams& p, cudaStream_t s, bool& supported, int& n_launches);
 int64_t sokoban_scratch_bytes();
-int64_t smb_scratch_bytes();
+int64_t smb_scratch_bytes(int64_t n_envs);
 int64_t maze3d_scratch_bytes();
 cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const pcgrl_obs_args& o, cudaStream_t s);
 
@@ -209,6 +209,7 @@ static int check_state(const pcgrl_state* st) {
 static int run(const KParams& p, int cfg_problem, void* stream, int force_path = -1) {
     const int problem = kernel_problem(cfg_problem);
     bool supported = false;
+    int multi = 0;
     cudaError_t e;
     if (problem == PCGRL_PROB_MINECRAFT_3D_MAZE)
         e = launch_maze3d(p, (cudaStream_t)stream, supported);
@@ -217,7 +218,7 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
     else if (problem == PCGRL_PROB_SOKOBAN)
         e = launch_sokoban(p, (cudaStream_t)stream, supported);
     else if (problem == PCGRL_PROB_SMB)
-        e = launch_smb(p, (cudaStream_t)stream, supported);
+        e = launch_smb(p, (cudaStream_t)stream, supported, multi);   // map statistics + lane-group playthroughs + fallback
     else {
         const int path = force_path >= 0 ? force_path : step_path(p.n_envs);
         if (p.mode == MODE_STEP && p.worklist && path > 0) {
@@ -238,7 +239,7 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
                                          "pcgrl_scratch_bytes() > 0)");
     if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     // sokoban: step kernel + BFS jobs + A* jobs + combine (step_sokoban.cu)
-    g_launches.fetch_add(problem == PCGRL_PROB_SOKOBAN ? 4 : 1, std::memory_order_relaxed);
+    g_launches.fetch_add(problem == PCGRL_PROB_SOKOBAN ? 4 : (multi ? multi : 1), std::memory_order_relaxed);
     return 0;
 }
 // Chunked, stream-pipelined host step: the shard is cut into chunks of whole CTA tiles; chunk c's action
@@ -311,10 +312,9 @@ int32_t pcgrl_config_check(pcgrl_config* cfg) {
 
 int64_t pcgrl_scratch_bytes(const pcgrl_config* cfg, int64_t n_envs) {
     if (check(cfg)) return -1;
-    (void)n_envs;
     // node pools / heaps / hash tables of the solver problems: one slice per resident search warp
     if (cfg->problem == PCGRL_PROB_SOKOBAN) return sokoban_scratch_bytes();
-    if (cfg->problem == PCGRL_PROB_SMB) return smb_scratch_bytes();
+    if (cfg->problem == PCGRL_PROB_SMB) return smb_scratch_bytes(n_envs);   // + the per-env length history
     if (cfg->problem == PCGRL_PROB_MINECRAFT_3D_MAZE || is_holey3d(cfg)) return maze3d_scratch_bytes();   // jump counts, parents
     return 0;  // binary / zelda keep all search state in registers / shared memory
 }

@@ -14,7 +14,7 @@ constexpr int MAZE_QCAP = 256;    // FIFO ring capacity (entries); measured maxi
                              // A/B on B200 (14^3, 65 536 envs, bench workload): 1.45e7 against 2.25e7 env-steps/s -- the
                              // queue rarely holds more than 1-3 entries (a player's frontier in a 14^3 level is narrow:
                              // 1.4 entries per round on 50 % AIR maps), and a round costs about four one-pop iterations.
-                             // Parity is green either way (fixtures, traces, oracle rollouts, holey problems).
+                             // Parity is green either way (fixtures, traces, CPU-restatement rollouts, holey problems).
 #endif
 #if PCGRL_MAZE_BATCH
 #define PCGRL_MAZE_SEARCH search_batch

@@ -182,7 +182,8 @@ __device__ inline int count_regions_runs32(const uint16_t* row, int Z, int Y, in
 //   static __device__ Ctx make_ctx(const KParams&, uint8_t* warp_smem, int global_warp);
 //   static __device__ void stats(const KParams&, Ctx&, const int8_t* grid, int lane, int32_t* out /*smem [K]*/);
 template <class Prob, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, const int smem_per_warp, const int slot) {
+__global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, const int smem_per_warp, const int slot,
+                                                             const int64_t tile_begin, const int64_t tile_end) {
     constexpr int K = Prob::K;
     constexpr int TILE = SEARCH_TILE;
     constexpr int SEARCH_THREADS = WARPS * 32;
@@ -197,8 +198,6 @@ __global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, con
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int8_t* grids_in = (p.mode == MODE_STATS) ? p.stats_grids : p.grids;
     typename Prob::Ctx ctx = Prob::make_ctx(p, dyn_smem + (size_t)warp * smem_per_warp, blockIdx.x * WARPS + warp);
-    const int64_t n_tiles = (p.n_envs + TILE - 1) / TILE;
-
     for (;;) {
         __syncthreads();   // previous tile's phase D is done with the shared lists
         if (tid == 0) {
@@ -207,8 +206,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, con
             s_next = 0;
         }
         __syncthreads();
-        const int64_t tile = s_tile;
-        if (tile >= n_tiles) break;
+        const int64_t tile = tile_begin + s_tile;   // this launch covers tiles [tile_begin, tile_end)
+        if (tile >= tile_end) break;
         const int64_t base = tile * TILE;
         const int tile_n = (int)min((int64_t)TILE, p.n_envs - base);
         for (int e = tid; e < TILE; e += SEARCH_THREADS) {
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_step_search(const KParams p, con
 // host side: persistent launch sized from the occupancy the dynamic shared memory allows
 template <class Prob, int WARPS = SEARCH_WARPS>
 static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_warp, int max_ctas_per_sm = 1 << 20,
-                                 int max_ctas = SEARCH_MAX_CTAS) {
+                                 int max_ctas = SEARCH_MAX_CTAS, int64_t env_begin = 0, int64_t env_end = -1) {
     static int n_sm = 0;
     static std::atomic<unsigned> next_slot{0};
     constexpr int SEARCH_THREADS = WARPS * 32;
@@ -261,14 +260,17 @@ static cudaError_t launch_search(const KParams& p, cudaStream_t s, int smem_per_
     int per_sm = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SEARCH_THREADS, dyn)) != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
-    const int64_t tiles = (p.n_envs + SEARCH_TILE - 1) / SEARCH_TILE;
-    if (tiles == 0) return cudaSuccess;
+    // envs [env_begin, env_end) only (whole tiles; default: the whole shard) -- for problems that bound the work of a launch
+    if (env_end < 0 || env_end > p.n_envs) env_end = p.n_envs;
+    const int64_t tile_begin = env_begin / SEARCH_TILE, tile_end = (env_end + SEARCH_TILE - 1) / SEARCH_TILE;
+    const int64_t tiles = tile_end - tile_begin;
+    if (tiles <= 0) return cudaSuccess;
     if (per_sm > max_ctas_per_sm) per_sm = max_ctas_per_sm;
     int64_t cap = (int64_t)n_sm * per_sm;
     if (max_ctas_per_sm < (1 << 20) && cap > max_ctas) cap = max_ctas;   // the global scratch is sized for this
     const int ctas = (int)(tiles < cap ? tiles : cap);
     const int slot = (int)(next_slot.fetch_add(1) % SEARCH_SLOTS);
-    kern<<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp, slot);
+    kern<<<ctas, SEARCH_THREADS, dyn, s>>>(p, smem_per_warp, slot, tile_begin, tile_end);
     return cudaGetLastError();
 }
 

@@ -108,7 +108,8 @@ def test_smb_random_grids_vs_oracle():
     rng = np.random.default_rng(79)
     base = np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02])
     base /= base.sum()
-    for shape, n in [((116, 16), 60), ((16, 116), 30), ((14, 30), 100), ((6, 9), 100)]:
+    # (140, 12): the bit map does not fit a lane group's slice -> every level is played by the whole-warp fallback
+    for shape, n in [((116, 16), 60), ((16, 116), 30), ((14, 30), 100), ((6, 9), 100), ((140, 12), 16)]:
         grids = []
         for i in range(n):
             pr = base if i % 3 else rng.dirichlet(np.ones(7))
@@ -123,6 +124,24 @@ def test_smb_random_grids_vs_oracle():
         for i in range(n):
             want = O.stats_vector("smb", O.get_stats("smb", grids[i]))
             assert got[i].tolist() == want, (shape, i, got[i].tolist(), want)
+
+
+def test_smb_group_overflow_takes_the_fallback(monkeypatch):
+    """Levels whose heap outgrows a lane group's slice are played again by a whole warp (k_smb_fallback): with the
+    slice shrunk to 64 entries most random levels take that road, and the stats stay the oracle's."""
+    from oracle import pcgrl_oracle as O
+    rng = np.random.default_rng(5)
+    base = np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02])
+    base /= base.sum()
+    grids = rng.choice(7, size=(40, 16, 116), p=base).astype(np.int8)   # heaps of ~1 900 entries on these
+    env = _mk("smb", "narrow", (16, 116), 1)
+    full = env.compute_stats(grids).cpu().numpy()
+    monkeypatch.setenv("PCGRL_SMB_GROUP_CAP", "64")
+    small = env.compute_stats(grids).cpu().numpy()
+    env.check_status()
+    assert np.array_equal(full, small)
+    for i in range(0, 40, 4):
+        assert full[i].tolist() == O.stats_vector("smb", O.get_stats("smb", grids[i])), i
 
 
 @pytest.mark.parametrize("problem,rep,shape,n,n_steps", [("sokoban", "cellular", (5, 5), 65536, 6),
