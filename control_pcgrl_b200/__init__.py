@@ -2,7 +2,7 @@
 
 Public surface (mirrors the reference's names):
     make("binary-narrow-v0", cfg=cfg)      single-env gym façade          (control_pcgrl/__init__.py)
-    make_env(cfg)                          wrapped env as rl/envs.py builds it
+    make_env(cfg)                          wrapped env as rl/envs.py builds it (cfg.multiagent.n_agents: + MultiAgentWrapper)
     BatchedPcgrlEnv(cfg, n_envs)           N grids on one GPU, one fused launch per step
     PcgrlVectorEnv(cfg, num_envs)          vector-env seam with auto-reset and device observations
     make_rllib_vector_env(cfg, num_envs)   ray.rllib VectorEnv (vector_reset / reset_at / vector_step) over one shard
@@ -23,7 +23,7 @@ def __getattr__(name):
         from . import vector_env
         return getattr(vector_env, name)
     if name in ("PcgrlEnv", "PcgrlCtrlEnv", "PcgrlEnv3D", "ControlWrapper", "UniformNoiseyTargets", "make_env",
-                "CroppedImagePCGRLWrapper", "ActionMapImagePCGRLWrapper", "CAactionWrapper"):
+                "CroppedImagePCGRLWrapper", "ActionMapImagePCGRLWrapper", "CAactionWrapper", "MultiAgentWrapper"):
         from . import envs
         return getattr(envs, name)
     raise AttributeError(name)

@@ -36,7 +36,8 @@ _NULL_CTX = contextlib.nullcontext()
 class BatchedPcgrlEnv:
     def __init__(self, cfg, n_envs: int, device="cuda:0", env_offset: int = 0, seed: int = 0,
                  action_kind: str | None = None, auto_reset: bool = False, random_init_probs: bool = True,
-                 reward_mode: str = "control", compact_host_io: bool = False, split_step: bool = True):
+                 reward_mode: str = "control", compact_host_io: bool = False, split_step: bool = True,
+                 n_agents: int | None = None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise _lib.PcgrlError("control_pcgrl_b200 needs a CUDA device (there is no CPU fallback)")
@@ -74,6 +75,13 @@ class BatchedPcgrlEnv:
         self.param_ranges = {k: abs(self.cond_bounds[k][1] - self.cond_bounds[k][0]) for k in self.ctrl_metrics}
 
         rep = self.representation
+        # multi-agent (cfg.multiagent.n_agents; envs/reps/wrappers.py:612-651 MultiAgentTurtleRepresentation,
+        # wrappers.py:697-736 MultiAgentWrapper): every agent keeps its own turtle position on the shared map, and a
+        # multi-agent step is one full env step per agent, in agent order.  0 / 1 = the single-agent env.
+        self.n_agents = int(c.n_agents if n_agents is None else n_agents)
+        if self.n_agents > 1 and rep != "turtle":
+            raise ValueError("multi-agent envs need the turtle representation (upstream, MultiAgentNarrowRepresentation "
+                             "raises 'Busted for now', envs/reps/wrappers.py:669)")
         # representation wrappers (envs/reps/wrappers.py wrap_rep :717-722)
         self.act_window = c.act_window
         if self.act_window is not None:
@@ -159,7 +167,10 @@ class BatchedPcgrlEnv:
 
         N, dev = self.n_envs, self.device
         self.grids = torch.zeros((N, self.row_stride), dtype=torch.int8, device=dev)
-        self.pos = torch.zeros((N, 3), dtype=torch.int32, device=dev)
+        # agent_pos[a] is agent a's position tensor; a step / observation of agent a hands its pointer to the kernels
+        # as pcgrl_state.pos, so the single-agent layout (and every kernel) is unchanged
+        self.agent_pos = torch.zeros((max(self.n_agents, 1), N, 3), dtype=torch.int32, device=dev)
+        self.pos = self.agent_pos[0]
         self.n_step = torch.zeros(N, dtype=torch.int32, device=dev)
         self.iteration = torch.zeros(N, dtype=torch.int32, device=dev)
         self.changes = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -207,6 +218,11 @@ class BatchedPcgrlEnv:
         st.worklist = _ptr(self.worklist)
         st.cache = _ptr(self.cache)
         self._st = st
+        self._st_agents = [st]
+        for a in range(1, self.n_agents):
+            sa = _lib.State.from_buffer_copy(st)
+            sa.pos = self.agent_pos[a].data_ptr()
+            self._st_agents.append(sa)
 
     def _stat_bytes(self):
         """Narrowest record type that holds every stat of this problem.  binary family: region counts and path
@@ -361,8 +377,13 @@ class BatchedPcgrlEnv:
                 sel = mask.to(self.device).bool()
                 self.static_mask[sel, :self.cells] = sm[sel]
         sp = None
+        agent_sp = None
         if pos is not None:
             p = torch.as_tensor(np.asarray(pos) if not torch.is_tensor(pos) else pos).to(self.device, torch.int32)
+            if self.n_agents > 1:      # [N, n_agents, ndim]: every agent's spawn position
+                agent_sp = torch.zeros((self.n_agents, self.n_envs, 3), dtype=torch.int32, device=self.device)
+                agent_sp[:, :, :self.ndim] = p.reshape(self.n_envs, self.n_agents, self.ndim).permute(1, 0, 2)
+                p = agent_sp[0, :, :self.ndim]
             sp = torch.zeros((self.n_envs, 3), dtype=torch.int32, device=self.device)
             sp[:, :self.ndim] = p.reshape(self.n_envs, self.ndim)
         m = None
@@ -372,17 +393,90 @@ class BatchedPcgrlEnv:
         with self._on_device():
             _lib.check(self.lib.pcgrl_reset(cc, self._st, _ptr(m), _ptr(src), _ptr(sp), self.seed, self._epoch,
                                             self._stream()), "pcgrl_reset")
+        if self.n_agents > 1:
+            self._spawn_agents(agent_sp, m)
         self._synced_steps = 0 if mask is None else None
         return self.stats
 
-    def step(self, actions: torch.Tensor):
+    def _spawn_agents(self, given, mask):
+        """MultiAgentTurtleRepresentation.reset (envs/reps/wrappers.py:616-627): the agents start on distinct map
+        cells drawn without replacement (given: [n_agents, N, 3] explicit positions).  The draw is this env's own
+        (torch generator on the device): like every random reset it is outside the parity contract."""
+        A, N = self.n_agents, self.n_envs
+        if given is None:
+            g = torch.Generator(device=self.device).manual_seed((self.seed * 1000003 + self._epoch) & 0x7FFFFFFF)
+            picks = []
+            for a in range(A):
+                free = max(self.cells - a, 1)
+                r = torch.randint(0, free, (N,), generator=g, device=self.device)
+                if a < self.cells:          # the r-th cell that no earlier agent took
+                    prev = torch.sort(torch.stack(picks), dim=0).values if picks else None
+                    for q in range(len(picks)):
+                        r = r + (r >= prev[q]).to(r.dtype)
+                picks.append(r)
+            given = torch.zeros((A, N, 3), dtype=torch.int32, device=self.device)
+            for a in range(A):
+                rem = picks[a]
+                for ax in range(self.ndim - 1, -1, -1):
+                    given[a, :, ax] = (rem % self.map_shape[ax]).to(torch.int32)
+                    rem = rem // self.map_shape[ax]
+        if mask is None:
+            self.agent_pos.copy_(given)
+        else:
+            sel = mask.bool()
+            self.agent_pos[:, sel] = given[:, sel]
+
+    def _agent_state(self, agent):
+        if not 0 <= int(agent) < max(self.n_agents, 1):
+            raise IndexError(f"agent {agent} of {max(self.n_agents, 1)}")
+        return self._st_agents[int(agent)]
+
+    def step(self, actions: torch.Tensor, agent: int = 0):
         """One env-step for all N envs.  `actions` is a device tensor laid out per `action_kind`.
-        Returns (reward[N] f32, done[N] u8) device tensors (overwritten by the next step)."""
+        Returns (reward[N] f32, done[N] u8) device tensors (overwritten by the next step).
+        agent: with n_agents > 1, whose turtle acts (MultiAgentWrapper.step, wrappers.py:724-731, steps the env once
+        per agent)."""
         a = self._check_actions(actions)
         with self._on_device():
-            _lib.check(self.lib.pcgrl_step(self._cc, self._st, a.data_ptr(), self._stream()), "pcgrl_step")
-        self._after_step()
+            _lib.check(self.lib.pcgrl_step(self._cc, self._agent_state(agent), a.data_ptr(), self._stream()),
+                       "pcgrl_step")
+        if self.n_agents > 1 and self._in_agent_round:
+            if self._synced_steps is not None:
+                self._synced_steps += 1
+        else:
+            self._after_step()
         return self.reward, self.done
+
+    _in_agent_round = False
+
+    def step_agents(self, actions: torch.Tensor):
+        """One multi-agent step: actions[N, n_agents], agent a acts a-th (MultiAgentWrapper.step,
+        wrappers.py:724-731: a full env step per agent, so iteration advances by n_agents).  Returns
+        (reward[n_agents, N] f32, done[n_agents, N] u8); with auto_reset, envs restart once every agent of the round
+        saw done (the wrapper's done['__all__'])."""
+        A = max(self.n_agents, 1)
+        if actions.dim() != 2 or tuple(actions.shape) != (self.n_envs, A):
+            raise ValueError(f"actions must be [n_envs, n_agents] = {(self.n_envs, A)}")
+        rewards = torch.empty((A, self.n_envs), dtype=torch.float32, device=self.device)
+        dones = torch.empty((A, self.n_envs), dtype=torch.uint8, device=self.device)
+        self._in_agent_round = True
+        try:
+            for a in range(A):
+                r, d = self.step(actions[:, a].contiguous(), agent=a)
+                rewards[a].copy_(r)
+                dones[a].copy_(d)
+        finally:
+            self._in_agent_round = False
+        if self.auto_reset:
+            if self.max_changes is None and self._synced_steps is not None:
+                # lock-step: the round's first agent saw done iff its sub-step count exceeded max_iterations
+                if self._synced_steps - (A - 1) > self.max_iterations:
+                    self.reset()
+            else:
+                all_done = dones.min(dim=0).values
+                if bool(all_done.any()):
+                    self.reset(mask=all_done)
+        return rewards, dones
 
     def _after_step(self):
         if self._synced_steps is not None:
@@ -453,7 +547,7 @@ class BatchedPcgrlEnv:
             self._hio = h
         return h
 
-    def step_host(self, actions, want_stats=True):
+    def step_host(self, actions, want_stats=True, agent: int = 0):
         """End-to-end step with HOST buffers (the call timed as `e2e`): actions are copied H2D from pinned
         memory, the fused kernel runs, reward / done / stats are copied back, and the stream is synchronised.
         Large binary / zelda shards are cut into chunks whose upload, kernel and download overlap on helper
@@ -480,10 +574,10 @@ class BatchedPcgrlEnv:
             a_ptr = a_ptr[1]
         with self._on_device():
             if self.compact_host_io:
-                rc = self.lib.pcgrl_step_host_packed(self._cc, self._st, a_ptr, h.act_dev.data_ptr(), h.nbytes,
+                rc = self.lib.pcgrl_step_host_packed(self._cc, self._agent_state(agent), a_ptr, h.act_dev.data_ptr(), h.nbytes,
                                                      h.rec.data_ptr(), self._stream())
             else:
-                rc = self.lib.pcgrl_step_host(self._cc, self._st, a_ptr, h.act_dev.data_ptr(), h.nbytes,
+                rc = self.lib.pcgrl_step_host(self._cc, self._agent_state(agent), a_ptr, h.act_dev.data_ptr(), h.nbytes,
                                               h.r.data_ptr(), h.d.data_ptr(), h.s.data_ptr() if want_stats else None,
                                               self._stream())
         if rc:
@@ -544,12 +638,13 @@ class BatchedPcgrlEnv:
         ch += 1 if self.static_mask is not None else 0      # 'static_builds' plane (wrappers.py:451-453)
         return (*dims, ch)
 
-    def observe(self, out: torch.Tensor | None = None, dtype=torch.float32, onehot: bool = True):
+    def observe(self, out: torch.Tensor | None = None, dtype=torch.float32, onehot: bool = True, agent: int = 0):
         """The wrapped observation of every env: [N, *obs_dims, channels] (channels last), exactly what
         CroppedImagePCGRLWrapper / ActionMapImagePCGRLWrapper + ControlWrapper return per env.
         onehot=False (uint8 only, no controls): the tile codes of the crop instead of their one-hot records --
         Cropped's own output (wrappers.py:407-437: 0 = out of bounds, tile t -> t + 1), one channel, for policies
-        that embed the tile themselves."""
+        that embed the tile themselves.
+        agent: with n_agents > 1, whose crop (every agent sees the shared map around its own position)."""
         if self.holey and self.ndim == 3:
             raise NotImplementedError("observations of the 3D holey problems (the bordered 3D map) are not built yet; "
                                       "env.maps / env.holes hold the level and the holes")
@@ -580,7 +675,7 @@ class BatchedPcgrlEnv:
         oa.out = out.data_ptr()
         oa.static_channel = 1 if self.static_mask is not None else 0
         with self._on_device():
-            _lib.check(self.lib.pcgrl_observe(self._cc, self._st, oa, self._stream()), "pcgrl_observe")
+            _lib.check(self.lib.pcgrl_observe(self._cc, self._agent_state(agent), oa, self._stream()), "pcgrl_observe")
         return out
 
     STATUS_BITS = (
@@ -613,7 +708,7 @@ class BatchedPcgrlEnv:
         row = self.stats[i].tolist()
         return OrderedDict(zip(self.stat_names, row))
 
-    _STATE_TENSORS = ("grids", "pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes",
+    _STATE_TENSORS = ("grids", "agent_pos", "n_step", "iteration", "changes", "stats", "targets", "static_mask", "holes",
                       "records", "cache")
 
     def state_dict(self):

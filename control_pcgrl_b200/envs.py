@@ -115,6 +115,23 @@ class _RepProxy:
         self._random_start = True
         self._old_map = None
         self._bordered_map = None
+        # multi-agent (envs/reps/wrappers.py:548-651): which agent the next observation is for (None: all of them)
+        self._active_agent = None
+
+    @property
+    def n_agents(self):
+        return self._o._b.n_agents
+
+    @property
+    def agent_positions(self):
+        b = self._o._b
+        return b.agent_pos[:, 0, :b.ndim].cpu().numpy().astype(np.int64)
+
+    def set_active_agent(self, agent_name):
+        self._active_agent = agent_name
+
+    def _agent_index(self, agent_name):
+        return int(str(agent_name).split("_")[-1])
 
     @property
     def unwrapped(self):
@@ -154,6 +171,11 @@ class _RepProxy:
 
     def get_observation(self):
         obs = {"map": self._map.copy()}
+        if self._o._b.n_agents > 1:
+            # MultiAgentRepresentationWrapper.get_observation (:588-604): one dict per agent, or the active agent's
+            pos = self.agent_positions
+            names = [f"agent_{i}" for i in range(len(pos))] if self._active_agent is None else [self._active_agent]
+            return {k: {"map": obs["map"].copy(), "pos": pos[self._agent_index(k)]} for k in names}
         if self._o._b.representation in ("narrow", "turtle"):
             obs["pos"] = np.array(self._pos)
         if self._o._b.holey:
@@ -311,6 +333,16 @@ class PcgrlEnv(spaces.GymEnv):
     def _launch_step(self, action):
         b = self._b
         rep = self._repr_name
+        if b.n_agents > 1:
+            # MultiAgentTurtleRepresentation.update (:631-647) takes {agent name: action}; MultiAgentWrapper hands it
+            # one agent per env step (wrappers.py:724-731), which is what one kernel step does
+            if not isinstance(action, dict) or len(action) != 1:
+                raise ValueError("a multi-agent env steps one agent at a time: action = {'agent_i': a} "
+                                 "(control_pcgrl_b200.MultiAgentWrapper does the round)")
+            (name, act), = action.items()
+            a = torch.tensor([int(np.asarray(act).reshape(-1)[0])], dtype=torch.int32, device=b.device)
+            b.step(a, agent=self._rep._agent_index(name))
+            return
         if b.act_window is not None:
             a = torch.tensor(np.asarray(action, dtype=np.int32).reshape(1, -1), device=b.device)
         elif rep in ("narrow", "turtle"):
@@ -374,6 +406,11 @@ class _ObsWrapper(spaces.GymWrapper):
 
     def _obs(self):
         b = self.env.unwrapped._b
+        if b.n_agents > 1:      # the same crop per agent, around its own position
+            rp = self.env.unwrapped._rep
+            names = [f"agent_{i}" for i in range(b.n_agents)] if rp._active_agent is None else [rp._active_agent]
+            return {k: b.observe(dtype=torch.float64, agent=rp._agent_index(k))[0][..., 2 * len(b.ctrl_metrics):]
+                    .cpu().numpy() for k in names}
         full = b.observe(dtype=torch.float64)[0]
         return full[..., 2 * len(b.ctrl_metrics):].cpu().numpy()
 
@@ -516,6 +553,9 @@ class ControlWrapper(spaces.GymWrapper):
         if not self.controllable:
             return ob
         b = self.unwrapped._b
+        if b.n_agents > 1:
+            rp = self.unwrapped._rep
+            return {k: b.observe(dtype=torch.float64, agent=rp._agent_index(k))[0].cpu().numpy() for k in ob}
         return b.observe(dtype=torch.float64)[0].cpu().numpy()
 
     def reset(self, *, seed=None, options=None):
@@ -564,6 +604,31 @@ class UniformNoiseyTargets(spaces.GymWrapper):
         return self.env.step(action, **kw)
 
 
+class MultiAgentWrapper(spaces.GymWrapper):
+    """wrappers.py:697-736: Dict observation / action spaces keyed 'agent_i'; a step takes {agent: action} and steps
+    the env once per agent in dict order (each agent's observation is the one right after its own sub-step);
+    done['__all__'] / truncated['__all__'] = every agent of the round saw done."""
+
+    def __init__(self, game, cfg=None):
+        super().__init__(game)
+        self.n_agents = game.unwrapped._b.n_agents
+        self.observation_space = spaces.Dict({f"agent_{i}": game.observation_space for i in range(self.n_agents)})
+        self.action_space = spaces.Dict({f"agent_{i}": game.action_space for i in range(self.n_agents)})
+
+    def reset(self, *, seed=None, options=None):
+        return self.env.reset()
+
+    def step(self, action):
+        obs, rew, done, truncated, info = {}, {}, {}, {}, {}
+        for k, v in action.items():
+            self.unwrapped._rep.set_active_agent(k)
+            obs_k, rew[k], done[k], truncated[k], info[k] = self.env.step({k: v})
+            obs.update(obs_k)
+        truncated["__all__"] = bool(np.all(list(truncated.values())))
+        done["__all__"] = bool(np.all(list(done.values())))
+        return obs, rew, done, truncated, info
+
+
 def make_env(cfg, device="cuda:0"):
     """rl/envs.py:28-81 make_env: pick the wrapper stack by representation, then ControlWrapper."""
     if isinstance(cfg, dict) and "task" in cfg and not hasattr(cfg, "task"):
@@ -581,4 +646,6 @@ def make_env(cfg, device="cuda:0"):
     env = ControlWrapper(env, ctrl_metrics=c.controls, cfg=cfg)
     if c.controls and not getattr(cfg, "evaluate", False):
         env = UniformNoiseyTargets(env, cfg)
+    if c.n_agents != 0:                                                          # rl/envs.py:74-75
+        env = MultiAgentWrapper(env, cfg)
     return env

@@ -637,6 +637,87 @@ def run_trace(name, problem, rep, map_shape, obs_window, weights, controls=None,
     print("wrote", path, "steps", [arrays[f"rewards_{e}"].shape[0] for e in range(n_envs)], "bytes", os.path.getsize(path))
 
 
+def multiagent_fixture():
+    """Multi-agent turtle through the reference's real stack: CroppedImagePCGRLWrapper + ControlWrapper +
+    MultiAgentWrapper (rl/envs.py:28-76, wrappers.py:697-736) over MultiAgentTurtleRepresentation
+    (envs/reps/wrappers.py:612-651).  One multi-agent step is one full env step per agent, in dict order; every
+    agent's observation is taken right after its own sub-step.  -> tests/golden/multiagent_turtle.npz"""
+    import random as _random
+    from types import SimpleNamespace
+    R.install()
+    from control_pcgrl import wrappers
+    ZP = [0.58, 0.3, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02]
+    cases = [("binary", (8, 8), (16, 16), BINARY_W, 2, None, None, 3),
+             ("zelda", (7, 11), (22, 22), ZELDA_W, 3, ZP, None, 2),
+             ("binary", (10, 6), (20, 20), BINARY_W, 4, None, 0.3, 2)]
+    arrays = {"n_cases": np.array(len(cases))}
+    for ci, (problem, map_shape, obs_window, weights, n_agents, init_p, chg_pct, n_envs) in enumerate(cases):
+        rng = np.random.default_rng(900 + ci)
+        cfg = R.make_cfg(problem, "turtle", map_shape, obs_window=obs_window, weights=weights,
+                         change_percentage=chg_pct)
+        cfg.multiagent = SimpleNamespace(n_agents=n_agents)
+        n_tiles = len(TILES[problem])
+        arrays[f"c{ci}_problem"] = np.array(problem)
+        arrays[f"c{ci}_map_shape"] = np.array(map_shape)
+        arrays[f"c{ci}_obs_window"] = np.array(obs_window)
+        arrays[f"c{ci}_n_agents"] = np.array(n_agents)
+        arrays[f"c{ci}_n_envs"] = np.array(n_envs)
+        arrays[f"c{ci}_change_percentage"] = np.array(-1.0 if chg_pct is None else chg_pct)
+        arrays[f"c{ci}_weight_keys"] = np.array(list(weights.keys()), dtype=str)
+        arrays[f"c{ci}_weight_vals"] = np.array(list(weights.values()), dtype=np.float64)
+        for e in range(n_envs):
+            env = R.make_wrapped_env(cfg)
+            menv = wrappers.MultiAgentWrapper(env, cfg)
+            env.unwrapped.seed(7000 + 31 * ci + e)
+            np.random.seed(7100 + 31 * ci + e)
+            _random.seed(7200 + 31 * ci + e)
+            g0 = (rng.integers(0, n_tiles, size=map_shape) if init_p is None else
+                  rng.choice(n_tiles, size=map_shape, p=init_p)).astype(np.uint8)
+            R.inject_map(env, g0)
+            obs, _ = menv.reset()
+            u = env.unwrapped
+            rep = u._rep
+            names = [f"agent_{i}" for i in range(n_agents)]
+            pos0 = np.array(rep.agent_positions, dtype=np.int64).copy()
+            obs0 = np.stack([np.asarray(obs[k], dtype=np.float64) for k in names])
+            stats0 = [int(u._rep_stats[k]) for k in STAT_NAMES[problem]]
+            acts, rews, dones, stats, poss, grids, obs_l, obs_s, its, chg = [], [], [], [], [], [], [], [], [], []
+            t, all_done = 0, False
+            while not all_done and t < 600:
+                a = {k: int(rng.integers(env.action_space.n)) for k in names}
+                # the wrapper steps the agents one after the other; the per-agent stats / positions are read by
+                # doing the same loop here (wrappers.py:724-731)
+                st_t, pos_t, rew_t, done_t, ob_t = [], [], [], [], []
+                for k in names:
+                    u._rep.set_active_agent(k)
+                    ob_k, r_k, d_k, tr_k, info_k = env.step({k: a[k]})
+                    st_t.append([int(u._rep_stats[m]) for m in STAT_NAMES[problem]])
+                    pos_t.append(np.array(rep.agent_positions, dtype=np.int64).copy())
+                    rew_t.append(float(r_k))
+                    done_t.append(bool(d_k))
+                    ob_t.append(np.asarray(ob_k[k], dtype=np.float64))
+                acts.append([a[k] for k in names]); rews.append(rew_t); dones.append(done_t); stats.append(st_t)
+                poss.append(pos_t)
+                its.append(int(info_k["iterations"])); chg.append(int(info_k["changes"]))
+                grids.append(np.array(rep.unwrapped._map, dtype=np.uint8))
+                if t % 37 == 0:
+                    obs_l.append(np.stack(ob_t)); obs_s.append(t)
+                all_done = all(done_t)
+                t += 1
+            pre = f"c{ci}_e{e}_"
+            arrays[pre + "grid0"] = g0; arrays[pre + "pos0"] = pos0; arrays[pre + "obs0"] = obs0
+            arrays[pre + "stats0"] = np.array(stats0)
+            arrays[pre + "actions"] = np.array(acts); arrays[pre + "rewards"] = np.array(rews)
+            arrays[pre + "dones"] = np.array(dones); arrays[pre + "stats"] = np.array(stats)
+            arrays[pre + "pos"] = np.array(poss); arrays[pre + "grids"] = np.stack(grids)
+            arrays[pre + "obs"] = np.stack(obs_l); arrays[pre + "obs_step"] = np.array(obs_s)
+            arrays[pre + "iterations"] = np.array(its); arrays[pre + "changes"] = np.array(chg)
+            print("multiagent", problem, map_shape, "agents", n_agents, "env", e, "steps", t)
+    path = os.path.join(OUT, "multiagent_turtle.npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", path, "bytes", os.path.getsize(path))
+
+
 def main(which=None):
     os.makedirs(OUT, exist_ok=True)
     jobs = {
@@ -669,6 +750,7 @@ def main(which=None):
     SMB_P = list(np.array([0.75, 0.1, 0.01, 0.04, 0.01, 0.02, 0.02]) / 0.95)
     jobs.update({
         "legacy_reward": legacy_reward_fixture,
+        "multiagent_turtle": multiagent_fixture,
         "stats_sokoban": lambda: save_stats_fixture("sokoban", sokoban_grids()),
         "stats_smb": lambda: save_stats_fixture("smb", smb_grids()),
         "stats_maze3d": lambda: save_stats_fixture("minecraft_3D_maze", maze3d_grids(), "maze3d"),

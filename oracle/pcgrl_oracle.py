@@ -643,7 +643,9 @@ class OracleEnv:
             return st
         return get_stats(self.problem, self.grid, self.holes)
 
-    def reset(self, grid, pos=None, targets=None, static=None, holes=None):
+    def reset(self, grid, pos=None, targets=None, static=None, holes=None, agent_pos=None):
+        # multi-agent turtle (envs/reps/wrappers.py:612-651): one position per agent, spawned by the wrapper
+        self.agent_pos = None if agent_pos is None else [[int(v) for v in q] for q in agent_pos]
         self.holes = None if holes is None else [int(v) for v in holes]   # pcgrl_holey_env.py:44-45
         if targets:
             self.targets.update(targets)                                        # control_wrappers.py:170-178
@@ -659,9 +661,15 @@ class OracleEnv:
         self.last_loss = control_loss(self.stats, self.targets, self.weights, self.metrics_used)
         return self.stats
 
-    def step(self, action):
+    def step(self, action, agent=None):
+        """agent: MultiAgentWrapper.step (wrappers.py:724-731) is one full env step per agent, in dict order;
+        MultiAgentTurtleRepresentation.update :631-647 runs the turtle update at that agent's position."""
         self.iteration += 1                                                     # pcgrl_env.py:279
+        if agent is not None:
+            self.state["pos"] = list(self.agent_pos[agent])
         change = rep_update(self.rep, self.grid, self.state, action)
+        if agent is not None:
+            self.agent_pos[agent] = [int(v) for v in self.state["pos"]]
         changed = change > 0
         if changed:
             self.changes += change

@@ -61,3 +61,26 @@ TRACES_WRAPPED = ["binary_patch33", "binary_patch42_chg", "zelda_squeegee", "maz
                   "zelda_static_turtle", "binary_static_patch", "sokoban_static_narrow"]
 # traces that stop before the episode ends (n_steps cap in oracle/gen_golden.py)
 TRACES_OPEN_ENDED = ("binary_cellular", "smb_narrow", "maze3d_narrow", "maze3d_cellular")
+
+
+def load_multiagent():
+    """tests/golden/multiagent_turtle.npz (oracle/gen_golden.py multiagent_fixture) -> list of cases, each a dict with
+    problem, map_shape, obs_window, n_agents, change_percentage, weights and `envs` (per-env arrays: grid0, pos0
+    [A, nd], obs0 [A, ...], stats0, actions [T, A], rewards [T, A], dones [T, A], stats [T, A, K], pos [T, A, A, nd]
+    (all agents' positions after each agent's sub-step), grids [T, ...] (after the whole multi-agent step), obs,
+    obs_step, iterations, changes)."""
+    z = np.load(os.path.join(GOLDEN, "multiagent_turtle.npz"))
+    cases = []
+    for ci in range(int(z["n_cases"])):
+        cp = float(z[f"c{ci}_change_percentage"])
+        c = dict(problem=str(z[f"c{ci}_problem"]), map_shape=tuple(int(v) for v in z[f"c{ci}_map_shape"]),
+                 obs_window=tuple(int(v) for v in z[f"c{ci}_obs_window"]), n_agents=int(z[f"c{ci}_n_agents"]),
+                 change_percentage=None if cp < 0 else cp,
+                 weights={str(k): float(v) for k, v in zip(z[f"c{ci}_weight_keys"], z[f"c{ci}_weight_vals"])}, envs=[])
+        for e in range(int(z[f"c{ci}_n_envs"])):
+            pre = f"c{ci}_e{e}_"
+            c["envs"].append({k: z[pre + k] for k in ("grid0", "pos0", "obs0", "stats0", "actions", "rewards", "dones",
+                                                      "stats", "pos", "grids", "obs", "obs_step", "iterations",
+                                                      "changes")})
+        cases.append(c)
+    return cases

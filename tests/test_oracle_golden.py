@@ -84,6 +84,36 @@ def test_trace_matches_reference(name):
         replay_oracle(tr, e)
 
 
+def test_multiagent_turtle_matches_reference():
+    """Multi-agent turtle: the reference's CroppedImagePCGRLWrapper + ControlWrapper +
+    MultiAgentWrapper stack, replayed by the restatement sub-step by sub-step."""
+    from tests.golden_util import load_multiagent
+    for c in load_multiagent():
+        n_tiles = len(O.TILES[c["problem"]])
+        for d in c["envs"]:
+            env = O.OracleEnv(c["problem"], "turtle", c["map_shape"], weights=c["weights"],
+                              change_percentage=c["change_percentage"])
+            st0 = env.reset(d["grid0"], agent_pos=d["pos0"])
+            assert O.stats_vector(c["problem"], st0) == [int(v) for v in d["stats0"]]
+            for i in range(c["n_agents"]):
+                got = O.cropped_onehot(env.grid, env.agent_pos[i], c["obs_window"], n_tiles)
+                np.testing.assert_allclose(got, d["obs0"][i], rtol=1e-12, atol=0)
+            for t in range(len(d["actions"])):
+                for i in range(c["n_agents"]):
+                    r, done, _ = env.step(int(d["actions"][t][i]), agent=i)
+                    assert done == bool(d["dones"][t][i]), (t, i)
+                    assert r == pytest.approx(float(d["rewards"][t][i]), rel=1e-6, abs=1e-9), (t, i)
+                    assert O.stats_vector(c["problem"], env.stats) == [int(v) for v in d["stats"][t][i]], (t, i)
+                    assert env.agent_pos == d["pos"][t][i].tolist(), (t, i)
+                    if t in d["obs_step"]:
+                        want = d["obs"][list(d["obs_step"]).index(t)][i]
+                        got = O.cropped_onehot(env.grid, env.agent_pos[i], c["obs_window"], n_tiles)
+                        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+                assert np.array_equal(env.grid, d["grids"][t]), t
+                assert env.iteration == int(d["iterations"][t]) and env.changes == int(d["changes"][t])
+            assert bool(d["dones"][-1].all())
+
+
 def test_legacy_range_reward_matches_reference():
     """Problem.get_reward of the reference's non-ctrl classes (fixture: oracle/gen_golden.py legacy_reward)."""
     import os
