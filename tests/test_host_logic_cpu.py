@@ -66,6 +66,24 @@ def test_problem_tables_match_reference_classes(problem, shape):
     assert ref._border_tile == spec.border_tile
 
 
+@pytest.mark.needs_reference
+@pytest.mark.parametrize("mod,cls", [("microstructure.microstructure_prob", "MicroStructureProblem"),
+                                     ("ddave.ddave_prob", "DDaveProblem"), ("mdungeon.mdungeon_prob", "MDungeonProblem"),
+                                     ("loderunner_prob", "LoderunnerProblem"),
+                                     ("loderunner_ctrl_prob", "LoderunnerCtrlProblem")])
+def test_unbuilt_rank4_problems_are_dead_upstream(mod, cls):
+    """the helper-based problems that are NOT built cannot be constructed in the reference at
+    this commit -- `__init__(self)` calls `super().__init__()` while Problem.__init__ needs the config."""
+    import importlib
+    from oracle import refshim as R
+    R.install()
+    C = getattr(importlib.import_module("control_pcgrl.envs.probs." + mod), cls)
+    with pytest.raises(TypeError):
+        C(cfg=R.make_cfg("binary", "narrow", (8, 8)))
+    with pytest.raises(TypeError):
+        C()
+
+
 def test_shard_range_partitions_exactly():
     for n in (0, 1, 7, 65536, 1000003):
         for w in (1, 2, 3, 8):
