@@ -645,9 +645,6 @@ class BatchedPcgrlEnv:
         Cropped's own output (wrappers.py:407-437: 0 = out of bounds, tile t -> t + 1), one channel, for policies
         that embed the tile themselves.
         agent: with n_agents > 1, whose crop (every agent sees the shared map around its own position)."""
-        if self.holey and self.ndim == 3:
-            raise NotImplementedError("observations of the 3D holey problems (the bordered 3D map) are not built yet; "
-                                      "env.maps / env.holes hold the level and the holes")
         if not onehot:
             if self.ctrl_metrics or (out is not None and out.dtype != torch.uint8):
                 raise ValueError("onehot=False is a uint8 observation without control planes")

@@ -28,8 +28,9 @@ struct ObsParams {
     const int32_t* stats;
     const double* targets;
     const uint8_t* static_mask;   // NULL: no static_builds plane
-    const int32_t* holes;         // holey problems: [N,4] entrance / exit in bordered coordinates, else NULL
+    const int32_t* holes;         // holey problems: [N,4] (3D: [N,6]) entrance / exit in bordered coordinates, else NULL
     int32_t border_tile;
+    int32_t hole_ints;            // 4, or 6 for the 3D holey problems (foot tiles; the head is the tile above, z + 1)
     void* out;
 };
 
@@ -47,7 +48,30 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
         const int q1 = r % p.o1;
         const int q0 = r / p.o1;
         int hot, frozen = 0;
-        if (p.holes) {
+        if (p.holes && p.ndim == 3) {
+            // 3D holey problems: the bordered 3D map, entrance and exit dug two tiles high (foot + head,
+            // HoleyRepresentation3D.dig_holes, envs/reps/wrappers.py:182-185), position shifted by the border
+            const int32_t* h = p.holes + env * 6;
+            int s0 = q0, s1 = q1, s2 = q2;
+            if (p.crop) {
+                const int32_t* pos = p.pos + env * 3;
+                s0 = pos[0] + 1 + q0 - p.o0 / 2;
+                s1 = pos[1] + 1 + q1 - p.o1 / 2;
+                s2 = pos[2] + 1 + q2 - p.o2 / 2;
+            }
+            int v = -1;                                       // outside the bordered map: the crop's padding
+            if ((unsigned)s0 < (unsigned)(p.d0 + 2) && (unsigned)s1 < (unsigned)(p.d1 + 2) &&
+                (unsigned)s2 < (unsigned)(p.d2 + 2)) {
+                if (s0 >= 1 && s0 <= p.d0 && s1 >= 1 && s1 <= p.d1 && s2 >= 1 && s2 <= p.d2) {
+                    v = p.grids[env * p.row_stride + ((s0 - 1) * p.d1 + (s1 - 1)) * p.d2 + (s2 - 1)];
+                } else {
+                    const bool ent = (s0 == h[0] || s0 == h[0] + 1) && s1 == h[1] && s2 == h[2];
+                    const bool ext = (s0 == h[3] || s0 == h[3] + 1) && s1 == h[4] && s2 == h[5];
+                    v = (ent || ext) ? 0 : p.border_tile;
+                }
+            }
+            hot = p.crop ? v + 1 : v;
+        } else if (p.holes) {
             // holey problems (2D): the observed map is the bordered map with the two holes dug as empty tiles, and
             // the position is shifted by the border (HoleyRepresentation.get_observation, envs/reps/wrappers.py:153-160)
             const int32_t* h = p.holes + env * 4;
@@ -454,9 +478,12 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     p.targets = st.targets;
     p.holes = nullptr;
     p.border_tile = 0;
-    const bool holey = cfg.problem == PCGRL_PROB_BINARY_HOLEY;
+    p.hole_ints = 4;
+    const bool holey3d = cfg.problem == PCGRL_PROB_MINECRAFT_3D_HOLEY_MAZE || cfg.problem == PCGRL_PROB_MINECRAFT_3D_DUNGEON_HOLEY;
+    const bool holey = cfg.problem == PCGRL_PROB_BINARY_HOLEY || holey3d;
     if (holey) {
-        if (!st.holes || cfg.ndim != 2 || a.static_channel) return cudaErrorInvalidValue;
+        if (!st.holes || cfg.ndim != (holey3d ? 3 : 2) || a.static_channel) return cudaErrorInvalidValue;
+        p.hole_ints = holey3d ? 6 : 4;
         if (a.holey_border_tile < 0 || a.holey_border_tile >= cfg.n_tiles) return cudaErrorInvalidValue;
         p.holes = st.holes;
         p.border_tile = a.holey_border_tile;
@@ -468,11 +495,12 @@ cudaError_t launch_observe(const pcgrl_config& cfg, const pcgrl_state& st, const
     }
     p.out = a.out;
     const int grow = holey ? 2 : 0;   // without a crop the whole (bordered) map is observed
-    if (!a.crop && (p.o0 != p.d0 + grow || p.o1 != p.d1 + grow || p.o2 != p.d2)) return cudaErrorInvalidValue;
+    if (!a.crop && (p.o0 != p.d0 + grow || p.o1 != p.d1 + grow || p.o2 != p.d2 + (holey3d ? grow : 0))) return cudaErrorInvalidValue;
     if ((a.out_kind == 0 || a.out_kind == 3) && a.n_ctrl > 0) return cudaErrorInvalidValue;  // target planes are fractional
     const int64_t total = st.n_envs * (int64_t)p.o0 * p.o1 * p.o2;
     if (total == 0) return cudaSuccess;
-    if (!getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps the one-thread-per-pixel kernel reachable for A/B runs)
+    // the staged writer knows the 2D border frame only; the bordered 3D map goes through the pixel-per-thread kernel
+    if (!holey3d && !getenv("PCGRL_OBSERVE_SCALAR")) {   // (the env var keeps that kernel reachable for A/B runs)
         bool done = false;
         cudaError_t e = (a.out_kind == 0 || a.out_kind == 3) ? launch_vec<uint8_t>(p, s, done)
                       : a.out_kind == 1 ? launch_vec<float>(p, s, done)

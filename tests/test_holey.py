@@ -389,3 +389,45 @@ def test_holey3d_rollout_matches_oracle(problem, rep, fixed):
             assert r_h[e] == pytest.approx(float(r), rel=1e-6, abs=1e-6), (t, e)
             assert bool(d_h[e]) == d
     env.check_status()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("problem", ["minecraft_3D_holey_maze", "minecraft_3D_dungeon_holey"])
+@pytest.mark.parametrize("rep", ["narrow", "turtle", "wide"])
+def test_maze3d_holey_observation(problem, rep):
+    """HoleyRepresentation3D.get_observation (envs/reps/wrappers.py:153-160, 182-185): the bordered 3D map with the
+    entrance and the exit dug two tiles high, position + 1, through Cropped + OneHotEncoding (window + 2) -- against
+    the restatement, with holes drawn on the device."""
+    import control_pcgrl_b200 as P
+    rng = np.random.default_rng(21)
+    n, size, window = 9, 5, (6, 8, 10)
+    spec_tiles = len(O.TILES[problem])
+    grids = rng.integers(0, spec_tiles, size=(n, size, size, size)).astype(np.int8)
+    cfg = P.make_config(problem, rep, map_shape=(size,) * 3, obs_window=window)
+    env = P.BatchedPcgrlEnv(cfg, n, action_kind="wide_coords" if rep == "wide" else None, seed=5)
+    pos = rng.integers(0, size, size=(n, 3))
+    env.reset(grids=grids, pos=pos if rep == "turtle" else None)
+    if rep == "narrow":
+        env.pos[:, :3] = torch.from_numpy(pos).to(env.device, torch.int32)
+    holes = env.holes.cpu().numpy()
+    assert len({tuple(h) for h in holes.tolist()}) > 1          # drawn per env
+    obs = env.observe(dtype=torch.float64).cpu().numpy()
+    for dt in (torch.uint8, torch.float32):
+        assert np.array_equal(env.observe(dtype=dt).cpu().numpy().astype(np.float64), obs)
+    codes = env.observe(onehot=False).cpu().numpy()[..., 0]
+    ow = tuple(d + 2 for d in (window if rep != "wide" else (size,) * 3))
+    assert obs.shape == (n, *ow, spec_tiles + (1 if rep != "wide" else 0))
+    dug = 0
+    for e in range(n):
+        b, ent, ext = O.bordered_with_holes_3d(grids[e], holes[e])
+        # the interior of the bordered map is rewritten from the map at every update (representation.py:162-164), so
+        # the reference's default exit (1, 1, 1) -- an interior cell -- does not stay dug
+        b[1:-1, 1:-1, 1:-1] = grids[e]
+        if rep == "wide":
+            want = O.full_onehot(b, spec_tiles)
+        else:
+            want = O.cropped_onehot(b, [int(v) + 1 for v in pos[e]], ow, spec_tiles)
+        assert np.array_equal(obs[e], want), (problem, rep, e)
+        assert np.array_equal(codes[e], want.argmax(-1)), (problem, rep, e)
+        dug += int((b == 0).sum() - (grids[e] == 0).sum())
+    assert dug >= 3 * n          # entrance and exit really are in the observed border
