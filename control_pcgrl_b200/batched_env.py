@@ -82,6 +82,9 @@ class BatchedPcgrlEnv:
         if self.n_agents > 1 and rep != "turtle":
             raise ValueError("multi-agent envs need the turtle representation (upstream, MultiAgentNarrowRepresentation "
                              "raises 'Busted for now', envs/reps/wrappers.py:669)")
+        # ShowAgentRepresentation (cfg.show_agents, envs/reps/wrappers.py:189-232): an 'agent_occupancy' plane behind
+        # the map channels of every agent's observation; upstream it needs several agents (:207-208)
+        self.show_agents = bool(c.show_agents) and self.n_agents > 1
         # representation wrappers (envs/reps/wrappers.py wrap_rep :717-722)
         self.act_window = c.act_window
         if self.act_window is not None:
@@ -636,7 +639,22 @@ class BatchedPcgrlEnv:
             dims = tuple(d + 2 for d in dims)
         ch = ((self.n_tiles + 1 if crop else self.n_tiles) if onehot else 1) + 2 * len(self.ctrl_metrics)
         ch += 1 if self.static_mask is not None else 0      # 'static_builds' plane (wrappers.py:451-453)
+        ch += 1 if self.show_agents else 0                  # 'agent_occupancy' plane
         return (*dims, ch)
+
+    def _agent_occupancy(self, agent, dims, dtype):
+        """[N, *dims]: 1 where any agent stands, in agent `agent`'s window (Cropped pads this key with 0)."""
+        nd, dev = self.ndim, self.device
+        occ = torch.zeros((self.n_envs, *dims), dtype=dtype, device=dev)
+        center = self.agent_pos[agent, :, :nd].long()
+        half = torch.tensor([d // 2 for d in dims], device=dev)
+        lim = torch.tensor(list(dims), device=dev)
+        env_idx = torch.arange(self.n_envs, device=dev)
+        for b in range(self.n_agents):
+            rel = self.agent_pos[b, :, :nd].long() - center + half
+            ok = ((rel >= 0) & (rel < lim)).all(dim=1)
+            occ[(env_idx[ok],) + tuple(rel[ok, i] for i in range(nd))] = 1
+        return occ
 
     def observe(self, out: torch.Tensor | None = None, dtype=torch.float32, onehot: bool = True, agent: int = 0):
         """The wrapped observation of every env: [N, *obs_dims, channels] (channels last), exactly what
@@ -650,6 +668,16 @@ class BatchedPcgrlEnv:
                 raise ValueError("onehot=False is a uint8 observation without control planes")
             dtype = torch.uint8
         shape = (self.n_envs, *self.obs_shape(onehot))
+        final = None
+        if self.show_agents:
+            # the kernel writes the map (+ target / static) channels; the occupancy plane is appended here (a handful
+            # of scatters, one per agent)
+            if out is not None and (tuple(out.shape) != shape or not out.is_contiguous()):
+                raise ValueError(f"out must be contiguous with shape {shape}")
+            final, out = out, None
+            if final is not None:
+                dtype = final.dtype
+            shape = (*shape[:-1], shape[-1] - 1)
         if out is None:
             out = torch.empty(shape, dtype=dtype, device=self.device)
         if tuple(out.shape) != shape or not out.is_contiguous():
@@ -673,6 +701,13 @@ class BatchedPcgrlEnv:
         oa.static_channel = 1 if self.static_mask is not None else 0
         with self._on_device():
             _lib.check(self.lib.pcgrl_observe(self._cc, self._agent_state(agent), oa, self._stream()), "pcgrl_observe")
+        if self.show_agents:
+            occ = self._agent_occupancy(agent, shape[1:-1], out.dtype)
+            if final is None:
+                return torch.cat([out, occ[..., None]], dim=-1)
+            final[..., :-1] = out
+            final[..., -1] = occ
+            return final
         return out
 
     STATUS_BITS = (

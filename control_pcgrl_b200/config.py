@@ -126,5 +126,6 @@ def normalise(cfg) -> SimpleNamespace:
                            n_static_walls=_get(cfg, "n_static_walls", None),
                            # MultiAgentWrapper / MultiAgentTurtleRepresentation (cfg.multiagent.n_agents, 0 = off)
                            n_agents=int(_get(_get(cfg, "multiagent", None), "n_agents", 0) or 0),
+                           show_agents=bool(_get(cfg, "show_agents", False)),
                            # HoleyProblem.adjust_param (binary_holey_prob.py:47-49)
                            fixed_holes=bool(_get(cfg, "fixed_holes", _get(task, "fixed_holes", False))))

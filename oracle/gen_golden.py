@@ -647,15 +647,19 @@ def multiagent_fixture():
     R.install()
     from control_pcgrl import wrappers
     ZP = [0.58, 0.3, 0.02, 0.02, 0.02, 0.02, 0.02, 0.02]
-    cases = [("binary", (8, 8), (16, 16), BINARY_W, 2, None, None, 3),
-             ("zelda", (7, 11), (22, 22), ZELDA_W, 3, ZP, None, 2),
-             ("binary", (10, 6), (20, 20), BINARY_W, 4, None, 0.3, 2)]
+    # last field: cfg.show_agents (ShowAgentRepresentation, envs/reps/wrappers.py:189-232: an 'agent_occupancy' plane)
+    cases = [("binary", (8, 8), (16, 16), BINARY_W, 2, None, None, 3, False),
+             ("zelda", (7, 11), (22, 22), ZELDA_W, 3, ZP, None, 2, False),
+             ("binary", (10, 6), (20, 20), BINARY_W, 4, None, 0.3, 2, False),
+             ("zelda", (7, 11), (10, 12), ZELDA_W, 3, ZP, None, 2, True)]
     arrays = {"n_cases": np.array(len(cases))}
-    for ci, (problem, map_shape, obs_window, weights, n_agents, init_p, chg_pct, n_envs) in enumerate(cases):
+    for ci, (problem, map_shape, obs_window, weights, n_agents, init_p, chg_pct, n_envs, show) in enumerate(cases):
         rng = np.random.default_rng(900 + ci)
         cfg = R.make_cfg(problem, "turtle", map_shape, obs_window=obs_window, weights=weights,
                          change_percentage=chg_pct)
         cfg.multiagent = SimpleNamespace(n_agents=n_agents)
+        cfg.show_agents = show
+        arrays[f"c{ci}_show_agents"] = np.array(show)
         n_tiles = len(TILES[problem])
         arrays[f"c{ci}_problem"] = np.array(problem)
         arrays[f"c{ci}_map_shape"] = np.array(map_shape)

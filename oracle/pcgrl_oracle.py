@@ -587,6 +587,21 @@ def static_builds_crop(static, pos, obs_window):
     return out
 
 
+def agent_occupancy_crop(agent_pos, pos, obs_window, map_shape):
+    """ShowAgentRepresentation (envs/reps/wrappers.py:201-232) through Cropped (wrappers.py:407-437, pad value 0 for
+    every key but 'map'): 1 where any agent stands, seen from `pos`; out of the map = 0."""
+    occ = np.zeros(tuple(map_shape), dtype=np.int64)
+    for q in agent_pos:
+        occ[tuple(int(v) for v in q)] = 1
+    ow = tuple(int(v) for v in obs_window)
+    out = np.zeros(ow, dtype=np.float64)
+    for o in np.ndindex(*ow):
+        src = tuple(pos[i] + o[i] - ow[i] // 2 for i in range(len(ow)))
+        if all(0 <= src[i] < occ.shape[i] for i in range(len(ow))):
+            out[o] = occ[src]
+    return out
+
+
 def full_onehot(grid, n_tiles):
     """ActionMapImagePCGRLWrapper (wrappers.py:502-526): one-hot of the whole map, no OOB channel."""
     return np.eye(n_tiles)[np.asarray(grid, dtype=np.int64)]

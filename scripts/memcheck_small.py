@@ -30,11 +30,10 @@ def roll(problem, rep, shape, n, steps, path=None, **kw):
             env.step_host(a.cpu().numpy())
         else:
             env.step(a)
-    if not (env.holey and env.ndim == 3):
-        if not env.ctrl_metrics:          # target planes are fractional: float observations only
-            env.observe(dtype=torch.uint8)
-            env.observe(dtype=torch.uint8, onehot=False)
-        env.observe(dtype=torch.float32)
+    if not env.ctrl_metrics:          # target planes are fractional: float observations only
+        env.observe(dtype=torch.uint8)
+        env.observe(dtype=torch.uint8, onehot=False)
+    env.observe(dtype=torch.float32)
     torch.cuda.synchronize()
     env.check_status()
     os.environ.pop("PCGRL_STEP_PATH", None)
@@ -53,8 +52,31 @@ roll("binary", "narrow", (64, 64), 300, 12)
 roll("zelda", "turtle", (40, 50), 300, 12)
 roll("sokoban", "cellular", (5, 5), 60000, 4, action_kind="ca_tiles")
 roll("sokoban", "narrow", (5, 5), 4000, 30)
-roll("smb", "narrow", (20, 16), 400, 10)
+roll("smb", "narrow", (20, 16), 400, 10)            # lane groups, heap in shared memory
+roll("smb", "narrow", (12, 40), 300, 8)             # lane groups, heap continued in the global slice
+os.environ["PCGRL_SMB_GROUP_CAP"] = "32"
+roll("smb", "narrow", (20, 16), 300, 6)             # most levels overflow the group's slice: whole-warp fallback
+os.environ.pop("PCGRL_SMB_GROUP_CAP")
+roll("smb", "turtle", (140, 12), 64, 6)             # bit map too tall for a group: every level through the fallback
 roll("minecraft_3D_maze", "narrow", (8, 8, 8), 600, 12)
 roll("minecraft_3D_holey_maze", "narrow", (7, 7, 7), 500, 12)
 roll("minecraft_3D_dungeon_holey", "turtle", (7, 7, 7), 500, 12, fixed_holes=True)
+
+
+def multiagent():
+    cfg = P.make_config("zelda", "turtle", map_shape=(7, 11), obs_window=(22, 22), max_board_scans=0.3)
+    cfg.multiagent.n_agents = 3
+    env = P.BatchedPcgrlEnv(cfg, 2000, seed=2, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device=env.device).manual_seed(0)
+    for t in range(12):
+        env.step_agents(torch.randint(0, 4 + env.n_tiles, (2000, 3), generator=g, device=env.device, dtype=torch.int32))
+    for a in range(3):
+        env.observe(dtype=torch.uint8, agent=a)
+    torch.cuda.synchronize()
+    env.check_status()
+    print("ok multi-agent zelda turtle", flush=True)
+
+
+multiagent()
 print("memcheck workload done")

@@ -76,6 +76,7 @@ def load_multiagent():
         c = dict(problem=str(z[f"c{ci}_problem"]), map_shape=tuple(int(v) for v in z[f"c{ci}_map_shape"]),
                  obs_window=tuple(int(v) for v in z[f"c{ci}_obs_window"]), n_agents=int(z[f"c{ci}_n_agents"]),
                  change_percentage=None if cp < 0 else cp,
+                 show_agents=bool(z[f"c{ci}_show_agents"]) if f"c{ci}_show_agents" in z else False,
                  weights={str(k): float(v) for k, v in zip(z[f"c{ci}_weight_keys"], z[f"c{ci}_weight_vals"])}, envs=[])
         for e in range(int(z[f"c{ci}_n_envs"])):
             pre = f"c{ci}_e{e}_"

@@ -16,10 +16,11 @@ def _cfg(c):
     cfg = P.make_config(c["problem"], "turtle", map_shape=c["map_shape"], obs_window=c["obs_window"],
                         weights=c["weights"], change_percentage=c["change_percentage"])
     cfg.multiagent.n_agents = c["n_agents"]
+    cfg.show_agents = c["show_agents"]      # ShowAgentRepresentation's 'agent_occupancy' plane (fixture case 3)
     return cfg
 
 
-@pytest.mark.parametrize("ci", [0, 1, 2])
+@pytest.mark.parametrize("ci", [0, 1, 2, 3])
 def test_batched_multiagent_matches_reference(ci):
     import control_pcgrl_b200 as P
     c = load_multiagent()[ci]
@@ -65,7 +66,7 @@ def test_batched_multiagent_matches_reference(ci):
 def test_make_env_multiagent_matches_reference():
     """The drop-in stack: make_env(cfg) with cfg.multiagent.n_agents -> MultiAgentWrapper, dict in / dict out."""
     import control_pcgrl_b200 as P
-    c = load_multiagent()[1]          # zelda, three agents
+    c = load_multiagent()[3]          # zelda, three agents, show_agents
     d = c["envs"][0]
     A = c["n_agents"]
     names = [f"agent_{i}" for i in range(A)]

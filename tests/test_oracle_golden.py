@@ -95,9 +95,15 @@ def test_multiagent_turtle_matches_reference():
                               change_percentage=c["change_percentage"])
             st0 = env.reset(d["grid0"], agent_pos=d["pos0"])
             assert O.stats_vector(c["problem"], st0) == [int(v) for v in d["stats0"]]
-            for i in range(c["n_agents"]):
+            def view(i):
                 got = O.cropped_onehot(env.grid, env.agent_pos[i], c["obs_window"], n_tiles)
-                np.testing.assert_allclose(got, d["obs0"][i], rtol=1e-12, atol=0)
+                if c["show_agents"]:      # ToImage appends the 'agent_occupancy' plane (wrappers.py:451-453)
+                    occ = O.agent_occupancy_crop(env.agent_pos, env.agent_pos[i], c["obs_window"], c["map_shape"])
+                    got = np.concatenate([got, occ[..., None]], axis=-1)
+                return got
+
+            for i in range(c["n_agents"]):
+                np.testing.assert_allclose(view(i), d["obs0"][i], rtol=1e-12, atol=0)
             for t in range(len(d["actions"])):
                 for i in range(c["n_agents"]):
                     r, done, _ = env.step(int(d["actions"][t][i]), agent=i)
@@ -107,8 +113,7 @@ def test_multiagent_turtle_matches_reference():
                     assert env.agent_pos == d["pos"][t][i].tolist(), (t, i)
                     if t in d["obs_step"]:
                         want = d["obs"][list(d["obs_step"]).index(t)][i]
-                        got = O.cropped_onehot(env.grid, env.agent_pos[i], c["obs_window"], n_tiles)
-                        np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+                        np.testing.assert_allclose(view(i), want, rtol=1e-12, atol=0)
                 assert np.array_equal(env.grid, d["grids"][t]), t
                 assert env.iteration == int(d["iterations"][t]) and env.changes == int(d["changes"][t])
             assert bool(d["dones"][-1].all())
