@@ -1,11 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "multiagent" 2>&1 | tail -4
-for lib in gpurun_variants/lib*.so; do
-  name=$(basename $lib .so); name=${name#lib}
-  for rep in 1 2; do
-  PCGRL_B200_LIB=$PWD/$lib timeout 200 python bench.py --workload minecraft_3D_maze-narrow-14x14x14 --steps 40 --warmup 4 --no-cpu-baseline --no-e2e --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('maze3d $name: value %.4g kernel_ms %.3f' % (d['value'], d['roofline']['kernel_ms_per_launch']))"
-  done
-done
+for chunks in 4 6; do for taper in 0 40 70; do for rep in 1 2; do
+  PCGRL_HOST_CHUNKS=$chunks PCGRL_HOST_TAPER=$taper timeout 200 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunks $chunks taper $taper: e2e %.4g value %.4g' % (d['e2e']['value'], d['value']))"
+done; done; done
 tail -3 gpurun_out/ab.err
