@@ -126,7 +126,9 @@ typedef struct pcgrl_state {
     int64_t  n_envs;
     int64_t  env_offset;   /* global index of env 0 of this shard (only seeds the reset RNG) */
     int8_t*  grids;        /* [N, row_stride] tile codes, row-major cells (C order of _map); in place */
-    int32_t* pos;          /* [N, 3] agent position in numpy axis order (unused axes 0) */
+    int32_t* pos;          /* [N, 3] agent position in numpy axis order (unused axes 0).  Multi-agent turtle
+                              (envs/reps/wrappers.py:612-651, one env step per agent): the caller keeps one such
+                              array per agent and passes the acting / observing agent's */
     int32_t* n_step;       /* [N] narrow scan counter (reps/narrow_rep.py:98-100) */
     int32_t* iteration;    /* [N] PcgrlEnv._iteration */
     int32_t* changes;      /* [N] PcgrlEnv._changes */
@@ -143,8 +145,10 @@ typedef struct pcgrl_state {
                               overflowed; bit3 (8) sokoban: more crates than a packed solver state holds (15);
                               bit4 (16) a stat did not fit cfg.record_stat_bytes in the packed record */
     void*    scratch;      /* pcgrl_scratch_bytes() bytes, may be NULL when that returns 0.  Must be zero-filled
-                              once before its first use (it holds hash-table generation counters) and must not
-                              be shared by launches that can run concurrently */
+                              once before its first use (it holds hash-table generation counters, solver job
+                              lists and, for smb, 4 bytes per env of playthrough-length history, which is why
+                              the size depends on n_envs) and must not be shared by launches that can run
+                              concurrently */
     uint8_t* static_mask;  /* [N, row_stride] or NULL (ABI 3): StaticTileRepresentation.static_tiles over the map
                               cells (the always-frozen border is implicit).  A frozen cell keeps its tile: the
                               edit is undone, yet still counted as a change (envs/reps/wrappers.py:358-376).
