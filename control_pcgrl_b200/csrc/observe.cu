@@ -143,6 +143,8 @@ __global__ void __launch_bounds__(256) k_observe(const ObsParams p) {
 // ------------------------------------------------------------------------------------------------
 struct ObsVec {
     int32_t G, GB, E, pix, n_ch, n_map_ch, stage_bytes, planes_bytes;
+    int32_t bits;                  // 1: two-tile crops from row bit masks + a 4-pixel record table (see k_observe_staged)
+    int32_t lut_off;               // byte offset of that table in the dynamic shared memory
     uint32_t m_pix, m_o2, m_o12;   // floor(2^32 / d) of the divisors
 };
 __host__ __device__ inline uint32_t floor_magic(uint32_t d) { return d <= 1 ? 0xFFFFFFFFu : (uint32_t)(0x100000000ull / d); }
@@ -179,6 +181,28 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
     const bool pack3 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 3 && !p.raw && n_pl == 0;
     // uint8 tile codes (one byte per pixel): 8 pixels are one 64-bit word
     const bool pack1 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 1 && p.raw && n_pl == 0;
+    // Two-tile maps behind a crop (binary: the headline observation).  75 % of a 32x32 window on a 16x16 map is
+    // padding, and the in-map / padding split of a warp's pixel groups made every warp run both record builders
+    // (157 instructions per 24-byte group, issue-bound at 0.63 of the HBM peak).  Instead: the trip's map rows are
+    // kept as 16-bit masks, a group's 8 tile bits and 8 inside bits are two clamped funnel shifts of its row, and
+    // the records of 4 pixels at a time come from a 256-entry table indexed by (inside nibble, tile nibble) --
+    // one instruction stream for padding and map pixels alike.
+    const bool bits = v.bits != 0 && (pack3 || pack1);
+    uint16_t* s_rowbits = (uint16_t*)(obs_smem + v.lut_off + 256 * 16 + 256 * 4);   // [envs of the trip][d0]
+    uint4* s_lut3 = (uint4*)(obs_smem + v.lut_off);                                  // 4 one-hot records (12 bytes)
+    uint32_t* s_lut1 = (uint32_t*)(obs_smem + v.lut_off + 256 * 16);                 // 4 tile codes
+    if (bits) {
+        const uint32_t in4 = (uint32_t)tid >> 4, t4 = (uint32_t)tid & 15u;
+        uint32_t rec[4], code = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t hot = ((in4 >> k) & 1u) ? 1u + ((t4 >> k) & 1u) : 0u;   // 0 = out of bounds, tile t -> t + 1
+            rec[k] = 1u << (8 * hot);
+            code |= hot << (8 * k);
+        }
+        s_lut3[tid] = make_uint4(rec[0] | (rec[1] << 24), (rec[1] >> 8) | (rec[2] << 16), (rec[2] >> 16) | (rec[3] << 8), 0u);
+        s_lut1[tid] = code;
+    }
     for (int64_t trip = blockIdx.x; trip < trips; trip += gridDim.x) {
         const int64_t env0 = trip * envs_per_trip;
         const int n_here = (int)min((int64_t)envs_per_trip, p.n_envs - env0);
@@ -191,6 +215,26 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
             for (int i = tid; i < nz; i += OBS_THREADS) ((uint4*)stage)[i] = z;
             const int nv = n_here * (p.row_stride / 16);
             const uint4* g = (const uint4*)(p.grids + env0 * p.row_stride);
+            if (bits) {
+                // one thread per map row: its tiles' low bits as a mask over x
+                for (int i = tid; i < n_here * p.d0; i += OBS_THREADS) {
+                    const int el = i / p.d0, y = i - el * p.d0;
+                    const int8_t* row = p.grids + (env0 + el) * p.row_stride + y * p.d1;
+                    uint32_t m = 0;
+                    if (p.d1 == 16) {
+                        // one 128-bit load; the low bits of four tiles are gathered into a nibble by one multiply
+                        // (bit 8j lands on 24 + j, the cross terms stay below bit 24)
+                        const uint4 t = *(const uint4*)row;
+                        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) m |= ((((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu) << (4 * k);
+                    } else {
+#pragma unroll 4
+                        for (int x = 0; x < p.d1; ++x) m |= (uint32_t)(row[x] & 1) << x;
+                    }
+                    s_rowbits[i] = (uint16_t)m;
+                }
+            } else
             for (int i = tid; i < nv; i += OBS_THREADS) ((uint4*)s_grid)[i] = g[i];
             if (p.static_mask) {
                 const uint4* m = (const uint4*)(p.static_mask + env0 * p.row_stride);
@@ -219,7 +263,9 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
         const int n_pix = n_here * v.pix;
         constexpr int PPT = ROWN ? ROWN : 4;   // pixels per thread
         for (int first = tid * PPT; first < n_pix; first += OBS_THREADS * PPT) {
-            // coordinates of the first pixel: (env of the trip, q0, q1[, q2]); in 2D the image is (o0, o1)
+            // coordinates of the first pixel: (env of the trip, q0, q1[, q2]); in 2D the image is (o0, o1).  (Hoisting
+            // this out of the trips when the thread stride is a whole number of images costs 5 live registers and with
+            // them a resident CTA: u8 binary-narrow 0.72 -> 0.66 of the HBM peak, f32 0.91 -> 0.86.)
             uint32_t r, q0, q1, q2 = 0;
             uint32_t el = fdiv((uint32_t)first, (uint32_t)v.pix, v.m_pix, r);
             if (D3) {
@@ -250,7 +296,23 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 // which of the 8 pixels lie inside the map: most of a crop is padding (a 32x32 window on a 16x16 map
                 // is 75 % out of bounds), and such pixels need no grid load -- a whole group outside is a constant
                 const bool none_in = !row_ok || (CROP && (sl + 7 < 0 || sl >= dl));
-                if (sizeof(T) == 1 && ROWN == 8 && pack3 && none_in) {
+                if (sizeof(T) == 1 && ROWN == 8 && bits) {
+                    // sl + 16 >= 0 (the window is at most 32 wide): bit k of the shifted row is map column sl + k
+                    const uint32_t rb = row_ok ? (uint32_t)s_rowbits[el * p.d0 + c0 + (int)q0] : 0u;
+                    const uint32_t inr = row_ok ? ((1u << p.d1) - 1u) : 0u;
+                    const uint32_t t8 = __funnelshift_rc(rb << 16, 0u, (uint32_t)(sl + 16)) & 0xFFu;
+                    const uint32_t in8 = __funnelshift_rc(inr << 16, 0u, (uint32_t)(sl + 16)) & 0xFFu;
+                    const uint32_t ilo = ((in8 & 0xFu) << 4) | (t8 & 0xFu), ihi = (in8 & 0xF0u) | (t8 >> 4);
+                    if (pack3) {
+                        const uint4 a = s_lut3[ilo], b = s_lut3[ihi];
+                        uint2* o8 = (uint2*)o;
+                        o8[0] = make_uint2(a.x, a.y);
+                        o8[1] = make_uint2(a.z, b.x);
+                        o8[2] = make_uint2(b.y, b.z);
+                    } else {
+                        *(uint2*)o = make_uint2(s_lut1[ilo], s_lut1[ihi]);
+                    }
+                } else if (sizeof(T) == 1 && ROWN == 8 && pack3 && none_in) {
                     uint2* o8 = (uint2*)o;       // eight records "1 0 0"
                     o8[0] = make_uint2(0x01000001u, 0x00010000u);
                     o8[1] = make_uint2(0x00000100u, 0x01000001u);
@@ -421,7 +483,13 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
     v.m_o2 = floor_magic((uint32_t)p.o2);
     v.m_o12 = floor_magic((uint32_t)(p.o1 * p.o2));   // 2D: o2 == 1, i.e. the magic of o1
     v.planes_bytes = (v.GB * v.G * 2 * p.n_ctrl * (int)sizeof(T) + 15) / 16 * 16;
-    const int dyn = v.stage_bytes + v.planes_bytes + v.GB * v.G * (p.row_stride * (p.static_mask ? 2 : 1) + 12);
+    int dyn = v.stage_bytes + v.planes_bytes + v.GB * v.G * (p.row_stride * (p.static_mask ? 2 : 1) + 12);
+    // two-tile crops of maps up to 16 wide in windows up to 32 wide (u8 one-hot or codes, no extra planes): row-mask path
+    v.bits = sizeof(T) == 1 && p.crop && p.ndim == 2 && p.n_tiles == 2 && p.d1 <= 16 && p.o1 <= 32 && p.o1 % 8 == 0 &&
+             !p.static_mask && !p.holes && p.n_ctrl == 0 && (p.raw ? n_ch == 1 : n_ch == 3) &&
+             !getenv("PCGRL_OBSERVE_NO_BITS");
+    v.lut_off = (dyn + 15) / 16 * 16;
+    if (v.bits) dyn = v.lut_off + 256 * 16 + 256 * 4 + (v.GB * v.G * p.d0 * 2 + 15) / 16 * 16;
     const bool d3 = p.ndim == 3, st = p.static_mask != nullptr, cr = p.crop != 0;
     const int last_axis = d3 ? p.o2 : p.o1;
     // 8 pixels per thread only for 1-byte elements: with 4-byte elements a thread's 8 records are 8 * n_ch words

@@ -1,7 +1,11 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-for chunks in 4 6; do for taper in 0 40 70; do for rep in 1 2; do
-  PCGRL_HOST_CHUNKS=$chunks PCGRL_HOST_TAPER=$taper timeout 200 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunks $chunks taper $taper: e2e %.4g value %.4g' % (d['e2e']['value'], d['value']))"
-done; done; done
+timeout 1200 python -m pytest tests -m gpu -x -q -k "observ or trace or vector or holey or multiagent or static or wrapped" 2>&1 | tail -3
+timeout 300 python scripts/bench_observe.py 2>>gpurun_out/ab.err > gpurun_out/r02_observe.jsonl; python - <<PY
+import json
+for l in open("gpurun_out/r02_observe.jsonl"):
+    d=json.loads(l); print("  %-34s %-16s ms %.4f frac %.3f" % (d["case"], d["dtype"], d["ms"], d["frac_of_hbm_peak"]))
+PY
+timeout 300 python scripts/bench_rl_loop.py 2>>gpurun_out/ab.err > gpurun_out/r02_rl_loop.jsonl; cat gpurun_out/r02_rl_loop.jsonl
 tail -3 gpurun_out/ab.err
