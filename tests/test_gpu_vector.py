@@ -113,3 +113,21 @@ def test_minecraft_2d_maze_is_the_binary_machine_under_other_tile_names():
     env = P.make("minecraft_2D_maze-narrow-v0")
     env.reset()
     assert env.get_num_tiles() == 2 and env.action_space.n == 2
+
+
+def test_policy_input_from_tile_codes_equals_reference_permute():
+    """rl/models.py:60-66 feeds `obs.permute(0, 3, 1, 2).float()`; the same tensor from 1-byte tile codes."""
+    import control_pcgrl_b200 as P
+    from control_pcgrl_b200.policy_input import conv_input_from_codes
+    for problem, rep, shape, window in (("binary", "narrow", (16, 16), (32, 32)), ("zelda", "turtle", (7, 11), (22, 22)),
+                                        ("binary", "wide", (16, 16), (16, 16))):
+        env = P.BatchedPcgrlEnv(P.make_config(problem, rep, map_shape=shape, obs_window=window), 300, seed=4)
+        env.reset()
+        for i, d in enumerate(shape):
+            env.pos[:, i] = torch.randint(0, d, (300,), device=env.device, dtype=torch.int32)
+        ref = env.observe(dtype=torch.float64).permute(0, 3, 1, 2).float()
+        got = conv_input_from_codes(env.observe(onehot=False), ref.shape[1])
+        assert got.shape == ref.shape and torch.equal(got, ref)
+        assert got.is_contiguous(memory_format=torch.channels_last)
+        conv = torch.nn.Conv2d(ref.shape[1], 8, kernel_size=7, stride=2, padding=3).to(env.device)
+        assert torch.allclose(conv(got), conv(ref.contiguous()), atol=1e-5)
