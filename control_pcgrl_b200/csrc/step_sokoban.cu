@@ -515,16 +515,21 @@ struct SokobanProb {
         for (;;) {
             if (iters >= SOK_POWER || hn == 0) break;
             ++iters;
-            int cur = 0, seen = 0;
-            if (lane == 0) cur = (int)(heap_pop(heap, hn) & 0xFFFFu);
-            cur = __shfl_sync(0xffffffffu, cur, 0);
+            int seen = 0;
+            // the node about to be popped is the heap's root: its state (L2) is requested before lane 0 walks the heap
+            // (~13 dependent shared-memory levels), so the two latencies overlap instead of adding up
+            const int cur = (int)(heap[0] & 0xFFFFu);
+            __syncwarp();                        // every lane has read the root before lane 0 rewrites the heap
             const uint4 s = c.state[cur];
             const uint32_t m = c.meta[cur];
+            if (lane == 0) heap_pop(heap, hn);
             const int h = m >> 16, d = m & 0xFFFFu;
             if (h == 0) {
                 out_depth = d;
                 return true;
             }
+            // (the table lookup on lane 1, as a second instruction stream next to lane 0's heap walk, gains nothing:
+            // A* launch 8.84 against 8.69 ms)
             if (lane == 0) {
                 uint32_t i = hash_state(s) & (ASTAR_TABLE - 1);
                 for (;;) {

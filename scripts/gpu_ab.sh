@@ -1,7 +1,10 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q -k "policy_input" 2>&1 | tail -3
+timeout 900 python -m pytest tests -m gpu -x -q -k "sokoban or search or fixtures" 2>&1 | tail -3
+for r in 1 2; do
+timeout 300 python bench.py --workload sokoban-cellular-5x5 --steps 30 --warmup 3 --no-cpu-baseline --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('sokoban: value %.4g e2e %.4g kernel_ms %.3f' % (d['value'], d['e2e']['value'], d['roofline']['kernel_ms_per_launch']))"
+done
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:sokoban\|k_step_search -c 160 --csv --log-file gpurun_out/r02_launches_sokoban.csv python bench.py --workload sokoban-cellular-5x5 --steps 30 --warmup 3 --no-e2e --no-cpu-baseline --no-configs > /dev/null 2>>gpurun_out/ab.err
 python - <<'PY'
 import csv, collections
