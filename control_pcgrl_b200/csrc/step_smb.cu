@@ -643,11 +643,13 @@ __global__ void __launch_bounds__(WARPS * 32) k_smb_solve(const KParams p, const
                 finished = true;
             } else {
                 ++iters;
-                uint32_t cur = 0;
-                if (sub == 0) cur = smb_pop_recycle(hp, hn);
-                cur = __shfl_sync(gmask, cur, gbase);
+                // the pop returns the heap's root: its node (L2) is requested before the leader walks the heap
+                const uint32_t cur = *hp.at(0) & 0xFFFFu;
+                __syncwarp(gmask);                               // the group has read the root before the leader rewrites it
+                const uint2 packed = c.nodes[cur];
+                if (sub == 0) smb_pop_recycle(hp, hn);
                 --hn;
-                const S::Node n = S::unpack(c.nodes[cur]);
+                const S::Node n = S::unpack(packed);
                 if (n.y >= c.H) {
                     // checkLose: skipped, still an iteration
                 } else if (n.x >= c.exit_x) {                    // checkWin
