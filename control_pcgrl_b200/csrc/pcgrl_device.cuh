@@ -17,7 +17,23 @@
 #ifndef PCGRL_OPT_BORROW
 #define PCGRL_OPT_BORROW 1     // 1: lowest-cell extraction through x - 1 (minus_one) fused into its consumers
 #endif
-#if PCGRL_OPT_SHR_IMAD
+#ifndef PCGRL_OPT_FUNNEL_IMAD
+#define PCGRL_OPT_FUNNEL_IMAD 0   // 1: the 16-bit funnel shift between board words as IMAD.HI + IMAD (FMA pipe) instead of SHF (ALU pipe)
+#endif
+#if PCGRL_OPT_FUNNEL_IMAD
+// (lo >> 16) | (hi << 16): the two halves occupy disjoint bits, so the OR is an add -- mul.hi + mad.  The multiplier
+// comes from constant memory: a literal 65536 is strength-reduced back into a shift
+static __constant__ unsigned int c_pcgrl_k16 = 65536u;
+#define PCGRL_FUNNEL16(lo, hi) ((hi) * c_pcgrl_k16 + __umulhi((lo), c_pcgrl_k16))
+#else
+#define PCGRL_FUNNEL16(lo, hi) __funnelshift_l((lo), (hi), 16)
+#endif
+#if PCGRL_OPT_SHR_IMAD == 2
+// x >> 1 as a multiply-high by 2^31 that the compiler cannot turn back into a shift (with the literal it does: the
+// SASS of the search kernels showed SHF.R.U32.HI, ALU pipe)
+static __constant__ unsigned int c_pcgrl_k31 = 0x80000000u;
+#define PCGRL_SHR1(x) __umulhi((x), c_pcgrl_k31)
+#elif PCGRL_OPT_SHR_IMAD
 #define PCGRL_SHR1(x) __umulhi((x), 0x80000000u)
 #else
 #define PCGRL_SHR1(x) ((x) >> 1)
@@ -202,8 +218,11 @@ struct Board {
     //
     // TWO layout: the "row above" word of board word i and the "row below" word of board word i-1 are the
     // same 32-bit window straddling words i-1 and i (high row of i-1, low row of i), so one funnel shift
-    // per word boundary serves both directions.  x>>1 is issued as a multiply-high (IMAD.HI, FMA pipe) and
-    // x<<1 as an add, which moves about a third of the integer work off the saturated ALU pipe.
+    // per word boundary serves both directions.  x<<1 is an add (IMAD.IADD, FMA pipe).  x>>1 is written as a
+    // multiply-high by 2^31, which nvcc 12.9 turns back into SHF.R; forcing real IMAD.HI for it and for the 16-bit
+    // funnel shifts (multipliers from constant memory, PCGRL_OPT_SHR_IMAD=2 / PCGRL_OPT_FUNNEL_IMAD=1) takes every
+    // shift off the ALU pipe but is SLOWER on B200: 0.2997 ms per step against 0.3064 (shr), 0.3092 (funnel),
+    // 0.3225 (both) at 1 Mi envs -- IMAD.HI is not a full-rate instruction.
     __device__ static __forceinline__ uint32_t expand_and(const uint32_t (&f)[NW], const uint32_t (&av)[NW],
                                                           uint32_t (&n)[NW]) {
         uint32_t any = 0;
@@ -211,7 +230,7 @@ struct Board {
             uint32_t s[NW + 1];  // s[i] = rows (2i-1, 2i): window between word i-1 and word i
             s[0] = f[0] << 16;
 #pragma unroll
-            for (int i = 1; i < NW; ++i) s[i] = __funnelshift_l(f[i - 1], f[i], 16);
+            for (int i = 1; i < NW; ++i) s[i] = PCGRL_FUNNEL16(f[i - 1], f[i]);
             s[NW] = f[NW - 1] >> 16;
 #pragma unroll
             for (int i = 0; i < NW; ++i) {
