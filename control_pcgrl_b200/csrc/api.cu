@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -246,7 +247,12 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
 // upload, step kernel and result download are queued on helper stream c % PIPE_STREAMS, so the H2D copy of
 // chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (two copy engines + the SMs).
 // Only for kernels that keep no cross-launch device state (scratch == 0, i.e. not the persistent solvers).
-constexpr int PIPE_STREAMS = 3;
+constexpr int PIPE_COMPUTE_MAX = 6;             // streams the chunks' kernels rotate over: n_compute of them (PCGRL_HOST_STREAMS)
+constexpr int PIPE_STREAMS = PIPE_COMPUTE_MAX + 2;  // + one upload stream and one download stream (the last two)
+static int pipe_compute() {
+    static const int v = getenv("PCGRL_HOST_STREAMS") ? std::min(std::max(atoi(getenv("PCGRL_HOST_STREAMS")), 1), PIPE_COMPUTE_MAX) : 3;
+    return v;
+}
 struct HostGraphKey {            // everything the queued operations depend on (compared bytewise)
     pcgrl_config cfg;
     pcgrl_state st;
@@ -275,6 +281,7 @@ struct HostPipe {
     bool ready = false, graph_broken = false;
     cudaStream_t s[PIPE_STREAMS];
     cudaEvent_t fork, join[PIPE_STREAMS];
+    cudaEvent_t up_ev[WL_CHUNKS], k_ev[WL_CHUNKS];   // chunk c's actions are on the device / its kernels are done
     HostGraph graphs[MAX_GRAPHS];
     unsigned next_graph = 0;
 };
@@ -483,19 +490,51 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
             if ((e = cudaEventCreateWithFlags(&hp.join[i], cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
         }
         if ((e = cudaEventCreateWithFlags(&hp.fork, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "event create");
+        for (int i = 0; i < WL_CHUNKS; ++i)
+            if ((e = cudaEventCreateWithFlags(&hp.up_ev[i], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&hp.k_ev[i], cudaEventDisableTiming)) != cudaSuccess)
+                return cuda_fail(e, "event create");
         hp.ready = true;
     }
     const int64_t per = ((n + chunks - 1) / chunks + 255) / 256 * 256;   // whole CTA tiles per chunk
     const int64_t a_env = actions_host ? action_bytes / n : 0;
     const int chunk_path = host_chunk_path(st->worklist && st->cache && cache_stride(cfg) > 0);
 
-    // Queue every chunk on its helper stream: upload, step, download.
+    // PCGRL_HOST_TRACE=n: device timeline of n pipelined calls after 40 warm ones (events after every chunk's upload, kernels
+    // and download, printed to stderr in microseconds from the fork) -- the stand-in for an nsys trace of the host leg.
+    // Tracing queues the operations directly (no CUDA graph).
+    static int trace_left = getenv("PCGRL_HOST_TRACE") ? atoi(getenv("PCGRL_HOST_TRACE")) : 0;
+    static int trace_skip = 40;            // warm calls first (graph capture, clocks, pinned pages)
+    static cudaEvent_t trace_ev[3 * WL_CHUNKS + 1];
+    static bool trace_ready = false;
+    cudaEvent_t* trace = nullptr;
+    if (trace_left > 0 && trace_skip > 0) --trace_skip;
+    else if (trace_left > 0) {
+        if (!trace_ready) {
+            for (auto& ev : trace_ev) cudaEventCreate(&ev);
+            trace_ready = true;
+        }
+        trace = trace_ev;
+    }
+    // Queue every chunk: its upload on the upload stream, its kernels on compute stream c % PIPE_COMPUTE, its download
+    // on the download stream, chained by events.  (With the copies on the compute stream itself, chunk c + 3 could not
+    // start before chunk c's DOWNLOAD had finished -- the device trace, PCGRL_HOST_TRACE, showed the fourth chunk's
+    // kernels starting 60 us after the first chunk's had ended.  PCGRL_HOST_SPLIT_COPIES=0 restores that order.)
+    static const bool split_copies = !(getenv("PCGRL_HOST_SPLIT_COPIES") && atoi(getenv("PCGRL_HOST_SPLIT_COPIES")) == 0);
     auto enqueue_chunks = [&]() -> int {
-        int c = 0;
-        for (int64_t off = 0; off < n; off += per, ++c) {
+        struct Chunk {
+            int64_t off, m;
+            char* a_dev;
+            pcgrl_state sub;
+        } ck[WL_CHUNKS];
+        int n_ck = 0;
+        for (int64_t off = 0; off < n; off += per, ++n_ck) {
+            Chunk& q = ck[n_ck];
             const int64_t m = std::min(per, n - off);
-            cudaStream_t cs = hp.s[c % PIPE_STREAMS];
-            pcgrl_state sub = *st;
+            q.off = off;
+            q.m = m;
+            pcgrl_state& sub = q.sub;
+            sub = *st;
             sub.n_envs = m;
             sub.env_offset = st->env_offset + off;
             sub.grids = st->grids + off * cfg->row_stride;
@@ -520,21 +559,55 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
                          : cfg->action_kind == PCGRL_ACT_CA_TILES ? cfg->row_stride
                          : cfg->action_kind == PCGRL_ACT_CA_LOGITS ? 4 * (int64_t)cfg->n_tiles * cells_of(cfg) : action_elem(cfg);
             }
-            char* a_dev = (char*)actions_dev + off * a_stride;
-            if (actions_host &&
-                (e = cudaMemcpyAsync(a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env), cudaMemcpyHostToDevice, cs)) != cudaSuccess)
+            q.a_dev = (char*)actions_dev + off * a_stride;
+        }
+        const int PIPE_COMPUTE = pipe_compute();
+        cudaStream_t up = hp.s[PIPE_COMPUTE_MAX], down = hp.s[PIPE_COMPUTE_MAX + 1];
+        // every upload first: 1 B per env, on its own stream, long before the chunk's turn comes
+        for (int c = 0; c < n_ck && actions_host; ++c) {
+            cudaStream_t us = split_copies ? up : hp.s[c % PIPE_COMPUTE];
+            if (!split_copies) continue;       // (old order: uploaded below, on the compute stream)
+            if ((e = cudaMemcpyAsync(ck[c].a_dev, (const char*)actions_host + ck[c].off * a_env, (size_t)(ck[c].m * a_env),
+                                     cudaMemcpyHostToDevice, us)) != cudaSuccess)
                 return cuda_fail(e, "H2D actions");
+            if ((e = cudaEventRecord(hp.up_ev[c], us)) != cudaSuccess) return cuda_fail(e, "event record");
+            if (trace) cudaEventRecord(trace[3 * c + 0], us);
+        }
+        for (int c = 0; c < n_ck; ++c) {
+            const int64_t off = ck[c].off, m = ck[c].m;
+            const pcgrl_state& sub = ck[c].sub;
+            cudaStream_t cs = hp.s[c % PIPE_COMPUTE];
+            if (actions_host) {
+                if (split_copies) {
+                    if ((e = cudaStreamWaitEvent(cs, hp.up_ev[c], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+                } else {
+                    if ((e = cudaMemcpyAsync(ck[c].a_dev, (const char*)actions_host + off * a_env, (size_t)(m * a_env),
+                                             cudaMemcpyHostToDevice, cs)) != cudaSuccess)
+                        return cuda_fail(e, "H2D actions");
+                    if (trace) cudaEventRecord(trace[3 * c + 0], cs);
+                }
+            } else if (trace) {
+                cudaEventRecord(trace[3 * c + 0], cs);
+            }
             // every chunk gets its own header and its own body range of the shard's work list
-            int rr = step_launch(cfg, &sub, a_dev, cs, st->worklist, c, off, chunk_path);
+            int rr = step_launch(cfg, &sub, ck[c].a_dev, cs, st->worklist, c, off, chunk_path);
             if (rr) return rr;
-            if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+            if (trace) cudaEventRecord(trace[3 * c + 1], cs);
+            cudaStream_t ds = cs;
+            if (split_copies) {
+                if ((e = cudaEventRecord(hp.k_ev[c], cs)) != cudaSuccess) return cuda_fail(e, "event record");
+                if ((e = cudaStreamWaitEvent(down, hp.k_ev[c], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+                ds = down;
+            }
+            if (records_host && (e = cudaMemcpyAsync(records_host + off * rs, sub.records, (size_t)(m * rs), cudaMemcpyDeviceToHost, ds)) != cudaSuccess)
                 return cuda_fail(e, "D2H records");
-            if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+            if (reward_host && (e = cudaMemcpyAsync(reward_host + off, sub.reward, m * sizeof(float), cudaMemcpyDeviceToHost, ds)) != cudaSuccess)
                 return cuda_fail(e, "D2H reward");
-            if (done_host && (e = cudaMemcpyAsync(done_host + off, sub.done, m, cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+            if (done_host && (e = cudaMemcpyAsync(done_host + off, sub.done, m, cudaMemcpyDeviceToHost, ds)) != cudaSuccess)
                 return cuda_fail(e, "D2H done");
-            if (stats_host && (e = cudaMemcpyAsync(stats_host + off * K, sub.stats, m * K * sizeof(int32_t), cudaMemcpyDeviceToHost, cs)) != cudaSuccess)
+            if (stats_host && (e = cudaMemcpyAsync(stats_host + off * K, sub.stats, m * K * sizeof(int32_t), cudaMemcpyDeviceToHost, ds)) != cudaSuccess)
                 return cuda_fail(e, "D2H stats");
+            if (trace) cudaEventRecord(trace[3 * c + 2], ds);
         }
         return 0;
     };
@@ -547,7 +620,7 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
     // with one cudaGraphLaunch; only the source addresses of the uploads change from step to step
     // (cudaGraphExecMemcpyNodeSetParams1D).  PCGRL_HOST_GRAPH=0 queues the operations directly, as before.
     static const bool use_graph = !(getenv("PCGRL_HOST_GRAPH") && atoi(getenv("PCGRL_HOST_GRAPH")) == 0);
-    if (use_graph && !hp.graph_broken) {
+    if (use_graph && !hp.graph_broken && !trace) {
         HostGraphKey key;
         std::memset(&key, 0, sizeof(key));
         key.cfg = *cfg;
@@ -645,16 +718,33 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
     }
 
     // ---- direct path: helper streams start after everything already queued on the caller's stream --------------------
+    if (trace) cudaEventRecord(trace[3 * WL_CHUNKS], s);
     if ((e = cudaEventRecord(hp.fork, s)) != cudaSuccess) return cuda_fail(e, "event record");
     for (int i = 0; i < PIPE_STREAMS; ++i)
         if ((e = cudaStreamWaitEvent(hp.s[i], hp.fork, 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
+    const auto t_host0 = std::chrono::steady_clock::now();
     if ((r = enqueue_chunks())) return r;
+    const auto t_host1 = std::chrono::steady_clock::now();
     // join: later work on the caller's stream (auto-reset, observe) is ordered after every chunk
     for (int i = 0; i < PIPE_STREAMS; ++i) {
         if ((e = cudaEventRecord(hp.join[i], hp.s[i])) != cudaSuccess) return cuda_fail(e, "event record");
         if ((e = cudaStreamWaitEvent(s, hp.join[i], 0)) != cudaSuccess) return cuda_fail(e, "stream wait");
     }
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(e, "stream sync");
+    if (trace) {
+        const auto t_host2 = std::chrono::steady_clock::now();
+        --trace_left;
+        fprintf(stderr, "[pcgrl host trace] %lld envs, %d chunks, enqueue %.1f us, enqueue + sync %.1f us; per chunk (us from the fork):"
+                        " upload done | kernels done | download done\n", (long long)n, chunks,
+                std::chrono::duration<double, std::micro>(t_host1 - t_host0).count(),
+                std::chrono::duration<double, std::micro>(t_host2 - t_host0).count());
+        for (int c = 0; c < chunks; ++c) {
+            float t[3] = {0, 0, 0};
+            for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], trace[3 * WL_CHUNKS], trace[3 * c + k]);
+            fprintf(stderr, "[pcgrl host trace]   chunk %d (stream %d): %8.1f | %8.1f | %8.1f\n", c, c % pipe_compute(),
+                    t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
+        }
+    }
     return 0;
 }
 

@@ -39,9 +39,11 @@ namespace pcgrl {
                                      // R=3: 0.412 / 0.393 / 0.384 / 0.378 ms per step)
 #endif
 #ifndef PCGRL_INC_CTAS_PER_SM_HOST
-#define PCGRL_INC_CTAS_PER_SM_HOST 3 // the same inside the host pipeline: most of the SM's registers stay free, so the
+#define PCGRL_INC_CTAS_PER_SM_HOST 4 // the same inside the host pipeline: most of the SM's registers stay free, so the
                                      // update / output kernels of the neighbouring chunks run next to the search
-                                     // (e2e at 4 chunks, 2 / 3 / 4 / 5 / 8 CTAs per SM: 2.48 / 2.60 / 2.51 / 2.36 / 2.11e9)
+                                     // (e2e at 4 chunks, 2 / 3 / 4 / 5 / 8 CTAs per SM: 2.48 / 2.60 / 2.51 / 2.36 / 2.11e9 with the
+                                     // copies on the compute streams; with separate copy streams 3 / 4 / 5 / 8:
+                                     // 2.56 / 2.75 / 2.71 / 2.42e9, profiles/r02_e2e_cps_chunks_split.txt)
 #endif
 #ifndef PCGRL_INC_MIN_CLAIM
 #define PCGRL_INC_MIN_CLAIM 12       // lanes that must be waiting before a warp hands out new items: the claim / init
