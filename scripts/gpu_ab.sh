@@ -1,16 +1,9 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/r02_pytest_gpu.txt
-(PCGRL_HOST_TRACE=2 timeout 200 python scripts/host_trace.py 2>&1 | grep "host trace\|call 4[0-9]"; python scripts/pcie_probe.py 2>&1 | tail -6) | tee gpurun_out/r02_host_trace.txt
-timeout 600 python bench.py > gpurun_out/r02_bench.json 2> gpurun_out/r02_final.err
-timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_steps20.json 2>> gpurun_out/r02_final.err
-python - <<'PY'
-import json
-for f in ("r02_bench", "r02_bench_steps20"):
-    d = json.loads(open(f"gpurun_out/{f}.json").read().strip().splitlines()[-1])
-    print(f, "value %.4g e2e %.4g frac %.3f kernel_ms %.4f launches %d clocks %s" % (d["value"], d["e2e"]["value"], d["roofline"]["frac"], d["roofline"]["kernel_ms_per_launch"], d["gpu_launches"], d["clocks"]))
-    for k, v in d["configs"].items():
-        print("   ", k, v.get("error") or "value %.4g e2e %.4g" % (v["value"], v["e2e"]["value"]))
-PY
-tail -3 gpurun_out/r02_final.err
+for last in 4 6 8; do for r in 1 2; do
+PCGRL_INC_CPS_LAST=$last timeout 200 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('last-chunk cps $last: e2e %.4g value %.4g' % (d['e2e']['value'], d['value']))"
+done; done
+PCGRL_HOST_CHUNKS=7 timeout 200 python bench.py --steps 200 --warmup 10 --no-cpu-baseline --no-configs 2>>gpurun_out/ab.err | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('chunks 7 (last alone, cps 8): e2e %.4g value %.4g' % (d['e2e']['value'], d['value']))"
+timeout 900 python -m pytest tests -m gpu -x -q -k "host or packed or compact or pipelined or split or vector" 2>&1 | tail -3
+tail -3 gpurun_out/ab.err
