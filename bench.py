@@ -328,10 +328,10 @@ def run_workload(a, workload, n_envs, steps, warmup, e2e_steps, rank, world, loc
         h2d, d2h = env.host_io_bytes()
         api = ("BatchedPcgrlEnv(compact_host_io=True).step_host -> pcgrl_step_host_packed (pinned %s actions H2D; ONE "
                "packed record array D2H: reward f32 | stats %s | done | changed, %d B per env; sync; binary / zelda "
-               "shards pipelined in chunks over 3 streams)" % (np.dtype(dt_a).name, env.record_dtype()["stats"].base.name,
+               "shards pipelined in chunks over 3 compute streams + an upload and a download stream)" % (np.dtype(dt_a).name, env.record_dtype()["stats"].base.name,
                                                                env.record_stride)) if env.compact_host_io else \
               ("BatchedPcgrlEnv.step_host -> pcgrl_step_host (pinned int32 actions H2D; reward, done, int32 stats D2H to "
-               "pinned host buffers; sync; binary / zelda shards pipelined in chunks over 3 streams)")
+               "pinned host buffers; sync; binary / zelda shards pipelined in chunks over 3 compute streams + an upload and a download stream)")
         e2e = {"value": world * n_envs * k_e2e / float(te[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e, "api": api}
 

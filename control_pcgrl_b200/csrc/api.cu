@@ -243,9 +243,10 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
     g_launches.fetch_add(problem == PCGRL_PROB_SOKOBAN ? 4 : (multi ? multi : 1), std::memory_order_relaxed);
     return 0;
 }
-// Chunked, stream-pipelined host step: the shard is cut into chunks of whole CTA tiles; chunk c's action
-// upload, step kernel and result download are queued on helper stream c % PIPE_STREAMS, so the H2D copy of
-// chunk c+1, the kernel of chunk c and the D2H copy of chunk c-1 overlap (two copy engines + the SMs).
+// Chunked, stream-pipelined host step: the shard is cut into chunks of whole CTA tiles; every chunk's action upload
+// is queued on the upload stream, its step kernels on compute stream c % n_compute, its result download on the
+// download stream (events in between), so uploads, kernels and downloads of different chunks overlap (two copy
+// engines + the SMs) and a chunk never waits for another chunk's download.
 // Only for kernels that keep no cross-launch device state (scratch == 0, i.e. not the persistent solvers).
 constexpr int PIPE_COMPUTE_MAX = 6;             // streams the chunks' kernels rotate over: n_compute of them (PCGRL_HOST_STREAMS)
 constexpr int PIPE_STREAMS = PIPE_COMPUTE_MAX + 2;  // + one upload stream and one download stream (the last two)
@@ -613,10 +614,10 @@ static int32_t step_host_impl(const pcgrl_config* cfg, const pcgrl_state* st, co
     };
 
     // ---- CUDA graph of the whole pipeline -------------------------------------------------------------------------
-    // A step of the host pipeline is ~25 queue operations (copies, launches, events over 3 streams) whose CPU cost sits
+    // A step of the host pipeline is ~25 queue operations (copies, launches, events over five streams) whose CPU cost sits
     // on the critical path of every step: the first kernel cannot start before its upload is queued, and the call
     // cannot return before the last event is.  The operations only depend on the pointers, so they are captured ONCE
-    // (stream capture on helper stream 0, the other two forked / joined by events inside the capture) and replayed
+    // (stream capture on helper stream 0, the others forked / joined by events inside the capture) and replayed
     // with one cudaGraphLaunch; only the source addresses of the uploads change from step to step
     // (cudaGraphExecMemcpyNodeSetParams1D).  PCGRL_HOST_GRAPH=0 queues the operations directly, as before.
     static const bool use_graph = !(getenv("PCGRL_HOST_GRAPH") && atoi(getenv("PCGRL_HOST_GRAPH")) == 0);
