@@ -298,8 +298,10 @@ static int host_chunks(const pcgrl_config* cfg, int64_t n, bool packed) {
     // measured on B200 (binary 16x16, e2e env-steps/s): 64 Ki envs 1 chunk best (2 / 4 chunks: 3.3 / 2.4e8); 256 Ki
     // 1 / 2 / 4 chunks -> 8.5 / 9.1 / 7.1e8; 512 Ki -> 1.07 / 1.26 / 1.09e9; 1 Mi 2 / 4 / 8 -> 1.77 / 2.0 / 1.77e9.
     // Every chunk costs ~18 us of queue operations, so small shards take fewer.
+    // With the copies on their own streams (profiles/r02_e2e_chunks_by_size.txt): 128 Ki 1 / 2 / 3 / 4 chunks -> 8.9 / 9.2 /
+    // 8.7 / 8.5e8; 256 Ki -> 1.40 / 1.44 / 1.35 / 1.30e9; 512 Ki -> 1.82 / 1.84 / 2.05 / 2.09e9; 1 Mi 4 / 6 / 8 -> 2.75 / 2.73 / 2.54e9.
     if (n < (1 << 17)) return 1;
-    if (n < (1 << 20)) return 2;
+    if (n < (1 << 19)) return 2;
     return 4;
 }
 }  // namespace pcgrl
