@@ -101,52 +101,41 @@ struct Maze3DProb {
     // ---- helper_3D._passable for one direction: foothold reached from (x, y, z) going (dx, dy) ----------
     // Returns false if the direction offers no move; else the foothold cell index, the number of path
     // entries the move appends (1 walk, 2 stairs / level jump, 3 jump up / down) and whether it is a jump.
+    // Branch-free: with w = the neighbour column's AIR bits z-2 .. z+3 (bits below 0 and from Z up read as "not
+    // AIR", which is what the reference's explicit range tests amount to) the four kinds of move are mutually
+    // exclusive bit patterns --
+    //   walk       !w1  w2  w3                      (:229-237)      step down  !w0  w1  w2  w3   (:243-252)
+    //   step up    !w2  w3  w4  and head-room c0[z+2] (:259-266)    jump        w0..w4 all AIR, c0[z+2], landing column in range (:279-288)
+    // and so are the three landings of a jump on the column two cells away (u = its bits z-2 .. z+3):
+    //   level !u1 u2 u3 u4 (:289-296)   up !u2 u3 u4 u5 (:297-304)   down !u0 u1 u2 u3 (:305-312)
+    // so the four lanes of a pop run one straight instruction stream instead of a cascade of divergent tests.
     __device__ static __forceinline__ bool move(const Ctx& c, int x, int y, int z, int dx, int dy, int& ncell,
                                                 int& cost, int& jump) {
         const int nx = x + dx, ny = y + dy;
         if (nx < 0 || ny < 0 || nx >= c.X || ny >= c.Y) return false;                    // :225
-        const int Z = c.Z;
         const uint32_t cn = c.col[ny * c.X + nx], c0 = c.col[y * c.X + x];
-#define AIR(m, k) (((m) >> (k)) & 1u)
-        jump = 0;
-        if ((z == 0 || !AIR(cn, z - 1)) && AIR(cn, z) && AIR(cn, z + 1)) {               // :229-237 walk
-            ncell = (z * c.Y + ny) * c.X + nx;
-            cost = 1;
-            return true;
-        }
-        if ((z == 1 || (z > 1 && !AIR(cn, z - 2))) && z >= 1 && AIR(cn, z - 1) && AIR(cn, z) && AIR(cn, z + 1)) {
-            ncell = ((z - 1) * c.Y + ny) * c.X + nx;                                     // :243-252 step down
-            cost = 2;
-            return true;
-        }
-        if (z + 2 < Z && !AIR(cn, z) && AIR(cn, z + 1) && AIR(cn, z + 2) && AIR(c0, z + 2)) {
-            ncell = ((z + 1) * c.Y + ny) * c.X + nx;                                     // :259-266 step up
-            cost = 2;
-            return true;
-        }
+        const uint32_t w = ((cn << 2) >> z) & 0x3Fu;
+        const uint32_t h2 = (c0 >> (z + 2)) & 1u;
+        const uint32_t w0 = w & 1u, w1 = (w >> 1) & 1u, w2 = (w >> 2) & 1u, w3 = (w >> 3) & 1u, w4 = (w >> 4) & 1u;
+        const uint32_t walk = (w1 ^ 1u) & w2 & w3;
+        const uint32_t down = (w0 ^ 1u) & w1 & w2 & w3;
+        const uint32_t up = (w2 ^ 1u) & w3 & w4 & h2;
         const int jx = nx + dx, jy = ny + dy;
-        if (z >= 2 && z + 2 < Z && ((cn >> (z - 2)) & 0x1Fu) == 0x1Fu && AIR(c0, z + 2) && jx >= 0 && jy >= 0 &&
-            jx < c.X && jy < c.Y) {                                                      // :279-288 jump over a gap
-            const uint32_t cj = c.col[jy * c.X + jx];
-            jump = 1;
-            if (AIR(cj, z + 1) && AIR(cj, z + 2) && AIR(cj, z) && !AIR(cj, z - 1)) {     // :289-296 level
-                ncell = (z * c.Y + jy) * c.X + jx;
-                cost = 2;
-                return true;
-            }
-            if (z + 3 < Z && AIR(cj, z + 3) && AIR(cj, z + 2) && AIR(cj, z + 1) && !AIR(cj, z)) {
-                ncell = ((z + 1) * c.Y + jy) * c.X + jx;                                 // :297-304 up
-                cost = 3;
-                return true;
-            }
-            if (AIR(cj, z) && AIR(cj, z + 1) && AIR(cj, z - 1) && !AIR(cj, z - 2)) {     // :305-312 down
-                ncell = ((z - 1) * c.Y + jy) * c.X + jx;
-                cost = 3;
-                return true;
-            }
-        }
-#undef AIR
-        return false;
+        const bool j_in = jx >= 0 && jy >= 0 && jx < c.X && jy < c.Y;
+        const uint32_t jp = ((w & 0x1Fu) == 0x1Fu) & h2 & (uint32_t)j_in;
+        const uint32_t cj = j_in ? c.col[jy * c.X + jx] : 0u;
+        const uint32_t u = ((cj << 2) >> z) & 0x3Fu;
+        const uint32_t u0 = u & 1u, u1 = (u >> 1) & 1u, u2 = (u >> 2) & 1u, u3 = (u >> 3) & 1u, u4 = (u >> 4) & 1u,
+                       u5 = (u >> 5) & 1u;
+        const uint32_t j_level = jp & (u1 ^ 1u) & u2 & u3 & u4;
+        const uint32_t j_up = jp & (u2 ^ 1u) & u3 & u4 & u5;
+        const uint32_t j_down = jp & (u0 ^ 1u) & u1 & u2 & u3;
+        const uint32_t landed = j_level | j_up | j_down;
+        jump = (int)jp;
+        const int nz = z + (int)(up | j_up) - (int)(down | j_down);
+        cost = (int)(walk + 2u * (down | up | j_level) + 3u * (j_up | j_down));
+        ncell = landed ? (nz * c.Y + jy) * c.X + jx : (nz * c.Y + ny) * c.X + nx;
+        return (walk | down | up | landed) != 0u;
     }
 
     // ---- helper_3D.run_dijkstra from `start` (warp-uniform FIFO; lanes 0..3 evaluate the 4 directions) -----
