@@ -92,6 +92,12 @@ struct KParams {
     uint8_t* cache;               // [N, cache_stride]
     int32_t cache_stride;
     int32_t host_chunk;           // 1: this launch is one chunk of the host pipeline (other chunks run beside it)
+    // progressive host pipeline (api.cu, step_split.cu): the three kernels of the split path launched separately
+    int32_t split_phase;          // 0: update + search + output; 1: update only; 2: ONE search over ml_lists chunk lists; 3: wait for
+                                  // this chunk's list to be searched (header word 5 == ml_target), then output
+    int32_t ml_lists;             // phase 2: number of chunk lists (headers 16 ints apart from wl_hdr)
+    int32_t ml_target;            // phase 3: search warps that must have reported the list
+    int64_t ml_per;               // phase 2: envs per chunk (the last chunk may hold fewer)
 };
 
 // one scalar action (narrow / turtle / flat wide) in the width the caller chose (cfg.action_elem_bytes)

@@ -45,6 +45,9 @@ namespace pcgrl {
                                      // copies on the compute streams; with separate copy streams 3 / 4 / 5 / 8:
                                      // 2.56 / 2.75 / 2.71 / 2.42e9, profiles/r02_e2e_cps_chunks_split.txt)
 #endif
+#ifndef PCGRL_PROG_CTAS_PER_SM
+#define PCGRL_PROG_CTAS_PER_SM 6
+#endif
 #ifndef PCGRL_INC_MIN_CLAIM
 #define PCGRL_INC_MIN_CLAIM 12       // lanes that must be waiting before a warp hands out new items: the claim / init
                                      // stream then runs with that many lanes (A/B 1 / 4 / 8 at R=3: 0.412 / 0.390 / 0.387)
@@ -524,6 +527,123 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_split_stats_inc_multi: ONE incremental search over the work lists of every chunk of the host pipeline.
+//
+// The chunked pipeline used to run one search launch per chunk on rotating streams; every launch has a tail in which
+// its lanes run dry, and concurrent launches share the SMs so that the first chunk's result was ready only after 2/3
+// of the whole step (profiles/r02_host_trace.txt: kernels done at 190 / 270 / 274 / 361 us).  Here every warp walks
+// the lists in chunk order -- its slice of list 0, then of list 1, ... -- and its lanes keep claiming across the list
+// boundaries, so the SIMT fill is that of the whole-shard search while chunk c is finished after about (c + 1) / n of
+// the kernel.  A warp reports a list (atomicAdd on header word 5, after a fence) once it has claimed its whole
+// slice of it and none of its lanes still works on one of its items; when all warps have reported, the chunk's
+// k_wait_list lets the output kernel and the download go (k_wait_list runs on another stream while this kernel is
+// still busy with the later lists).
+// ------------------------------------------------------------------------------------------------
+template <int NW, bool TWO>
+__global__ void __launch_bounds__(STAT_THREADS, NW >= 8 ? PCGRL_PROG_CTAS_PER_SM : 1) k_split_stats_inc_multi(const KParams p) {
+    using M = BinaryIncMachine<NW, TWO>;
+    __shared__ uint32_t s_work[STAT_THREADS * M::SMEM_WORDS];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int n_lists = p.ml_lists;
+    const int n_warps = gridDim.x * (STAT_THREADS / 32);
+    const int gw = blockIdx.x * (STAT_THREADS / 32) + (tid >> 5);
+    if (blockIdx.x == 0 && tid < n_lists) {   // publish every list's count, clear the other counter (as wl_count_search)
+        int32_t* hdr = p.wl_hdr + 16 * tid;
+        const int par = *(volatile const int*)(hdr + 3) & 1;
+        hdr[4] = *(volatile const int*)(hdr + par);
+        hdr[par ^ 1] = 0;
+    }
+    const int W = p.d1;
+    int cl = -1, lo = 0, hi = 0, sig = 0;                  // warp-uniform: list being claimed from, slice, next list to report
+    M m;
+    bool active = false;
+    int my_list = 0, my_item = 0;                          // per lane; pointers are rebuilt from them (registers)
+    for (;;) {
+        unsigned need = __ballot_sync(0xffffffffu, !active);
+        if (need && (__popc(need) >= PCGRL_INC_MIN_CLAIM || need == 0xffffffffu || (cl == n_lists - 1 && hi - lo < PCGRL_INC_MIN_CLAIM))) {
+            for (;;) {
+                while (lo >= hi && cl + 1 < n_lists) {     // next list: this warp's slice of it
+                    ++cl;
+                    const int32_t* hdr = p.wl_hdr + 16 * cl;
+                    const int par = *(volatile const int*)(hdr + 3) & 1;
+                    const int count = *(volatile const int*)(hdr + par);
+                    const int per_w = (count + n_warps - 1) / n_warps;
+                    lo = min(count, gw * per_w);
+                    hi = min(count, lo + per_w);
+                }
+                if (lo >= hi) break;                       // every list is claimed
+                const int mine = lo + __popc(need & lt);
+                if (!active && mine < hi) {
+                    const int64_t first = (int64_t)cl * p.ml_per;
+                    const int2 it = ((const int2*)(p.worklist + 4 * first))[mine];
+                    const int y = it.y / W, x = it.y - y * W;
+                    const int bitpos = TWO ? y * 16 + x : y * 32 + x;
+                    const int32_t* st = p.stats + 2 * (first + it.x);
+                    m.init(s_work + tid * M::SMEM_WORDS, (const uint32_t*)(p.cache + (first + it.x) * p.cache_stride), bitpos, st[0], st[1]);
+                    my_item = mine;
+                    my_list = cl;
+                    active = true;
+                }
+                lo = min(hi, lo + __popc(need));
+                need = __ballot_sync(0xffffffffu, !active);
+                if (!need || lo < hi) break;               // lanes left over at the end of a slice go on to the next list
+            }
+        }
+        const unsigned act = __ballot_sync(0xffffffffu, active);
+        // lists below the oldest one that is still in flight or not claimed to the end are finished for this warp
+        const int oldest = __reduce_min_sync(0xffffffffu, active ? my_list : (lo < hi ? cl : cl + 1));
+        while (sig < oldest) {
+            __threadfence();                               // every lane's stats / cache rows of that list
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(p.wl_hdr + 16 * sig + 5, 1);
+            }
+            ++sig;
+        }
+        if (!act) {
+            if (lo >= hi && cl + 1 >= n_lists) break;
+            continue;
+        }
+        if (active) {
+            bool alive = m.expand();
+#pragma unroll
+            for (int r = 1; r < PCGRL_INC_EXPAND_R; ++r)
+                if (alive) alive = m.expand();
+            if (!alive && m.transition()) {
+                int out[2];
+                m.finish(out, const_cast<uint32_t*>(m.cache));
+                const int64_t first = (int64_t)my_list * p.ml_per;
+                const int64_t cap = min(p.ml_per, p.n_envs - first);
+                *(int2*)(p.worklist + 4 * first + 2 * cap + 2 * (int64_t)my_item) = make_int2(out[0], out[1]);
+                active = false;
+            }
+        }
+    }
+}
+
+// One thread waits until every search warp has reported the chunk's list, then re-arms the counter for the next
+// step.  Launched AFTER the search kernel (so it can never sit in front of it in a hardware queue) on the stream
+// that carries the chunk's output kernel and download.  A wait of more than two seconds sets status bit 5.
+__global__ void k_wait_list(int32_t* hdr, int target, int32_t* status) {
+    if (threadIdx.x != 0) return;
+    volatile int* f = hdr + 5;
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (*f < target) {
+        __nanosleep(400);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 2000000000ull) {
+            if (status) atomicOr(status, 32);
+            break;
+        }
+    }
+    __threadfence();
+    *f = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // k_step_inc: the whole binary env step in ONE launch around the incremental search (no global work list).
 // Every warp owns a contiguous slice of the shard's envs and loops over three kinds of work, each issued with
 // (nearly) all 32 lanes:
@@ -681,6 +801,30 @@ static cudaError_t sm_count(int& n) {
     return cudaSuccess;
 }
 
+// CTAs of the progressive pipeline's search: one short of filling the SMs' register files (8 CTAs of 64 registers x
+// 128 threads), so that the chunks' wait / output kernels become resident beside it.  PCGRL_PROG_CPS overrides (A/B).
+static int64_t prog_search_ctas(int64_t n, int n_sm) {
+    static int env_v = -1;
+    if (env_v < 0) {
+        const char* e = getenv("PCGRL_PROG_CPS");
+        env_v = e ? atoi(e) : 0;
+    }
+    const int64_t want = (n + STAT_THREADS - 1) / STAT_THREADS;
+    const int64_t cap = (int64_t)n_sm * (env_v > 0 ? env_v : PCGRL_PROG_CTAS_PER_SM);
+    return want < cap ? want : cap;
+}
+// search warps of that launch (= reports every chunk's k_wait_list waits for); < 0 on error
+int split_prog_search_warps(int64_t n) {
+    int n_sm = 0;
+    if (sm_count(n_sm) != cudaSuccess) return -1;
+    return (int)prog_search_ctas(n, n_sm) * (STAT_THREADS / 32);
+}
+// can this config run the progressive host pipeline (binary, one-cell edits, maps <= 16x16, cache + work list)?
+bool split_prog_supported(const KParams& p, int problem) {
+    return problem == PCGRL_PROB_BINARY && p.ndim == 2 && p.d0 <= 16 && p.d1 <= 16 && p.cache && p.worklist &&
+           p.rep != PCGRL_REP_CELLULAR && p.action_kind != PCGRL_ACT_PATCH;
+}
+
 template <class Machine, int NW, bool TWO>
 static cudaError_t launch_split(const KParams& p, cudaStream_t s, int incremental) {
     constexpr int K = Machine::Prob::K;
@@ -697,8 +841,23 @@ static cudaError_t launch_split(const KParams& p, cudaStream_t s, int incrementa
             return cudaGetLastError();
         }
     }
+    if constexpr (Machine::HAS_CACHE && TWO) {
+        if (p.split_phase == 2) {   // progressive host pipeline: one search over every chunk's list
+            int n_sm = 0;
+            if ((e = sm_count(n_sm)) != cudaSuccess) return e;
+            k_split_stats_inc_multi<NW, TWO><<<(unsigned)prog_search_ctas(n, n_sm), STAT_THREADS, 0, s>>>(p);
+            return cudaGetLastError();
+        }
+    }
+    if (p.split_phase == 3) {       // ... and per chunk: wait for its list, then the output kernel
+        k_wait_list<<<1, 32, 0, s>>>(p.wl_hdr, p.ml_target, p.status);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        k_split_out<K><<<(unsigned)((n + OUT_THREADS - 1) / OUT_THREADS), OUT_THREADS, 0, s>>>(p);
+        return cudaGetLastError();
+    }
     k_split_act<<<(unsigned)((n + ACT_THREADS - 1) / ACT_THREADS), ACT_THREADS, 0, s>>>(p);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (p.split_phase == 1) return cudaSuccess;
     bool ran_inc = false;
     if constexpr (Machine::HAS_CACHE && TWO) {
         if (incremental == 1) {
@@ -746,8 +905,9 @@ static cudaError_t dispatch_split(const KParams& p, cudaStream_t s, int incremen
 cudaError_t launch_bitboard_split(const KParams& p, int problem, cudaStream_t s, int incremental, bool& supported,
                                   int& n_launches) {
     supported = false;
-    n_launches = 3;
+    n_launches = p.split_phase == 0 ? 3 : p.split_phase == 3 ? 2 : 1;
     if (p.mode != MODE_STEP || !p.worklist || p.rep == PCGRL_REP_CELLULAR) return cudaSuccess;
+    if (p.split_phase != 0 && (!split_prog_supported(p, problem) || incremental != 1)) return cudaSuccess;
     if (problem == PCGRL_PROB_BINARY) {
         const int inc = p.cache != nullptr && p.d0 <= 16 && p.d1 <= 16 ? incremental : 0;
         if (inc == 2) n_launches = 1;

@@ -49,7 +49,7 @@ def test_step_paths_agree_and_match_fresh_stats(problem, rep, shape, controls, m
     kw = dict(controls=controls, max_board_scans=0.6)
     if rep == "wide":
         kw["obs_window"] = shape
-    paths = ["fused", "split", "inc", "incfused"]
+    paths = ["fused", "split", "inc", "incfused", "lg"]
     envs = _envs(problem, rep, shape, n, paths, **kw)
     has_cache = envs[2].cache is not None
     assert has_cache == (problem == "binary" and max(shape) <= 16)
@@ -85,8 +85,33 @@ def test_step_paths_agree_and_match_fresh_stats(problem, rep, shape, controls, m
             for e in envs[2:]:
                 fresh = e.compute_stats(e.maps, holes=e.holes) if e.holey else e.compute_stats(e.maps)
                 assert torch.equal(fresh, e.stats), (t, int((fresh != e.stats).any(dim=1).sum()))
+            if has_cache:      # the incremental paths keep the same cache rows (they may alternate on one shard)
+                assert torch.equal(envs[2].cache, envs[3].cache) and torch.equal(envs[2].cache, envs[4].cache), t
     for e in envs:
         e.check_status()
+
+
+@pytest.mark.parametrize("n,shape", [(30_000, (16, 16)), (60_000, (16, 16)), (400_000, (16, 16)), (400_000, (6, 9))])
+def test_lanegroup_step_tiles_and_persistent_grid(n, shape, monkeypatch):
+    """k_step_lanegroup picks 8 / 16 / 32 envs per warp by shard size and loops when the shard needs more warps than
+    one wave holds: every variant must agree with the three-launch incremental path, and a shard may alternate
+    between the two from step to step (same cache rows)."""
+    envs = _envs("binary", "narrow", shape, n, ["inc", "lg"], max_board_scans=0.02)
+    for e in envs:
+        e.reset()
+    a, b = envs
+    gen = torch.Generator(device=a.device).manual_seed(9)
+    for t in range(int(a.max_iterations * 2.2) + 3):
+        act = torch.randint(0, 2, (n,), generator=gen, device=a.device, dtype=torch.int32)
+        monkeypatch.setenv("PCGRL_STEP_PATH", "inc" if t % 5 != 4 else "lg")
+        ra, da = a.step(act)
+        ra, da = ra.clone(), da.clone()
+        monkeypatch.setenv("PCGRL_STEP_PATH", "lg" if t % 7 != 6 else "inc")
+        rb, db = b.step(act)
+        assert torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(a.stats, b.stats) and torch.equal(a.grids, b.grids) and torch.equal(a.cache, b.cache), t
+    assert torch.equal(b.compute_stats(b.maps), b.stats)
+    b.check_status()
 
 
 def test_incremental_cache_is_consistent_with_the_grids(monkeypatch):
@@ -154,3 +179,64 @@ def test_incremental_hand_built_maps():
         fresh = env.compute_stats(env.maps)
         assert torch.equal(fresh, env.stats), ((y, x, v), fresh.tolist(), env.stats.tolist())
     env.check_status()
+
+
+@pytest.mark.parametrize("rep,shape,controls,compact", [("narrow", (16, 16), None, True),
+                                                        ("wide", (16, 16), ["regions", "path-length"], False),
+                                                        ("turtle", (7, 5), None, True),
+                                                        ("narrow", (3, 4), None, False),
+                                                        ("narrow", (2, 16), None, True)])
+def test_progressive_host_pipeline_equals_device_step(rep, shape, controls, compact, monkeypatch):
+    """pcgrl_step_host's progressive pipeline (per-chunk update kernels, ONE search over every chunk's work list in
+    chunk order, per-chunk wait + output + download) must give exactly what a whole-shard pcgrl_step gives, for every
+    chunk count (ragged last chunk, chunks smaller than a warp's slice, more chunks than the search has lists to
+    fill), across auto-resets, and interleaved with the chunk-per-stream pipeline and plain device steps on the same
+    work-list headers."""
+    import control_pcgrl_b200 as P
+    n = 70_001
+    kw = dict(obs_window=shape) if rep == "wide" else {}
+    cfg = P.make_config("binary", rep, map_shape=shape, controls=controls, max_board_scans=0.05, **kw)
+    a = P.BatchedPcgrlEnv(cfg, n, seed=3, auto_reset=True, compact_host_io=compact)
+    b = P.BatchedPcgrlEnv(cfg, n, seed=3, auto_reset=True)
+    assert a.cache is not None and a.worklist is not None
+    if controls:
+        g = torch.Generator(device=a.device).manual_seed(1)
+        a.sample_uniform_targets(generator=g)
+        b.targets.copy_(a.targets)
+    a.reset()
+    b.reset()
+    n_act = _n_act(a, rep, shape)
+    rng = np.random.default_rng(0)
+    monkeypatch.setenv("PCGRL_HOST_PROG_MIN", "1024")
+    launches = a.lib.pcgrl_launch_count
+    for t, (chunks, prog) in enumerate([("2", 1), ("8", 1), ("5", 1), ("64", 1), ("3", 0), ("", 1), ("7", 1), ("1", 1),
+                                        ("4", 0), ("16", 1)] * 3):
+        if chunks:
+            monkeypatch.setenv("PCGRL_HOST_CHUNKS", chunks)
+        else:
+            monkeypatch.delenv("PCGRL_HOST_CHUNKS", raising=False)
+        monkeypatch.setenv("PCGRL_HOST_PROG", str(prog))
+        act = rng.integers(0, n_act, size=n).astype(a.action_shape_dtype()[1])
+        l0 = launches()
+        r, d, s = a.step_host(act)
+        launched = launches() - l0
+        if prog and chunks not in ("1", ""):      # (the default is one chunk below 128 Ki envs: plain upload / step / download)
+            n_ck = int(chunks)
+            n_ck = -(-n // ((-(-n // n_ck) + 255) // 256 * 256))      # ragged: chunks of whole 256-env tiles
+            # n_ck update kernels + 1 search + n_ck (wait + output) [+ the auto-reset launch]
+            assert launched in (3 * n_ck + 1, 3 * n_ck + 2), (chunks, launched)
+        if t % 4 == 3:     # a plain device step in between (header 0 is shared by all paths)
+            act2 = rng.integers(0, n_act, size=n).astype(np.int32)
+            a.step(torch.from_numpy(act2.astype(a.action_shape_dtype()[1])).to(a.device))
+            b.step(torch.from_numpy(act).to(b.device, dtype=torch.int32))
+            b.step(torch.from_numpy(act2).to(b.device))
+        else:
+            rb, db = b.step(torch.from_numpy(act).to(b.device, dtype=torch.int32))
+            np.testing.assert_array_equal(np.asarray(r), rb.cpu().numpy())
+            np.testing.assert_array_equal(np.asarray(d).astype(bool), db.cpu().numpy().astype(bool))
+        assert torch.equal(a.grids, b.grids) and torch.equal(a.stats, b.stats) and torch.equal(a.pos, b.pos)
+        assert torch.equal(a.iteration, b.iteration) and torch.equal(a.changes, b.changes)
+        assert torch.equal(a.cache, b.cache)
+    a.check_status()
+    fresh = a.compute_stats(a.grids)
+    assert torch.equal(fresh, a.stats)
