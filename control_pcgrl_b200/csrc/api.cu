@@ -110,7 +110,7 @@ static int cache_stride(const pcgrl_config* c) {
     return bitboard_cache_stride(kernel_problem(c->problem), c->ndim, c->dims[0], c->dims[1], c->representation,
                                  c->action_kind);
 }
-// PCGRL_STEP_PATH = fused | split | inc | incfused (default incfused): which of the equivalent step paths pcgrl_step
+// PCGRL_STEP_PATH = fused | split | inc | incfused | lg (default by shard size, step_path()): which of the equivalent step paths pcgrl_step
 // takes when the caller supplied the buffers for all of them (A/B runs and the path-equivalence tests)
 static int path_of(const char* e, int dflt) {
     if (!e) return dflt;
@@ -120,7 +120,12 @@ static int path_of(const char* e, int dflt) {
 // Measured on B200, binary 16x16, ms per step of a shard of 64 Ki / 256 Ki / 512 Ki / 1 Mi envs:
 //   fused 0.066 / 0.131 / 0.220 / 0.385   inc (3 launches) 0.063 / 0.114 / 0.175 / 0.304   incfused 0.058 / 0.122 / 0.203 / 0.367
 // so a plain pcgrl_step takes the one-launch incremental kernel for small shards and the three-launch one above.
-static int step_path(int64_t n_envs) { return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (160 << 10) ? 3 : 2); }
+// The lane-group kernel (step_lanegroup.cu, path 4 "lg"; kernel times, profiles/r02_lanegroup_by_size.txt): 1 Ki / 4 Ki / 16 Ki
+// envs 24.9 / 27.1 / 31.5 us against 30.8 / 32.6 / 33.7 us for incfused, 64 Ki 67.5 / 58.0 -- it takes the shards below 24 Ki envs
+// (RLlib-scale batches).
+static int step_path(int64_t n_envs) {
+    return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (24 << 10) ? 4 : n_envs < (160 << 10) ? 3 : 2);
+}
 // Chunks of the host pipeline run on different streams.  With the search kernel of the three-launch incremental
 // path limited to 3 CTAs per SM (PCGRL_INC_CTAS_PER_SM_HOST) the memory-bound update / output kernels of the
 // neighbouring chunks run NEXT TO it: e2e 2.60e9 env-steps/s at 4 chunks, against 2.24e9 with the fused kernel and

@@ -29,7 +29,9 @@
 namespace pcgrl {
 
 #ifndef PCGRL_LG_EXPAND_R
-#define PCGRL_LG_EXPAND_R 4       // BFS levels between two looks at the frontier (a dead frontier stays dead: extra levels are no-ops)
+#define PCGRL_LG_EXPAND_R 12      // BFS levels per trip (computed blind, see expand_window).  A/B 4 / 6 / 8 / 12 (kernel time, CUDA
+                                  // events): 2 Ki envs 28.8 / 26.4 / 25.7 / 25.0 us, 16 Ki envs 34.9 / 32.4 / 31.8 / 31.5 us -- a small
+                                  // shard has issue slots to spare, so few long trips beat many short ones
 #endif
 constexpr int LG_THREADS = 128;
 
@@ -111,16 +113,34 @@ struct LaneGroupInc {
             hit = false;
         }
     }
-    // one BFS level of the groups with `run`; returns whether the group's frontier is still alive (false for !run)
-    __device__ __forceinline__ bool expand(bool run) {
-        const uint32_t n = nbr(front) & avail;
-        const bool any = gany(run && n != 0u);
-        if (any) {          // (front keeps the last non-empty level when the frontier dies)
-            avail &= ~n;
-            front = n;
-            ++level;
+    // PCGRL_LG_EXPAND_R BFS levels of the groups with `run`; returns whether the group's frontier is still alive
+    // afterwards (false for !run).  The levels are computed blind, one straight dependent chain of shuffles and
+    // logic ops -- a dead frontier stays dead and leaves avail alone, so running past the end is harmless -- and only
+    // then the ballots (independent of each other, off the chain) say how many levels were real: front must end up
+    // as the LAST NON-EMPTY level (its lowest cell is the far tile) and level counts only those.
+    __device__ __forceinline__ bool expand_window(bool run) {
+        uint32_t f = front, av = avail, hist[PCGRL_LG_EXPAND_R];
+#pragma unroll
+        for (int r = 0; r < PCGRL_LG_EXPAND_R; ++r) {
+            const uint32_t n = nbr(f) & av;
+            av &= ~n;
+            f = n;
+            hist[r] = n;
         }
-        return any;
+        int adv = 0;
+        uint32_t last = front;
+#pragma unroll
+        for (int r = 0; r < PCGRL_LG_EXPAND_R; ++r) {
+            const bool some = gany(run && hist[r] != 0u);   // monotone: once a level is empty the later ones are too
+            adv += some ? 1 : 0;
+            last = some ? hist[r] : last;
+        }
+        if (run) {
+            avail = av;
+            front = last;
+            level += adv;
+        }
+        return run && adv == PCGRL_LG_EXPAND_R;
     }
     // The groups with `dead` (busy, frontier died) take their transition; returns true for the groups whose search is
     // over.  Each phase is one block entered by the whole warp if any group needs it.
@@ -273,9 +293,7 @@ __global__ void __launch_bounds__(LG_THREADS) k_step_lanegroup(const __grid_cons
                 todo &= ~((2u << last) - 1u);
             }
             if (!__any_sync(0xffffffffu, active)) break;
-            bool alive = m.expand(active);
-#pragma unroll
-            for (int r = 1; r < PCGRL_LG_EXPAND_R; ++r) alive = m.expand(alive);
+            const bool alive = m.expand_window(active);
             if (m.transition(active && !alive)) {
                 int out[2];
                 m.finish(out, row);

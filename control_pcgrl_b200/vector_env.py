@@ -14,9 +14,20 @@ from .batched_env import BatchedPcgrlEnv
 
 
 class PcgrlVectorEnv:
+    """shards > 1: the N envs live in `shards` independent BatchedPcgrlEnv objects (consecutive env ranges, the same
+    maps as one shard would draw: resets are counter-based on the global env index), each stepped and observed on
+    its own CUDA stream.  The binary step is bound by the integer pipes and the observation writer by HBM, so one
+    shard's search runs beside another shard's observation writes instead of the two taking turns
+    (scripts/bench_rl_loop.py).  Outputs are the same [N, ...] tensors either way."""
+
     def __init__(self, cfg, num_envs: int, device="cuda:0", obs_dtype=torch.float32, env_offset=0, seed=0,
-                 uniform_targets: bool | None = None):
-        self.env = BatchedPcgrlEnv(cfg, num_envs, device=device, env_offset=env_offset, seed=seed, auto_reset=False)
+                 uniform_targets: bool | None = None, shards: int = 1):
+        shards = max(1, min(int(shards), num_envs))
+        per = -(-num_envs // shards)
+        self._ranges = [(lo, min(num_envs, lo + per)) for lo in range(0, num_envs, per)]
+        self.shards = [BatchedPcgrlEnv(cfg, hi - lo, device=device, env_offset=env_offset + lo, seed=seed, auto_reset=False)
+                       for lo, hi in self._ranges]
+        self.env = self.shards[0]          # metadata (spaces, names, bounds); the only shard when shards == 1
         self.num_envs = num_envs
         self.obs_dtype = obs_dtype
         b = self.env
@@ -37,49 +48,97 @@ class PcgrlVectorEnv:
         self._obs = torch.empty((num_envs, *shp), dtype=obs_dtype, device=b.device)
         self.episode_return = torch.zeros(num_envs, dtype=torch.float64, device=b.device)
         self.episode_length = torch.zeros(num_envs, dtype=torch.int32, device=b.device)
+        if len(self.shards) > 1:
+            self._streams = [torch.cuda.Stream(device=b.device) for _ in self.shards]
+            self._reward = torch.zeros(num_envs, dtype=torch.float32, device=b.device)
+            self._done = torch.zeros(num_envs, dtype=torch.uint8, device=b.device)
+
+    def _on_shards(self, fn):
+        """fn(i, shard, lo, hi) for every shard on its own stream; the caller's stream waits for all of them."""
+        cur = torch.cuda.current_stream(self.env.device)
+        for i, (b, st, (lo, hi)) in enumerate(zip(self.shards, self._streams, self._ranges)):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                fn(i, b, lo, hi)
+        for st in self._streams:
+            cur.wait_stream(st)
 
     def reset(self, grids=None, pos=None):
-        if self.uniform_targets:
-            self.env.sample_uniform_targets()
-        self.env.reset(grids=grids, pos=pos)
+        if len(self.shards) == 1:
+            if self.uniform_targets:
+                self.env.sample_uniform_targets()
+            self.env.reset(grids=grids, pos=pos)
+            self.episode_return.zero_()
+            self.episode_length.zero_()
+            return self.env.observe(out=self._obs), {}
+
+        def one(i, b, lo, hi):
+            if self.uniform_targets:
+                b.sample_uniform_targets()
+            b.reset(grids=None if grids is None else grids[lo:hi], pos=None if pos is None else pos[lo:hi])
+            b.observe(out=self._obs[lo:hi])
+        self._on_shards(one)
         self.episode_return.zero_()
         self.episode_length.zero_()
-        return self.env.observe(out=self._obs), {}
+        return self._obs, {}
 
-    def step(self, actions: torch.Tensor):
-        """-> obs, reward, terminated(False), truncated(done), info; finished envs are reset in place and
-        their `obs` row is the first observation of the new episode (gymnasium autoreset semantics);
-        info carries the final stats of finished episodes.  reward / done are the env's own output tensors: a
-        reset leaves them alone (include/pcgrl_b200.h, pcgrl_reset), so they need no copies."""
-        b = self.env
+    def _step_shard(self, b, actions, lo, hi, infos):
+        """One shard's step + auto-reset + observation (on the current stream); -> (reward, done) of the shard."""
         reward, done = b.step(actions)
-        self.episode_return += reward.double()
-        self.episode_length += 1
-        info = {}
+        ret, length = self.episode_return[lo:hi], self.episode_length[lo:hi]
+        ret += reward.double()
+        length += 1
         # lock-step episodes (no change budget, every env reset together): the episode end is known on the host
         # without a device-to-host sync, and STAYS known afterwards because the reset below is a full one
         lock_step = b.max_changes is None and b._synced_steps is not None
         any_done = (b._synced_steps > b.max_iterations) if lock_step else bool(done.any())
         if any_done:
             d = done.bool()
-            info = {"final_stats": b.stats.clone(), "final_return": self.episode_return.clone(),
-                    "final_length": self.episode_length.clone(), "_final": d}
+            infos.append((lo, {"final_stats": b.stats.clone(), "final_return": ret.clone(),
+                               "final_length": length.clone(), "_final": d}))
             if lock_step:
                 if self.uniform_targets:
                     b.sample_uniform_targets()
                 b.reset()
-                self.episode_return.zero_()
-                self.episode_length.zero_()
+                ret.zero_()
+                length.zero_()
             else:
                 if self.uniform_targets:
                     keep = b.targets.clone()
                     b.sample_uniform_targets()
                     b.targets[~d] = keep[~d]
                 b.reset(mask=done)
-                self.episode_return[d] = 0
-                self.episode_length[d] = 0
-        obs = b.observe(out=self._obs)
-        return obs, reward, torch.zeros_like(done), done, info
+                ret[d] = 0
+                length[d] = 0
+        b.observe(out=self._obs[lo:hi])
+        return reward, done
+
+    def step(self, actions: torch.Tensor):
+        """-> obs, reward, terminated(False), truncated(done), info; finished envs are reset in place and
+        their `obs` row is the first observation of the new episode (gymnasium autoreset semantics);
+        info carries the final stats of finished episodes.  reward / done are the env's own output tensors: a
+        reset leaves them alone (include/pcgrl_b200.h, pcgrl_reset), so they need no copies."""
+        infos = []
+        if len(self.shards) == 1:
+            reward, done = self._step_shard(self.env, actions, 0, self.num_envs, infos)
+            return self._obs, reward, torch.zeros_like(done), done, (infos[0][1] if infos else {})
+
+        def one(i, b, lo, hi):
+            r, d = self._step_shard(b, actions[lo:hi], lo, hi, infos)
+            self._reward[lo:hi].copy_(r)
+            self._done[lo:hi].copy_(d)
+        self._on_shards(one)
+        info = {}
+        if infos:      # some shard saw an episode end: whole-batch tensors, rows of the other shards not final
+            K = self.env.K
+            info = {"final_stats": torch.zeros((self.num_envs, K), dtype=torch.int32, device=self.env.device),
+                    "final_return": torch.zeros(self.num_envs, dtype=torch.float64, device=self.env.device),
+                    "final_length": torch.zeros(self.num_envs, dtype=torch.int32, device=self.env.device),
+                    "_final": torch.zeros(self.num_envs, dtype=torch.bool, device=self.env.device)}
+            for lo, part in infos:
+                for k, v in part.items():
+                    info[k][lo:lo + v.shape[0]] = v
+        return self._obs, self._reward, torch.zeros_like(self._done), self._done, info
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -2,7 +2,7 @@
 # Build kernel variants (-D knobs) here, time each on the GPU box.
 #   local:  bash scripts/ab_variants.sh build FILE.cu "A:-DX=1" "B:-DX=0"   -> gpurun_variants/libA.so ...
 #           (FILE.cu is recompiled per variant and linked with the other objects of build/obj; a name starting with
-#            F_ / S_ / I_ / X_ is timed on the fused / split / split-incremental / fused-incremental step path)
+#            F_ / S_ / I_ / X_ / L_ is timed on the fused / split / split-incremental / fused-incremental / lane-group step path)
 #   remote: bash scripts/ab_variants.sh run [bench args]
 set -u
 cd "$(dirname "$0")/.."
@@ -21,7 +21,7 @@ else
   mkdir -p gpurun_out
   for lib in gpurun_variants/lib*.so; do
     name=$(basename $lib .so); name=${name#lib}
-    case $name in F_*) path=fused;; S_*) path=split;; I_*) path=inc;; X_*) path=incfused;; *) path=incfused;; esac
+    case $name in L_*) path=lg;; F_*) path=fused;; S_*) path=split;; I_*) path=inc;; X_*) path=incfused;; *) path=incfused;; esac
     for rep in 1 2; do
       PCGRL_STEP_PATH=$path PCGRL_B200_LIB=$PWD/$lib timeout 90 python bench.py --no-cpu-baseline --no-e2e --no-configs "$@" 2>>gpurun_out/ab.err | python -c "
 import json,sys

@@ -238,5 +238,5 @@ def test_progressive_host_pipeline_equals_device_step(rep, shape, controls, comp
         assert torch.equal(a.iteration, b.iteration) and torch.equal(a.changes, b.changes)
         assert torch.equal(a.cache, b.cache)
     a.check_status()
-    fresh = a.compute_stats(a.grids)
+    fresh = a.compute_stats(a.maps)
     assert torch.equal(fresh, a.stats)

@@ -131,3 +131,41 @@ def test_policy_input_from_tile_codes_equals_reference_permute():
         assert got.is_contiguous(memory_format=torch.channels_last)
         conv = torch.nn.Conv2d(ref.shape[1], 8, kernel_size=7, stride=2, padding=3).to(env.device)
         assert torch.allclose(conv(got), conv(ref.contiguous()), atol=1e-5)
+
+
+@pytest.mark.parametrize("problem,rep,change_pct", [("binary", "narrow", None), ("zelda", "turtle", 0.3)])
+def test_sharded_vector_env_equals_one_shard(problem, rep, change_pct):
+    """PcgrlVectorEnv(shards=k) steps and observes consecutive env ranges on their own streams (the search of one
+    range beside the observation writes of another); maps, observations, rewards, dones and the episode
+    bookkeeping must be those of the one-shard env -- resets are counter-based on the global env index, with and
+    without lock-step episodes (a change budget makes envs finish at different steps)."""
+    import control_pcgrl_b200 as P
+    from control_pcgrl_b200.vector_env import PcgrlVectorEnv
+    n = 5_003
+    kw = dict(change_percentage=change_pct) if change_pct else {}
+    cfg = P.make_config(problem, rep, max_board_scans=0.08, **kw)
+    one = PcgrlVectorEnv(cfg, n, seed=5, obs_dtype=torch.uint8)
+    many = PcgrlVectorEnv(cfg, n, seed=5, obs_dtype=torch.uint8, shards=3)
+    assert len(many.shards) == 3 and sum(b.n_envs for b in many.shards) == n
+    o1, _ = one.reset()
+    o2, _ = many.reset()
+    assert torch.equal(o1, o2)
+    n_act = one.single_action_space.n
+    gen = torch.Generator(device=o1.device).manual_seed(2)
+    ends = 0
+    for t in range(int(one.env.max_iterations * 2.3) + 5):
+        act = torch.randint(0, n_act, (n,), generator=gen, device=o1.device, dtype=torch.int32)
+        a1, r1, _, d1, i1 = one.step(act)
+        a2, r2, _, d2, i2 = many.step(act)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), t
+        assert torch.equal(a1, a2), t
+        assert torch.equal(one.episode_return, many.episode_return) and torch.equal(one.episode_length, many.episode_length)
+        assert bool(i1) == bool(i2), t
+        if i1:
+            ends += 1
+            f = i1["_final"]
+            assert torch.equal(f, i2["_final"])
+            for k in ("final_stats", "final_return", "final_length"):
+                assert torch.equal(i1[k][f], i2[k][f]), (t, k)
+    assert ends >= 2
+    assert torch.equal(torch.cat([b.maps for b in many.shards]), one.env.maps)
