@@ -345,7 +345,7 @@ def run_workload(a, workload, n_envs, steps, warmup, e2e_steps, rank, world, loc
     per_launch_ms = kern_ms / steps
     achieved = step_bytes * n_envs / (per_launch_ms * 1e-3) / 1e9
     if env.cache is not None:      # binary with the incremental search (csrc/step_split.cu), path by shard size
-        kernel = "k_split_act + k_split_stats_inc + k_split_out" if n_envs >= (160 << 10) else \
+        kernel = "k_split_act + k_split_stats_inc + k_split_out" if n_envs >= (224 << 10) else \
             "k_step_inc" if n_envs >= (24 << 10) else "k_step_lanegroup"
     elif problem in ("binary", "zelda", "binary_holey"):
         kernel = "k_step_bitboard"

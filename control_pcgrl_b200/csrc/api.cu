@@ -123,8 +123,11 @@ static int path_of(const char* e, int dflt) {
 // The lane-group kernel (step_lanegroup.cu, path 4 "lg"; kernel times, profiles/r02_lanegroup_by_size.txt): 1 Ki / 4 Ki / 16 Ki
 // envs 24.9 / 27.1 / 31.5 us against 30.8 / 32.6 / 33.7 us for incfused, 64 Ki 67.5 / 58.0 -- it takes the shards below 24 Ki envs
 // (RLlib-scale batches).
+// With its grid sized so that every CTA works and warps take two update rounds (step_split.cu, launch_split) the
+// one-launch kernel holds up to ~256 Ki envs (profiles/r02_step_inc_rounds.txt, kernel ms incfused / inc: 160 Ki 0.086 / 0.105,
+// 256 Ki 0.112-0.125 / 0.116, 384 Ki 0.166 / 0.143, 512 Ki 0.209 / 0.177): the three-launch path takes over at 224 Ki.
 static int step_path(int64_t n_envs) {
-    return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (24 << 10) ? 4 : n_envs < (160 << 10) ? 3 : 2);
+    return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (24 << 10) ? 4 : n_envs < (224 << 10) ? 3 : 2);
 }
 // Chunks of the host pipeline run on different streams.  With the search kernel of the three-launch incremental
 // path limited to 3 CTAs per SM (PCGRL_INC_CTAS_PER_SM_HOST) the memory-bound update / output kernels of the

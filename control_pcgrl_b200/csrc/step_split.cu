@@ -668,6 +668,9 @@ __device__ __noinline__ void inc_output_env(const KParams& p, int64_t env, int r
 #ifndef PCGRL_STEP_INC_MIN_CTAS
 #define PCGRL_STEP_INC_MIN_CTAS 6
 #endif
+#ifndef PCGRL_STEP_INC_ROUNDS
+#define PCGRL_STEP_INC_ROUNDS 1      // update rounds (of 32 envs) per warp the grid is sized for, see launch_split
+#endif
 template <int NW, bool TWO>
 __global__ void __launch_bounds__(STAT_THREADS, PCGRL_STEP_INC_MIN_CTAS) k_step_inc(const __grid_constant__ KParams p) {
     using M = BinaryIncMachine<NW, TWO>;
@@ -835,8 +838,22 @@ static cudaError_t launch_split(const KParams& p, cudaStream_t s, int incrementa
         if (incremental == 2) {     // the whole step in one launch (k_step_inc)
             int n_sm = 0;
             if ((e = sm_count(n_sm)) != cudaSuccess) return e;
-            const int64_t want = (n + STAT_THREADS - 1) / STAT_THREADS;
+            // envs per warp = 32 * m.  A warp's first 32 envs yield ~16 changed ones, i.e. half-empty warps for the whole
+            // search; with two update rounds per warp the ring refills and every lane gets an item.  And the grid is
+            // sized so that EVERY CTA gets work: with the plain cap (6 CTAs per SM) a 128 Ki-env shard ran 64 envs per warp
+            // on 512 of its 888 CTAs while the others exited at once.  A/B of m (profiles/r02_step_inc_rounds.txt, kernel
+            // ms, m = 1 / 2 / 3 / 4): 32 Ki envs 0.042 / 0.048 / 0.062 / 0.075, 64 Ki 0.060 / 0.056 / 0.070 / 0.077,
+            // 128 Ki 0.095 / 0.075 / 0.083 / 0.089.  PCGRL_STEP_INC_ROUNDS overrides.
+            static int rounds = -1;
+            if (rounds < 0) {
+                const char* ev = getenv("PCGRL_STEP_INC_ROUNDS");
+                rounds = ev ? atoi(ev) : 0;
+            }
             const int64_t cap = (int64_t)n_sm * inc_ctas_per_sm(p.host_chunk != 0);
+            int64_t m = rounds > 0 ? rounds : (n >= (48 << 10) ? 2 : PCGRL_STEP_INC_ROUNDS);
+            const int64_t need_m = (n + STAT_THREADS * cap - 1) / (STAT_THREADS * cap);
+            if (m < need_m) m = need_m;
+            const int64_t want = (n + STAT_THREADS * m - 1) / (STAT_THREADS * m);
             k_step_inc<NW, TWO><<<(unsigned)(want < cap ? want : cap), STAT_THREADS, 0, s>>>(p);
             return cudaGetLastError();
         }
