@@ -126,8 +126,17 @@ static int path_of(const char* e, int dflt) {
 // With its grid sized so that every CTA works and warps take two update rounds (step_split.cu, launch_split) the
 // one-launch kernel holds up to ~256 Ki envs (profiles/r02_step_inc_rounds.txt, kernel ms incfused / inc: 160 Ki 0.086 / 0.105,
 // 256 Ki 0.112-0.125 / 0.116, 384 Ki 0.166 / 0.143, 512 Ki 0.209 / 0.177): the three-launch path takes over at 224 Ki.
-static int step_path(int64_t n_envs) {
-    return path_of(getenv("PCGRL_STEP_PATH"), n_envs < (24 << 10) ? 4 : n_envs < (224 << 10) ? 3 : 2);
+// zelda's searches are short (7x11 maps, three small BFS): the one-launch fused kernel beats the three-launch split path
+// at every size (profiles/r02_zelda_paths.txt, kernel ms fused / split: 64 Ki envs 0.037 / 0.041, 256 Ki 0.058 / 0.075,
+// 1 Mi 0.175 / 0.201), so zelda only takes the split path when PCGRL_STEP_PATH asks for it.
+// The problems without a search cache (binary_holey, binary maps of 17..32 rows) run the from-scratch machines either
+// way: fused below 128 Ki envs, the split path (full warps from a global list) above (profiles/r02_zelda_paths.txt:
+// binary 24x24 64 Ki envs 0.207 / 0.227 ms fused / split, 512 Ki 1.019 / 0.943; binary_holey 64 Ki 0.087 / 0.086, 1 Mi 0.820 / 0.580).
+static int step_path(int64_t n_envs, int problem, bool has_cache) {
+    const int dflt = problem == PCGRL_PROB_ZELDA ? 0
+                   : !has_cache ? (n_envs < (128 << 10) ? 0 : 1)
+                   : n_envs < (24 << 10) ? 4 : n_envs < (224 << 10) ? 3 : 2;
+    return path_of(getenv("PCGRL_STEP_PATH"), dflt);
 }
 // Chunks of the host pipeline run on different streams.  With the search kernel of the three-launch incremental
 // path limited to 3 CTAs per SM (PCGRL_INC_CTAS_PER_SM_HOST) the memory-bound update / output kernels of the
@@ -233,7 +242,7 @@ static int run(const KParams& p, int cfg_problem, void* stream, int force_path =
     else if (problem == PCGRL_PROB_SMB)
         e = launch_smb(p, (cudaStream_t)stream, supported, multi);   // map statistics + lane-group playthroughs + fallback
     else {
-        int path = force_path >= 0 ? force_path : step_path(p.n_envs);
+        int path = force_path >= 0 ? force_path : step_path(p.n_envs, problem, p.cache != nullptr);
         if (p.mode == MODE_STEP && path == 4) {   // lane groups (step_lanegroup.cu): small binary shards with a search cache
             if (p.cache) {
                 e = launch_bitboard_lanegroup(p, problem, (cudaStream_t)stream, supported);

@@ -18,8 +18,10 @@
 //               per-component computation; components the edit does not touch keep their first tile, far tile
 //               and eccentricity).  Work per item is uneven (0..135 expansions), so lanes claim items one by one
 //               from their warp's slice of the list instead of running in batches.
-//   k_split_out    thread-per-changed-env: fp64 loss(new) - loss(old), stats / reward / packed record; the last CTA
-//                  re-arms the list header for the next step.
+//   k_split_out    thread-per-changed-env: fp64 loss(new) - loss(old), stats / reward / packed record; the list is
+//                  handed from step to step through ping-pong counters (see the header layout below).
+//   k_step_inc     all three in ONE launch for mid-size shards; k_split_stats_inc_multi / k_wait_list: the progressive
+//                  host pipeline (measured, off by default).  step_lanegroup.cu holds the small-shard kernel.
 //
 // Reference path replaced: the same as step_bitboard.cu (envs/pcgrl_env.py:267-342, envs/reps/*_rep.py,
 // envs/probs/binary/binary_prob.py:152-158, envs/probs/zelda/zelda_ctrl_prob.py:90-168, envs/helper.py:200-276,
