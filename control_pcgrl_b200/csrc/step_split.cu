@@ -54,6 +54,9 @@ namespace pcgrl {
 #define PCGRL_INC_MIN_CLAIM 12       // lanes that must be waiting before a warp hands out new items: the claim / init
                                      // stream then runs with that many lanes (A/B 1 / 4 / 8 at R=3: 0.412 / 0.390 / 0.387)
 #endif
+#ifndef PCGRL_INC_DYNAMIC
+#define PCGRL_INC_DYNAMIC 0          // > 0: items per fetch from the global list counter (see k_split_stats_inc); 0: static slices
+#endif
 #ifndef PCGRL_INC_EXPAND_R
 #define PCGRL_INC_EXPAND_R 12        // board expansions per trip.  Every trip also issues each transition stream that
                                      // some lane needs (flood done / next component / second sweep / re-sweep / finish,
@@ -463,12 +466,24 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
     __shared__ uint32_t s_work[STAT_THREADS * M::SMEM_WORDS];
     const int tid = threadIdx.x, lane = tid & 31;
     const int count = wl_count_search(p);
+#if PCGRL_INC_DYNAMIC > 0
+    // Dynamic distribution: a warp fetches the next PCGRL_INC_DYNAMIC items of the list from a global counter (header
+    // words 6 / 7, alternating with the step parity like the item counters; block 0 clears the one the NEXT step uses)
+    // whenever its lanes need items.  With static slices of ~110 items whose cost varies 0..135 expansions each, the
+    // slowest of the 4 736 warps carries ~25 % more work than the average one and the kernel ends with a thin tail.
+    const int par = wl_parity(p);
+    int* ctr = p.wl_hdr + 6 + par;
+    if (blockIdx.x == 0 && tid == 0) p.wl_hdr[6 + (par ^ 1)] = 0;
+    int lo = 0, hi = 0;
+    bool drained = count == 0, last_batch = false;
+#else
     const int n_warps = gridDim.x * (STAT_THREADS / 32);
     const int gw = blockIdx.x * (STAT_THREADS / 32) + (tid >> 5);
     const int per = (count + n_warps - 1) / n_warps;
     int lo = min(count, gw * per);
     const int hi = min(count, lo + per);
     if (lo >= hi) return;
+#endif
     const int2* items = wl_items(p);
     int32_t* stats_out = wl_stats(p);
     const int W = p.d1;
@@ -477,8 +492,27 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
     int item = 0;
     int64_t env = 0;
     for (;;) {
-        const unsigned need = __ballot_sync(0xffffffffu, !active);
+        unsigned need = __ballot_sync(0xffffffffu, !active);
+#if PCGRL_INC_DYNAMIC > 0
+        // up to two rounds per trip: lanes left over when a batch runs out take theirs from the next one at once
+        for (int round = 0; round < 2 && need; ++round) {
+            if (!(round || __popc(need) >= PCGRL_INC_MIN_CLAIM || need == 0xffffffffu || (last_batch && lo < hi))) break;
+            if (lo >= hi) {
+                if (drained) break;
+                int b = 0;
+                if (lane == 0) b = atomicAdd(ctr, PCGRL_INC_DYNAMIC);
+                b = __shfl_sync(0xffffffffu, b, 0);
+                lo = min(count, b);
+                hi = min(count, b + PCGRL_INC_DYNAMIC);
+                last_batch = b + PCGRL_INC_DYNAMIC >= count;      // the counter is past the end: nothing after this batch
+                if (lo >= hi) {
+                    drained = true;
+                    break;
+                }
+            }
+#else
         if (need && lo < hi && (__popc(need) >= PCGRL_INC_MIN_CLAIM || need == 0xffffffffu || hi - lo < PCGRL_INC_MIN_CLAIM)) {
+#endif
             const int mine = lo + __popc(need & ((1u << lane) - 1u));
             if (!active && mine < hi) {
                 item = mine;
@@ -492,9 +526,20 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
                 alive = true;
             }
             lo = min(hi, lo + __popc(need));
+#if PCGRL_INC_DYNAMIC > 0
+            if (lo < hi) break;                                    // the batch served every idle lane
+            need = __ballot_sync(0xffffffffu, !active);
+#endif
         }
         const unsigned act = __ballot_sync(0xffffffffu, active);
+#if PCGRL_INC_DYNAMIC > 0
+        if (!act) {
+            if (drained) break;
+            continue;          // every lane is idle: the next trip fetches a batch
+        }
+#else
         if (!act) break;
+#endif
 #if PCGRL_INC_THETA > 0
         const int want = max(1, (__popc(act) * PCGRL_INC_THETA) >> 5);
         for (;;) {
