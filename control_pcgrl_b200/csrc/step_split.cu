@@ -55,7 +55,10 @@ namespace pcgrl {
                                      // stream then runs with that many lanes (A/B 1 / 4 / 8 at R=3: 0.412 / 0.390 / 0.387)
 #endif
 #ifndef PCGRL_INC_DYNAMIC
-#define PCGRL_INC_DYNAMIC 0          // > 0: items per fetch from the global list counter (see k_split_stats_inc); 0: static slices
+#define PCGRL_INC_DYNAMIC 0          // > 0: items per fetch from the global list counter (see k_split_stats_inc); 0: static slices.
+                                     // A/B static / 16 / 32 / 64 (400 steps, 1 Mi envs, profiles/r02_ab_inc_dynamic.txt): 0.300-0.304 /
+                                     // 0.304 / 0.295 / 0.313 ms per step; as the default (32) the 800-step bench line did not move
+                                     // (0.2909 against 0.2913 ms) and e2e fell 2.60 -> 2.51e9: the tail is not where the time goes.  Off.
 #endif
 #ifndef PCGRL_INC_EXPAND_R
 #define PCGRL_INC_EXPAND_R 12        // board expansions per trip.  Every trip also issues each transition stream that
@@ -89,7 +92,8 @@ constexpr int OUT_THREADS = 256;
 // stats per item.  The headers of all pipeline chunks live together at the front of pcgrl_state.worklist, where no
 // body ever lands, so they stay zero whatever chunking the previous step used.
 // Header (all zero before the first step): [0], [1] item counters used alternately, [3] the step count, whose parity
-// picks the counter, [4] the step's final item count.  k_split_act adds to counter [par]; the search kernel clears
+// picks the counter, [4] the step's final item count, [5] search warps that reported the list (progressive host
+// pipeline), [6], [7] fetch counters of the dynamic distribution, alternating like [0], [1].  k_split_act adds to counter [par]; the search kernel clears
 // counter [par ^ 1] for the next step and publishes the count in [4]; k_split_out reads [4] and bumps [3] -- every
 // word is written by exactly one thread of a kernel none of whose CTAs reads it, so the three launches need no
 // "last CTA out" atomics or fences to hand the list over.
@@ -99,6 +103,7 @@ __device__ __forceinline__ int wl_count_search(const KParams& p) {
     const int count = *(volatile const int*)(p.wl_hdr + par);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.wl_hdr[par ^ 1] = 0;
+        p.wl_hdr[6 + (par ^ 1)] = 0;    // the next step's fetch counter (k_split_stats_inc, dynamic distribution)
         p.wl_hdr[4] = count;
     }
     return count;
@@ -471,9 +476,7 @@ __global__ void __launch_bounds__(STAT_THREADS) k_split_stats_inc(const KParams 
     // words 6 / 7, alternating with the step parity like the item counters; block 0 clears the one the NEXT step uses)
     // whenever its lanes need items.  With static slices of ~110 items whose cost varies 0..135 expansions each, the
     // slowest of the 4 736 warps carries ~25 % more work than the average one and the kernel ends with a thin tail.
-    const int par = wl_parity(p);
-    int* ctr = p.wl_hdr + 6 + par;
-    if (blockIdx.x == 0 && tid == 0) p.wl_hdr[6 + (par ^ 1)] = 0;
+    int* ctr = p.wl_hdr + 6 + wl_parity(p);     // (wl_count_search cleared it one step ago, whichever split kernel ran)
     int lo = 0, hi = 0;
     bool drained = count == 0, last_batch = false;
 #else
@@ -600,6 +603,7 @@ __global__ void __launch_bounds__(STAT_THREADS, NW >= 8 ? PCGRL_PROG_CTAS_PER_SM
         const int par = *(volatile const int*)(hdr + 3) & 1;
         hdr[4] = *(volatile const int*)(hdr + par);
         hdr[par ^ 1] = 0;
+        hdr[6 + (par ^ 1)] = 0;
     }
     const int W = p.d1;
     int cl = -1, lo = 0, hi = 0, sig = 0;                  // warp-uniform: list being claimed from, slice, next list to report

@@ -240,3 +240,27 @@ def test_progressive_host_pipeline_equals_device_step(rep, shape, controls, comp
     a.check_status()
     fresh = a.compute_stats(a.maps)
     assert torch.equal(fresh, a.stats)
+
+
+def test_one_shard_may_alternate_between_all_step_paths(monkeypatch):
+    """The split paths hand their work list from step to step through alternating header words (item counters, the
+    dynamic search's fetch counters); a shard that switches path from step to step -- three-launch incremental,
+    three-launch from scratch, one-launch, lane groups, fused -- must keep giving the fused kernel's results, and the
+    incremental cache must survive the steps that do not use it."""
+    n = 40_000
+    a, b = _envs("binary", "narrow", (16, 16), n, ["inc", "fused"], max_board_scans=0.05)
+    a.reset()
+    b.reset()
+    gen = torch.Generator(device=a.device).manual_seed(4)
+    order = ["inc", "split", "inc", "inc", "split", "split", "inc", "incfused", "inc", "lg", "inc", "fused", "inc", "split"]
+    for t in range(3 * len(order) + int(a.max_iterations) + 2):
+        act = torch.randint(0, 2, (n,), generator=gen, device=a.device, dtype=torch.int32)
+        monkeypatch.setenv("PCGRL_STEP_PATH", order[t % len(order)])
+        ra, da = a.step(act)
+        ra, da = ra.clone(), da.clone()
+        monkeypatch.setenv("PCGRL_STEP_PATH", "fused")
+        rb, db = b.step(act)
+        assert torch.equal(ra, rb) and torch.equal(da, db), (t, order[t % len(order)])
+        assert torch.equal(a.stats, b.stats) and torch.equal(a.grids, b.grids), (t, order[t % len(order)])
+    assert torch.equal(a.compute_stats(a.maps), a.stats)
+    a.check_status()
