@@ -52,7 +52,8 @@ namespace pcgrl {
 #endif
 #ifndef PCGRL_INC_MIN_CLAIM
 #define PCGRL_INC_MIN_CLAIM 12       // lanes that must be waiting before a warp hands out new items: the claim / init
-                                     // stream then runs with that many lanes (A/B 1 / 4 / 8 at R=3: 0.412 / 0.390 / 0.387)
+                                     // stream then runs with that many lanes (A/B 1 / 4 / 8 at R=3: 0.412 / 0.390 / 0.387; at
+                                     // R=12, 8 / 12 / 16 / 24: 0.2978 / 0.2996 / 0.3022 / 0.3263 ms, profiles/r02_ab_inc_claim_window.txt)
 #endif
 #ifndef PCGRL_INC_DYNAMIC
 #define PCGRL_INC_DYNAMIC 0          // > 0: items per fetch from the global list counter (see k_split_stats_inc); 0: static slices.
@@ -65,7 +66,8 @@ namespace pcgrl {
                                      // some lane needs (flood done / next component / second sweep / re-sweep / finish,
                                      // ~580 instructions at 2-3 lanes), so few long trips beat many short ones although
                                      // lanes idle inside the window: A/B 2 / 3 / 4 / 6 / 8 / 12 -> 0.466 / 0.412 / 0.356 /
-                                     // 0.325 / 0.308 / 0.303 ms per step (1 Mi envs, 8 CTAs per SM)
+                                     // 0.325 / 0.308 / 0.303 ms per step (1 Mi envs, 8 CTAs per SM); 16 / 20 -> 0.3018 / 0.3140
+                                     // against 0.2996 for 12 in a later run
 #endif
 #ifndef PCGRL_CONVERGE
 #define PCGRL_CONVERGE 1             // 1: every lane of a warp starts every search trip together (vote at the loop head)
