@@ -161,7 +161,7 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, uint32_t d, uint32_t magic,
 constexpr int OBS_MAX_CTA_ENVS = 64;   // GB * G
 constexpr int OBS_THREADS = 256;
 
-template <typename T, bool CROP, bool STATIC, bool D3, int ROWN /* 0, or 4 / 8: pixels per thread, all in one image row */>
+template <typename T, bool CROP, bool STATIC, bool D3, int ROWN /* 0, or 4 / 8 / 32: pixels per thread, all in one image row */>
 __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams p, const ObsVec v) {
     extern __shared__ __align__(16) uint8_t obs_smem[];
     T* stage = (T*)obs_smem;                                         // [envs of the trip][pix][n_ch]
@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
     const int n_pl = 2 * p.n_ctrl;
     // u8 one-hot records of 3 channels (binary behind a crop: the headline observation): 8 pixels are 24 bytes, built
     // in registers and stored as three 64-bit words -- no zero fill, no byte stores
-    const bool pack3 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 3 && !p.raw && n_pl == 0;
+    constexpr bool R8 = ROWN == 8 || ROWN == 32;
+    const bool pack3 = sizeof(T) == 1 && R8 && !STATIC && v.n_ch == 3 && !p.raw && n_pl == 0;
     // uint8 tile codes (one byte per pixel): 8 pixels are one 64-bit word
-    const bool pack1 = sizeof(T) == 1 && ROWN == 8 && !STATIC && v.n_ch == 1 && p.raw && n_pl == 0;
+    const bool pack1 = sizeof(T) == 1 && R8 && !STATIC && v.n_ch == 1 && p.raw && n_pl == 0;
     // Two-tile maps behind a crop (binary: the headline observation).  75 % of a 32x32 window on a 16x16 map is
     // padding, and the in-map / padding split of a warp's pixel groups made every warp run both record builders
     // (157 instructions per 24-byte group, issue-bound at 0.63 of the HBM peak).  Instead: the trip's map rows are
@@ -296,7 +297,38 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe_staged(const ObsParams 
                 // which of the 8 pixels lie inside the map: most of a crop is padding (a 32x32 window on a 16x16 map
                 // is 75 % out of bounds), and such pixels need no grid load -- a whole group outside is a constant
                 const bool none_in = !row_ok || (CROP && (sl + 7 < 0 || sl >= dl));
-                if (sizeof(T) == 1 && ROWN == 8 && bits) {
+                if (sizeof(T) == 1 && ROWN == 32 && bits) {
+                    // A whole 32-pixel window row per thread (q1 == 0): the index math above is paid once per 32 pixels
+                    // instead of once per 8 (the 1-byte tile codes ran at 6 instructions per output byte), the row's 32
+                    // tile bits and 32 inside bits are two funnel shifts, eight table lookups give the records of four
+                    // pixels each, and the row leaves as 128-bit stores.
+                    const uint32_t rb = row_ok ? (uint32_t)s_rowbits[el * p.d0 + c0 + (int)q0] : 0u;
+                    const uint32_t inr = row_ok ? ((1u << p.d1) - 1u) : 0u;
+                    const uint32_t t32 = __funnelshift_rc(rb << 16, 0u, (uint32_t)(sl + 16));     // bit k = map column sl + k
+                    const uint32_t in32 = __funnelshift_rc(inr << 16, 0u, (uint32_t)(sl + 16));
+                    uint4* o16 = (uint4*)o;
+                    if (pack3) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {      // 16 pixels = 48 bytes = three 128-bit stores
+                            uint4 r[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int sh = 16 * h + 4 * j;
+                                r[j] = s_lut3[(((in32 >> sh) & 0xFu) << 4) | ((t32 >> sh) & 0xFu)];
+                            }
+                            o16[3 * h + 0] = make_uint4(r[0].x, r[0].y, r[0].z, r[1].x);
+                            o16[3 * h + 1] = make_uint4(r[1].y, r[1].z, r[2].x, r[2].y);
+                            o16[3 * h + 2] = make_uint4(r[2].z, r[3].x, r[3].y, r[3].z);
+                        }
+                    } else {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            w[j] = s_lut1[(((in32 >> (4 * j)) & 0xFu) << 4) | ((t32 >> (4 * j)) & 0xFu)];
+                        o16[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        o16[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                } else if (sizeof(T) == 1 && ROWN == 8 && bits) {
                     // sl + 16 >= 0 (the window is at most 32 wide): bit k of the shifted row is map column sl + k
                     const uint32_t rb = row_ok ? (uint32_t)s_rowbits[el * p.d0 + c0 + (int)q0] : 0u;
                     const uint32_t inr = row_ok ? ((1u << p.d1) - 1u) : 0u;
@@ -502,6 +534,11 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
         : (d3 ? k_observe_staged<T, false, false, true, RN> : k_observe_staged<T, false, false, false, RN>))
     void (*kern)(const ObsParams, const ObsVec) = rown == 8 ? OBS_PICK(8) : (rown == 4 ? OBS_PICK(4) : OBS_PICK(0));
 #undef OBS_PICK
+    // row-mask crops whose window is exactly 32 wide (binary 16x16 behind its 32x32 crop): a whole window row per thread
+    if constexpr (sizeof(T) == 1) {
+        if (v.bits && rown == 8 && p.o1 == 32 && !d3 && !st && cr && !getenv("PCGRL_OBSERVE_NO_ROW32"))
+            kern = k_observe_staged<T, true, false, false, 32>;
+    }
     cudaError_t e;
     if (dyn > 48 * 1024 &&
         (e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn)) != cudaSuccess)

@@ -21,7 +21,7 @@ class PcgrlVectorEnv:
     (scripts/bench_rl_loop.py).  Outputs are the same [N, ...] tensors either way."""
 
     def __init__(self, cfg, num_envs: int, device="cuda:0", obs_dtype=torch.float32, env_offset=0, seed=0,
-                 uniform_targets: bool | None = None, shards: int = 1):
+                 uniform_targets: bool | None = None, shards: int = 1, onehot: bool = True):
         shards = max(1, min(int(shards), num_envs))
         per = -(-num_envs // shards)
         self._ranges = [(lo, min(num_envs, lo + per)) for lo in range(0, num_envs, per)]
@@ -29,13 +29,18 @@ class PcgrlVectorEnv:
                        for lo, hi in self._ranges]
         self.env = self.shards[0]          # metadata (spaces, names, bounds); the only shard when shards == 1
         self.num_envs = num_envs
+        # onehot=False: observations are the crop's tile codes, one uint8 per pixel (Cropped's own output, a third of
+        # the one-hot bytes); control_pcgrl_b200.policy_input.conv_input_from_codes expands them inside the policy
+        self.onehot = bool(onehot)
+        if not self.onehot:
+            obs_dtype = torch.uint8
         self.obs_dtype = obs_dtype
         b = self.env
         if b.ctrl_metrics and obs_dtype == torch.uint8:
             raise ValueError("target channels are fractional: use a float obs_dtype with controls")
         self.uniform_targets = bool(b.ctrl_metrics) if uniform_targets is None else uniform_targets
-        shp = b.obs_shape()
-        self.single_observation_space = spaces.Box(0, 1, shape=shp, dtype=np.float32)
+        shp = b.obs_shape(self.onehot)
+        self.single_observation_space = spaces.Box(0, 1 if self.onehot else b.n_tiles + 1, shape=shp, dtype=np.float32)
         rep = b.representation
         if rep == "narrow":
             self.single_action_space = spaces.Discrete(b.n_tiles)
@@ -70,13 +75,13 @@ class PcgrlVectorEnv:
             self.env.reset(grids=grids, pos=pos)
             self.episode_return.zero_()
             self.episode_length.zero_()
-            return self.env.observe(out=self._obs), {}
+            return self.env.observe(out=self._obs, onehot=self.onehot), {}
 
         def one(i, b, lo, hi):
             if self.uniform_targets:
                 b.sample_uniform_targets()
             b.reset(grids=None if grids is None else grids[lo:hi], pos=None if pos is None else pos[lo:hi])
-            b.observe(out=self._obs[lo:hi])
+            b.observe(out=self._obs[lo:hi], onehot=self.onehot)
         self._on_shards(one)
         self.episode_return.zero_()
         self.episode_length.zero_()
@@ -110,7 +115,7 @@ class PcgrlVectorEnv:
                 b.reset(mask=done)
                 ret[d] = 0
                 length[d] = 0
-        b.observe(out=self._obs[lo:hi])
+        b.observe(out=self._obs[lo:hi], onehot=self.onehot)
         return reward, done
 
     def step(self, actions: torch.Tensor):

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Device-time the RL-side loop: PcgrlVectorEnv.step (fused env step + auto-reset) + the observation of every env,
 every step, all on the GPU (what a policy that lives on the same device consumes).
-    python scripts/bench_rl_loop.py [--envs N] [--steps K] [--obs uint8 float32] [--shards 1 2 4]"""
+    python scripts/bench_rl_loop.py [--envs N] [--steps K] [--obs uint8 float32 codes] [--shards 1 2 4]"""
 import argparse
 import json
 import os
@@ -20,10 +20,12 @@ ap.add_argument("--envs", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=1600)
 ap.add_argument("--shards", type=int, nargs="+", default=[1, 2],
                 help="env ranges stepped + observed on their own streams (PcgrlVectorEnv(shards=k)); one line per value")
-ap.add_argument("--obs", nargs="+", default=["uint8", "float32"])
+ap.add_argument("--obs", nargs="+", default=["uint8", "float32", "codes"],
+                help="uint8 / float32: one-hot crops; codes: the crop's tile codes, 1 byte per pixel (PcgrlVectorEnv(onehot=False))")
 a = ap.parse_args()
 for obs, shards in [(o, k) for o in a.obs for k in a.shards]:
-    env = PcgrlVectorEnv(P.make_config("binary", "narrow"), a.envs, obs_dtype=getattr(torch, obs), shards=shards)
+    env = PcgrlVectorEnv(P.make_config("binary", "narrow"), a.envs, shards=shards, onehot=obs != "codes",
+                         obs_dtype=torch.uint8 if obs == "codes" else getattr(torch, obs))
     env.reset()
     acts = torch.randint(0, 2, (a.steps + 5, a.envs), device=env.env.device, dtype=torch.int32)
     for t in range(5):

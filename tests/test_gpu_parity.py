@@ -591,3 +591,26 @@ def test_tile_code_observation_is_the_argmax_of_the_onehot(problem, rep, shape, 
         monkeypatch.setenv("PCGRL_OBSERVE_SCALAR", "1")
         assert torch.equal(env.observe(onehot=False), raw)
         monkeypatch.delenv("PCGRL_OBSERVE_SCALAR", raising=False)
+
+
+@pytest.mark.parametrize("shape,obs", [((16, 16), (32, 32)), ((10, 16), (20, 32)), ((5, 12), (10, 32)), ((16, 9), (32, 32))])
+def test_row_per_thread_observation_writer(shape, obs, monkeypatch):
+    """Two-tile crops whose window is exactly 32 wide take the 32-pixels-per-thread path of the staged writer (a whole
+    window row from two funnel shifts and eight table lookups): uint8 one-hot and tile codes must equal the float
+    writer's output (which shares none of that code) and the 8-pixel path, for positions all over the map, ragged last
+    trips included."""
+    for n in (5, 333, 4099):
+        env = _mk("binary", "narrow", shape, n, obs_window=obs, seed=n)
+        env.reset()
+        for i, d in enumerate(shape):
+            env.pos[:, i] = torch.randint(0, d, (n,), device=env.device, dtype=torch.int32)
+        env.pos[0, 0], env.pos[0, 1] = 0, 0
+        env.pos[1, 0], env.pos[1, 1] = shape[0] - 1, shape[1] - 1
+        want = env.observe(dtype=torch.float32)
+        u8 = env.observe(dtype=torch.uint8)
+        codes = env.observe(onehot=False)
+        assert torch.equal(u8.float(), want)
+        assert torch.equal(codes[..., 0].long(), want.argmax(dim=-1))
+        monkeypatch.setenv("PCGRL_OBSERVE_NO_ROW32", "1")
+        assert torch.equal(env.observe(dtype=torch.uint8), u8) and torch.equal(env.observe(onehot=False), codes)
+        monkeypatch.delenv("PCGRL_OBSERVE_NO_ROW32", raising=False)

@@ -169,3 +169,25 @@ def test_sharded_vector_env_equals_one_shard(problem, rep, change_pct):
                 assert torch.equal(i1[k][f], i2[k][f]), (t, k)
     assert ends >= 2
     assert torch.equal(torch.cat([b.maps for b in many.shards]), one.env.maps)
+
+
+def test_vector_env_tile_code_observations():
+    """PcgrlVectorEnv(onehot=False) hands out the crop's tile codes (1 byte per pixel); expanded by
+    policy_input.conv_input_from_codes they are the one-hot observation of the same env, step by step."""
+    import control_pcgrl_b200 as P
+    from control_pcgrl_b200.policy_input import conv_input_from_codes
+    from control_pcgrl_b200.vector_env import PcgrlVectorEnv
+    n = 777
+    cfg = P.make_config("zelda", "turtle", max_board_scans=0.1)
+    hot = PcgrlVectorEnv(cfg, n, seed=3, obs_dtype=torch.float32)
+    codes = PcgrlVectorEnv(cfg, n, seed=3, onehot=False, shards=2)
+    o1, _ = hot.reset()
+    o2, _ = codes.reset()
+    assert o2.dtype == torch.uint8 and tuple(o2.shape) == (n, *hot.env.obs_window, 1)
+    gen = torch.Generator(device=o1.device).manual_seed(0)
+    for t in range(40):
+        assert torch.equal(conv_input_from_codes(o2, hot.env.n_tiles + 1), o1.permute(0, 3, 1, 2)), t
+        act = torch.randint(0, hot.single_action_space.n, (n,), generator=gen, device=o1.device, dtype=torch.int32)
+        o1, r1, _, d1, _ = hot.step(act)
+        o2, r2, _, d2, _ = codes.step(act)
+        assert torch.equal(r1, r2) and torch.equal(d1, d2), t
