@@ -1,14 +1,16 @@
 // Lane-group env step for SMALL binary shards: NW lanes per level grid, one board word (two 16-cell rows) per lane.
 //
 // The thread-per-grid kernels (step_bitboard.cu, step_split.cu) keep a whole 16x16 board in one thread's registers:
-// ~50 dependent instructions per BFS level, ~35 levels and a handful of transitions per changed grid.  On a big shard
-// that is what fills the integer pipes; on a small one (RLlib-scale batches up to ~256 Ki envs, BASELINE config 2's
-// 65 536 envs) the GPU is far from full and the step takes as long as ONE thread needs for its longest grid:
-// 58 us for 64 Ki envs whatever the kernel ("small shards are latency-bound").  Here a grid's board is spread
-// over NW lanes (NW = rows / 2: 8 lanes for 16x16), so a BFS level is ~14 instructions per lane -- x+-1 inside the
-// word, y+-1 inside the word as a 16-bit rotate, y+-1 across words as two width-NW shuffles -- and the frontier test
-// one ballot; component bookkeeping (lowest cell, popcount sums) is a ballot / REDUX over the group.  The dependent
-// chain per grid is ~3.5x shorter and eight times as many lanes have work.
+// ~50 instructions per BFS level, ~35 levels and a handful of transitions per changed grid.  On a big shard that is
+// what fills the integer pipes; a small shard (RLlib-scale batches) leaves the GPU far from full and its step lasts as
+// long as the dependent chain of its WORST grid (~200 levels over the flood and the sweeps of a map with long
+// corridors).  Here a grid's board is spread over NW lanes (NW = rows / 2: 8 lanes for 16x16), so a BFS level is ~14
+// instructions per lane -- x+-1 inside the word, y+-1 inside the word as a 16-bit rotate, y+-1 across words as two
+// width-NW shuffles -- and component bookkeeping (lowest cell, popcount sums, frontier tests) is a ballot / butterfly
+// over the group.  Measured (profiles/r02_lanegroup_by_size.txt, profiles/r02_small_shard_ncu_summary.txt): a level
+// costs a shuffle round trip (~55 cycles) instead of ~120-200 cycles of one thread's ALU chain; kernel time 24.9 / 27.1 /
+// 31.5 us against 30.8 / 32.6 / 33.7 us for k_step_inc at 1 Ki / 4 Ki / 16 Ki envs, and a loss from 64 Ki envs on (4 grids
+// per warp-instruction against 11-14), so pcgrl_step takes this kernel below 24 Ki envs only (api.cu, step_path()).
 //
 // One warp steps a tile of T consecutive envs (T = 8, 16 or 32, chosen so that the grid still fills the GPU):
 //   update   thread-per-env representation update, counters, done (as k_split_act); ballot of the changed envs
