@@ -121,7 +121,8 @@ class PcgrlVectorEnv:
     def step(self, actions: torch.Tensor):
         """-> obs, reward, terminated(False), truncated(done), info; finished envs are reset in place and
         their `obs` row is the first observation of the new episode (gymnasium autoreset semantics);
-        info carries the final stats of finished episodes.  reward / done are the env's own output tensors: a
+        info carries the final stats of finished episodes (rows where info["_final"] is set; with shards > 1 the
+        rows of ranges that saw no episode end are zero).  reward / done are the env's own output tensors: a
         reset leaves them alone (include/pcgrl_b200.h, pcgrl_reset), so they need no copies."""
         infos = []
         if len(self.shards) == 1:
