@@ -534,6 +534,16 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
         : (d3 ? k_observe_staged<T, false, false, true, RN> : k_observe_staged<T, false, false, false, RN>))
     void (*kern)(const ObsParams, const ObsVec) = rown == 8 ? OBS_PICK(8) : (rown == 4 ? OBS_PICK(4) : OBS_PICK(0));
 #undef OBS_PICK
+    // u8 windows 22 wide (zelda 7x11 behind its 22x22 crop: neither a multiple of 8 nor of 4, so it ran the 4-pixel path
+    // with carries): half a window row (11 pixels) or a whole one per thread.  PCGRL_OBSERVE_ROW22 = 0 / 11 / 22 (A/B).
+    if constexpr (sizeof(T) == 1) {
+        if (rown == 0 && p.o1 == 22 && !d3 && !st && cr && !p.holes) {
+            const char* e22 = getenv("PCGRL_OBSERVE_ROW22");
+            const int r22 = e22 ? atoi(e22) : 11;
+            if (r22 == 11) kern = k_observe_staged<T, true, false, false, 11>;
+            if (r22 == 22) kern = k_observe_staged<T, true, false, false, 22>;
+        }
+    }
     // row-mask crops whose window is exactly 32 wide (binary 16x16 behind its 32x32 crop): a whole window row per thread
     if constexpr (sizeof(T) == 1) {
         if (v.bits && rown == 8 && p.o1 == 32 && !d3 && !st && cr && !getenv("PCGRL_OBSERVE_NO_ROW32"))

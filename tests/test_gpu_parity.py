@@ -614,3 +614,22 @@ def test_row_per_thread_observation_writer(shape, obs, monkeypatch):
         monkeypatch.setenv("PCGRL_OBSERVE_NO_ROW32", "1")
         assert torch.equal(env.observe(dtype=torch.uint8), u8) and torch.equal(env.observe(onehot=False), codes)
         monkeypatch.delenv("PCGRL_OBSERVE_NO_ROW32", raising=False)
+
+
+def test_zelda_u8_observation_rows_per_thread(monkeypatch):
+    """zelda's 22-wide window takes 11 pixels (half a window row) per thread in the staged u8 writer; it must equal the
+    float writer and the 4-pixel path, with control planes absent / present and positions all over the map."""
+    for n in (3, 1000):
+        env = _mk("zelda", "turtle", (7, 11), n, obs_window=(22, 22), seed=n)
+        env.reset()
+        for i, d in enumerate((7, 11)):
+            env.pos[:, i] = torch.randint(0, d, (n,), device=env.device, dtype=torch.int32)
+        want = env.observe(dtype=torch.float32)
+        got = {}
+        for mode in ("11", "22", "0"):
+            monkeypatch.setenv("PCGRL_OBSERVE_ROW22", mode)
+            got[mode] = env.observe(dtype=torch.uint8)
+            assert torch.equal(got[mode].float(), want), mode
+            codes = env.observe(onehot=False)
+            assert torch.equal(codes[..., 0].long(), want.argmax(dim=-1)), mode
+        monkeypatch.delenv("PCGRL_OBSERVE_ROW22", raising=False)
