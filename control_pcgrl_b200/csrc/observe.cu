@@ -544,6 +544,15 @@ static cudaError_t launch_vec(const ObsParams& p, cudaStream_t s, bool& done) {
             if (r22 == 22) kern = k_observe_staged<T, true, false, false, 22>;
         }
     }
+    // ... and for the 3D maze's 14-wide last axis (14^3 window of a 14^3 level): PCGRL_OBSERVE_ROW14 = 0 / 7 / 14 (A/B)
+    if constexpr (sizeof(T) == 1) {
+        if (rown == 0 && d3 && p.o2 == 14 && !st && cr && !p.holes) {
+            const char* e14 = getenv("PCGRL_OBSERVE_ROW14");
+            const int r14 = e14 ? atoi(e14) : 7;
+            if (r14 == 7) kern = k_observe_staged<T, true, false, true, 7>;
+            if (r14 == 14) kern = k_observe_staged<T, true, false, true, 14>;
+        }
+    }
     // row-mask crops whose window is exactly 32 wide (binary 16x16 behind its 32x32 crop): a whole window row per thread
     if constexpr (sizeof(T) == 1) {
         if (v.bits && rown == 8 && p.o1 == 32 && !d3 && !st && cr && !getenv("PCGRL_OBSERVE_NO_ROW32"))

@@ -633,3 +633,19 @@ def test_zelda_u8_observation_rows_per_thread(monkeypatch):
             codes = env.observe(onehot=False)
             assert torch.equal(codes[..., 0].long(), want.argmax(dim=-1)), mode
         monkeypatch.delenv("PCGRL_OBSERVE_ROW22", raising=False)
+
+
+def test_maze3d_u8_observation_rows_per_thread(monkeypatch):
+    """The 3D maze's 14-wide last window axis: 14 (or 7) pixels per thread in the staged u8 writer against the float
+    writer and the 4-pixel path."""
+    for n in (3, 700):
+        env = _mk("minecraft_3D_maze", "narrow", (14, 14, 14), n, obs_window=(14, 14, 14), seed=n)
+        env.reset()
+        for i in range(3):
+            env.pos[:, i] = torch.randint(0, 14, (n,), device=env.device, dtype=torch.int32)
+        want = env.observe(dtype=torch.float32)
+        for mode in ("14", "7", "0"):
+            monkeypatch.setenv("PCGRL_OBSERVE_ROW14", mode)
+            assert torch.equal(env.observe(dtype=torch.uint8).float(), want), mode
+            assert torch.equal(env.observe(onehot=False)[..., 0].long(), want.argmax(dim=-1)), mode
+        monkeypatch.delenv("PCGRL_OBSERVE_ROW14", raising=False)
